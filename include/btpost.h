@@ -1,0 +1,159 @@
+/*
+ * btpost.h -- C ABI of libbtpost, the sm_100a post-processing + evaluation hot path for
+ * multitask bone-tumor YOLO heads.
+ *
+ * The reference (rafifmalikdzaki/Multitask-Bonetumor-yolo) has no FFI: the path is inline eager
+ * PyTorch inside `MultiTaskLitModel.validation_step` (src/running_main_v2.py:643-945) and the
+ * intended method `_prepare_det_outputs_for_metrics_and_logging` (src/evaluate_model.py:174-178).
+ * Each entry point below names the reference statements it replaces.  Everything is plain C:
+ * pointers, sizes, POD structs; no torch types.  All pointers are DEVICE pointers owned by the
+ * caller unless stated otherwise.  The library never allocates, never synchronises, keeps no
+ * mutable global state, and enqueues all work on the caller's stream (CUDA-graph capturable).
+ *
+ * Return value: 0 on success, a negative BT_ERR_* otherwise (btpost_error_string decodes it).
+ */
+#ifndef BTPOST_H_
+#define BTPOST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTPOST_VERSION 100 /* 0.1.0 */
+
+enum {
+    BT_OK = 0,
+    BT_ERR_BAD_ARG = -1,       /* null pointer / non-positive size / inconsistent params */
+    BT_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels implement */
+    BT_ERR_WORKSPACE = -3,     /* workspace smaller than btpost_workspace_bytes() */
+    BT_ERR_MISALIGNED = -4,    /* pointer not aligned as documented */
+    BT_ERR_CUDA = -5,          /* a CUDA launch failed; cudaGetLastError text via error_string */
+    BT_ERR_NCCL = -6
+};
+
+/* Number of COCO area ranges (all, small, medium, large) -- SURVEY.md A.3. */
+#define BT_NUM_AREA 4
+#define BT_MAX_IOU_THRS 16
+#define BT_MAX_CLASSES 16
+
+enum { BT_LAYOUT_L2 = 0, BT_LAYOUT_L1 = 1 };
+enum { BT_CLASS_AGNOSTIC = 0, BT_CLASS_AWARE = 1, BT_CLASS_OFFSET = 2 };
+enum { BT_GT_LITERAL = 0, BT_GT_INTENDED = 1 };
+enum { BT_MASK_U8 = 0, BT_MASK_F32 = 1 };
+
+/* Problem description.  Mirrors the reference's module constants CONF_TH / NMS_IOU / TOP_K
+ * (src/running_main_v2.py:51-53) and hparams img_size / nc_det / proto_ch / iou_match_thresh
+ * (src/running_main_v2.py:150-188). */
+typedef struct BtParams {
+    int32_t batch;            /* B images in this call                                        */
+    int32_t num_anchors;      /* N (8400 @640^2, 21504 @1024^2)                               */
+    int32_t nc;               /* detection classes (<= BT_MAX_CLASSES)                        */
+    int32_t nm;               /* mask coefficients / prototype channels (must be 32)          */
+    int32_t reg_max;          /* DFL bins (L1 layout only; 16)                                */
+    int32_t img_h, img_w;     /* network input size S                                         */
+    int32_t proto_h, proto_w; /* prototype resolution; must equal img/4                       */
+    int32_t layout;           /* BT_LAYOUT_L2: head [B,4+nc+nm,N]; BT_LAYOUT_L1: 3 raw maps   */
+    float conf_thres;         /* CONF_TH, strict >                                            */
+    double iou_thres;         /* NMS_IOU (torchvision takes a double)                         */
+    int32_t max_det;          /* TOP_K                                                        */
+    int32_t max_cand;         /* candidate capacity per image (Ultralytics max_nms); 0 => N   */
+    int32_t class_mode;       /* BT_CLASS_*; reference = agnostic                             */
+    float max_wh;             /* class offset for BT_CLASS_OFFSET (Ultralytics 7680)          */
+    int32_t clamp_boxes;      /* clamp_(0, img) after the filter (reference: 1)               */
+    int32_t gt_mode;          /* BT_GT_LITERAL reproduces cat(...).view(-1,4) as shipped      */
+    int32_t max_gt;           /* GT capacity per image (<= 32)                                */
+    int32_t num_gt_rows;      /* rows of det_boxes_gt [G_total, 6]                            */
+    float iou_match_thresh;   /* anchor<->GT confusion-matrix matching threshold (0.5)        */
+    int32_t crop;             /* crop instance masks to their box at prototype resolution     */
+    int32_t gt_mask_dtype;    /* BT_MASK_U8 or BT_MASK_F32 (reference dataset dtype)          */
+    float proj_bias;          /* bias of seg_proto_projector Conv2d(nm->1,k=1)                */
+    int32_t num_iou_thrs;     /* T (10 for mAP50-95, 1 for mAP50)                             */
+    double iou_thrs[BT_MAX_IOU_THRS]; /* float64(fp32 linspace(0.5,0.95,10))                  */
+    int32_t image_offset;     /* global index of image 0 (for sweep records / sharding)       */
+    int32_t reserved[7];
+} BtParams;
+
+/* Device buffers.  Inputs are read-only.  Any OUTPUT pointer may be NULL to skip that output
+ * unless marked required.  Shapes use B=batch, N=num_anchors, K=max_det, G=max_gt, S=img,
+ * A=BT_NUM_AREA, T=num_iou_thrs. */
+typedef struct BtIO {
+    /* ---- inputs ---- */
+    const float *head;          /* L2: [B, 4+nc+nm, N] fp32 (segment_preds_cat, main_modelv2.py:367) */
+    const float *maps[3];       /* L1: [B, 4*reg_max+nc, H_l, W_l], strides 8/16/32            */
+    const float *coeffs;        /* L1: mask coefficients [B, nm, N] (Segment `mc`)             */
+    const float *protos;        /* [B, nm, proto_h, proto_w] fp32, 16-byte aligned             */
+    const float *det_boxes_gt;  /* [num_gt_rows, 6] (batch_idx, cls, cx, cy, w, h) normalised  */
+    const void *masks_gt;       /* [B, 1, S, S] u8 or f32 {0,1}                                */
+    const float *proj_weight;   /* [nm] seg_proto_projector weight                             */
+    /* ---- detection outputs (required) ---- */
+    int32_t *det_count;         /* [B]                                                         */
+    float *dets;                /* [B, K, 6] xyxy, score, float(label)   (a5 `[K,6]`)          */
+    int64_t *det_keep;          /* [B, K] NMS keep indices into the filtered list (int64)      */
+    int32_t *det_anchor;        /* [B, K] original anchor index                                */
+    float *det_coeff;           /* [B, K, nm] mask coefficients of kept detections             */
+    int32_t *n_cand;            /* [B] candidates that passed the filter                       */
+    /* ---- GT outputs (required) ---- */
+    int32_t *gt_count;          /* [B]                                                         */
+    float *gt_boxes;            /* [B, G, 4] clamped xyxy (mAP copy, running_main_v2.py:849-865) */
+    float *gt_boxes_raw;        /* [B, G, 4] unclamped xyxy (loss copy, :409-433)              */
+    int32_t *gt_labels;         /* [B, G]                                                      */
+    /* ---- metric accumulators (ACCUMULATED: caller zeroes them at sweep start) ---- */
+    int64_t *cm;                /* [nc, nc] confusion counts [gt][pred]  (a10)                 */
+    int64_t *seg_cnt4;          /* [4] tp, fp, fn, tn of the projector mask (a8 i)             */
+    int64_t *uni_cnt4;          /* [4] same for the union of instance masks                    */
+    /* ---- per-batch metric outputs ---- */
+    int32_t *cm_pos;            /* [B] positive anchors per image                              */
+    int64_t *seg_img3;          /* [B, 3] inter, |P|, |G| for the projector mask (a8 ii,iii)   */
+    float *seg_dice;            /* [B]                                                         */
+    float *seg_iou;             /* [B]                                                         */
+    int64_t *uni_img3;          /* [B, 3] same for the union of instance masks                 */
+    float *uni_dice;            /* [B]                                                         */
+    float *uni_iou;             /* [B]                                                         */
+    int32_t *inst_area;         /* [B, K] pixels of each instance mask                         */
+    int32_t *inst_inter;        /* [B, K] pixels of each instance mask inside the GT mask      */
+    /* ---- optional dense outputs ---- */
+    uint8_t *seg_mask;          /* [B, S, S] projector mask (seg_preds, running_main_v2.py:703) */
+    float *seg_logits;          /* [B, S, S] upsampled projector logits (seg_logits_for_logging) */
+    uint8_t *uni_mask;          /* [B, S, S] union of instance masks                           */
+    uint8_t *inst_masks;        /* [B, K, S, S] every instance mask (Ultralytics process_mask) */
+    /* ---- COCO matching outputs (a9) ---- */
+    int32_t *dt_match;          /* [B, A, T, K] matched GT index + 1, 0 = unmatched            */
+    uint8_t *dt_ignore;         /* [B, A, T, K]                                                */
+    uint8_t *gt_ignore;         /* [B, A, G]                                                   */
+} BtIO;
+
+/* Library / build identification. */
+int btpost_version(void);
+const char *btpost_error_string(int code);
+/* Fills *bytes with the workspace size btpost_* calls need for `p` (256-byte aligned pointer). */
+int btpost_workspace_bytes(const BtParams *p, size_t *bytes);
+
+/* Stage entry points.  They share one workspace layout, so they may be called in sequence on
+ * the same stream (decode_filter -> nms_match -> masks) or through btpost_run. */
+
+/* a2+a3+a6+a10: box decode, max/argmax over classes, strict conf filter, clamp, ordered
+ * compaction; GT prep; anchor<->GT confusion-matrix matching.
+ * Replaces src/running_main_v2.py:743-795, :842-882, :402-449,:476-486 (+ batch_bbox_iou :68-94). */
+int btpost_decode_filter(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+
+/* a4+a5+a9(match): stable descending sort, greedy NMS with early exit at max_det (keeps are
+ * bit-exact against torchvision.ops.nms(...)[:TOP_K]), gather of kept detections, COCOeval
+ * evaluateImg matching.  Replaces src/running_main_v2.py:817-839 and the per-image part of
+ * torchmetrics MeanAveragePrecision (:884-892). */
+int btpost_nms_match(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+
+/* a7+a8: projector mask (Conv2d nm->1, bilinear x4, sigmoid>0.5) and instance masks
+ * (coeff . protos, crop, bilinear x4, sigmoid>0.5), pixel counters, per-image Dice / IoU.
+ * Replaces src/running_main_v2.py:689-713, src/test_model.py:15-23,80-89. */
+int btpost_masks(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+
+/* Whole hot path for one batch: the three stages above, back to back on `stream`. */
+int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTPOST_H_ */

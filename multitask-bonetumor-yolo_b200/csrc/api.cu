@@ -1,0 +1,137 @@
+// C ABI of libbtpost (declared in include/btpost.h): argument validation + stage dispatch.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace bt {
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_params(const BtParams *p, const BtIO *io) {
+    if (!p || !io) return BT_ERR_BAD_ARG;
+    if (p->batch <= 0 || p->num_anchors <= 0 || p->nc <= 0 || p->max_det <= 0) return BT_ERR_BAD_ARG;
+    if (p->nc > BT_MAX_CLASSES || p->nm != 32) return BT_ERR_UNSUPPORTED;
+    if (p->max_gt <= 0 || p->max_gt > 32) return BT_ERR_UNSUPPORTED;
+    if (p->max_det > 4096) return BT_ERR_UNSUPPORTED;
+    if (p->img_h <= 0 || p->img_w <= 0) return BT_ERR_BAD_ARG;
+    if (p->proto_h * 4 != p->img_h || p->proto_w * 4 != p->img_w) return BT_ERR_UNSUPPORTED;
+    if (p->img_w % 32 != 0 || p->proto_h < 2 || p->proto_w < 2) return BT_ERR_UNSUPPORTED;
+    if (p->num_iou_thrs < 0 || p->num_iou_thrs > BT_MAX_IOU_THRS) return BT_ERR_BAD_ARG;
+    if (p->num_gt_rows < 0) return BT_ERR_BAD_ARG;
+    if (!(p->iou_thres == p->iou_thres)) return BT_ERR_BAD_ARG;
+    if (p->layout == BT_LAYOUT_L1) {
+        if (p->reg_max <= 0 || p->reg_max > 32) return BT_ERR_UNSUPPORTED;
+        if (p->img_w % 32 != 0 || p->img_h % 32 != 0) return BT_ERR_UNSUPPORTED;
+        int n = 0;
+        for (int s = 8; s <= 32; s *= 2) n += (p->img_w / s) * (p->img_h / s);
+        if (n != p->num_anchors) return BT_ERR_BAD_ARG;
+    } else if (p->layout != BT_LAYOUT_L2) {
+        return BT_ERR_BAD_ARG;
+    }
+    return BT_OK;
+}
+
+static int check_ws(const BtParams *p, void *ws, size_t ws_bytes) {
+    if (!ws) return BT_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(ws) & 255) return BT_ERR_MISALIGNED;
+    if (ws_bytes < carve(p, nullptr).bytes) return BT_ERR_WORKSPACE;
+    return BT_OK;
+}
+
+static int check_stage1(const BtParams *p, const BtIO *io) {
+    if (p->layout == BT_LAYOUT_L2) {
+        if (!io->head) return BT_ERR_BAD_ARG;
+    } else {
+        if (!io->maps[0] || !io->maps[1] || !io->maps[2]) return BT_ERR_BAD_ARG;
+    }
+    if (p->num_gt_rows > 0 && !io->det_boxes_gt) return BT_ERR_BAD_ARG;
+    if (!io->n_cand || !io->gt_count || !io->gt_boxes || !io->gt_boxes_raw || !io->gt_labels || !io->cm || !io->cm_pos)
+        return BT_ERR_BAD_ARG;
+    return BT_OK;
+}
+
+static int check_stage2(const BtParams *p, const BtIO *io) {
+    if (!io->n_cand || !io->det_count || !io->dets || !io->det_keep || !io->det_anchor || !io->det_coeff)
+        return BT_ERR_BAD_ARG;
+    if (p->layout == BT_LAYOUT_L2 ? !io->head : !io->coeffs) return BT_ERR_BAD_ARG;
+    if (io->dt_match && (!io->gt_count || !io->gt_boxes || !io->gt_labels || p->num_iou_thrs <= 0)) return BT_ERR_BAD_ARG;
+    return BT_OK;
+}
+
+static int check_stage3(const BtParams *p, const BtIO *io) {
+    (void)p;
+    if (!io->protos || !io->masks_gt || !io->proj_weight || !io->dets || !io->det_count || !io->det_coeff)
+        return BT_ERR_BAD_ARG;
+    if (!aligned16(io->protos) || !aligned16(io->masks_gt)) return BT_ERR_MISALIGNED;
+    if ((io->seg_mask && !aligned16(io->seg_mask)) || (io->uni_mask && !aligned16(io->uni_mask))) return BT_ERR_MISALIGNED;
+    return BT_OK;
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+extern "C" {
+
+int btpost_version(void) { return BTPOST_VERSION; }
+
+const char *btpost_error_string(int code) {
+    switch (code) {
+        case BT_OK: return "ok";
+        case BT_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or inconsistent parameters)";
+        case BT_ERR_UNSUPPORTED: return "unsupported shape (need nm=32, proto=img/4, img_w%32==0, nc<=16, max_gt<=32)";
+        case BT_ERR_WORKSPACE: return "workspace too small (see btpost_workspace_bytes)";
+        case BT_ERR_MISALIGNED: return "misaligned pointer (workspace 256 B; protos/masks 16 B)";
+        case BT_ERR_CUDA: return "CUDA launch failed";
+        case BT_ERR_NCCL: return "NCCL call failed";
+        default: return "unknown error";
+    }
+}
+
+int btpost_workspace_bytes(const BtParams *p, size_t *bytes) {
+    if (!p || !bytes) return BT_ERR_BAD_ARG;
+    if (p->batch <= 0 || p->num_anchors <= 0) return BT_ERR_BAD_ARG;
+    *bytes = carve(p, nullptr).bytes;
+    return BT_OK;
+}
+
+int btpost_decode_filter(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_params(p, io);
+    if (rc == BT_OK) rc = check_ws(p, ws, ws_bytes);
+    if (rc == BT_OK) rc = check_stage1(p, io);
+    if (rc != BT_OK) return rc;
+    return launch_decode_filter(*p, *io, carve(p, ws), static_cast<cudaStream_t>(stream));
+}
+
+int btpost_nms_match(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_params(p, io);
+    if (rc == BT_OK) rc = check_ws(p, ws, ws_bytes);
+    if (rc == BT_OK) rc = check_stage2(p, io);
+    if (rc != BT_OK) return rc;
+    return launch_nms_match(*p, *io, carve(p, ws), static_cast<cudaStream_t>(stream));
+}
+
+int btpost_masks(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_params(p, io);
+    if (rc == BT_OK) rc = check_ws(p, ws, ws_bytes);
+    if (rc == BT_OK) rc = check_stage3(p, io);
+    if (rc != BT_OK) return rc;
+    return launch_masks(*p, *io, carve(p, ws), static_cast<cudaStream_t>(stream));
+}
+
+int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_params(p, io);
+    if (rc == BT_OK) rc = check_ws(p, ws, ws_bytes);
+    if (rc == BT_OK) rc = check_stage1(p, io);
+    if (rc == BT_OK) rc = check_stage2(p, io);
+    if (rc == BT_OK) rc = check_stage3(p, io);
+    if (rc != BT_OK) return rc;
+    Workspace w = carve(p, ws);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = launch_decode_filter(*p, *io, w, s);
+    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s);
+    if (rc == BT_OK) rc = launch_masks(*p, *io, w, s);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// Kernel 1: fused box decode + class max/argmax + strict confidence filter + clamp + ORDERED
+// stream compaction, with GT preparation and the anchor<->GT confusion-matrix matching riding on
+// the same pass over the head tensor.
+//
+// Reference statements replaced (paths under /root/reference/src):
+//   decode      running_main_v2.py:743-775 (L1) / Ultralytics xywh->xyxy on segment_preds_cat (L2,
+//               main_modelv2.py:367-375)
+//   filter      running_main_v2.py:788-795   (max over classes, > CONF_TH strict, clamp_ after gather)
+//   GT prep     running_main_v2.py:842-882 (clamped mAP copy) and :403-433 (unclamped loss copy)
+//   CM match    running_main_v2.py:435-449,476-486 + batch_bbox_iou :68-94
+//
+// B200 mapping: one thread-block CLUSTER of 8 CTAs per image (grid 8 x B).  Each CTA owns a
+// contiguous eighth of the anchors, reads the 4+nc box/score rows with 16-byte vector loads
+// (coalesced: the head is [C, N] row-major per image), counts its survivors, and the eight counts
+// are exchanged through distributed shared memory so that every CTA knows its output offset
+// without a second kernel, global atomics or spin-waits.  The candidate list therefore comes out
+// in anchor order, which is what makes NMS keep indices comparable with the reference's.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bt {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_CLUSTER = 8;
+constexpr int K1_MAX_GT = 32;
+
+struct K1Params {
+    const float *head;   // L2
+    const float *maps[3];  // L1
+    int lvl_off[4];      // anchor offset of each level (L1)
+    int lvl_w[3];
+    float lvl_stride[3];
+    int reg_max;
+    int N, nc, nm, C;    // C = rows per image in the head (4+nc+nm) / channels of a map (L1)
+    float conf;
+    int clamp;
+    float img_w, img_h;
+    int cap;
+    const float *gt_rows;
+    int n_rows, gt_mode, max_gt;
+    float cm_thr;
+    float4 *cand_box;
+    float *cand_score;
+    int32_t *cand_label, *cand_anchor, *n_cand;
+    int32_t *gt_count;
+    float *gt_boxes, *gt_boxes_raw;
+    int32_t *gt_labels;
+    unsigned long long *cm;
+    int32_t *cm_pos;
+};
+
+// Exclusive prefix of `c` over the block in thread order; `total` = block sum.
+__device__ __forceinline__ int block_excl_scan(int c, int &total, int *s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < K1_WARPS; ++w) {
+        int v = s_warp[w];
+        if (w < wid) off += v;
+        tot += v;
+    }
+    __syncthreads();
+    total = tot;
+    return off + incl - c;
+}
+
+struct Decoded {
+    float x1, y1, x2, y2;  // raw (unclamped) xyxy
+    float score;
+    int label;
+};
+
+// ---- L2 decoder: rows 0..3 = cx, cy, w, h in pixels; rows 4..4+nc = class scores.
+template <int VEC>
+struct L2Decoder {
+    const float *img;  // head + b*C*N
+    int N, nc;
+    __device__ __forceinline__ void load_row(int row, int n, float (&v)[VEC]) const {
+        const float *p = img + (size_t)row * N + n;
+        if (VEC == 4) {
+            float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+            v[0] = __ldg(p);
+        }
+    }
+    __device__ __forceinline__ void scores(int n, float (&best)[VEC], int (&lab)[VEC]) const {
+        load_row(4, n, best);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) lab[i] = 0;
+        for (int c = 1; c < nc; ++c) {
+            float s[VEC];
+            load_row(4 + c, n, s);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                if (s[i] > best[i]) { best[i] = s[i]; lab[i] = c; }
+        }
+    }
+    __device__ __forceinline__ void boxes(int n, float (&x1)[VEC], float (&y1)[VEC], float (&x2)[VEC],
+                                          float (&y2)[VEC]) const {
+        float cx[VEC], cy[VEC], w[VEC], h[VEC];
+        load_row(0, n, cx); load_row(1, n, cy); load_row(2, n, w); load_row(3, n, h);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float hw = __fmul_rn(w[i], 0.5f), hh = __fmul_rn(h[i], 0.5f);
+            x1[i] = __fsub_rn(cx[i], hw); y1[i] = __fsub_rn(cy[i], hh);
+            x2[i] = __fadd_rn(cx[i], hw); y2[i] = __fadd_rn(cy[i], hh);
+        }
+    }
+};
+
+// exp shared bit-for-bit with oracle/btpost_oracle.c::bto_expf (Cody-Waite + degree-6 polynomial,
+// fma/mul/add only).
+__device__ __forceinline__ float bt_expf(float x) {
+    if (x < -87.0f) return 0.0f;
+    float t = __fmul_rn(x, 1.4426950408889634f);
+    float n = rintf(t);
+    float r = __fmaf_rn(n, -0.693145751953125f, x);
+    r = __fmaf_rn(n, -1.428606765330187e-06f, r);
+    float p = 1.3888889225e-03f;
+    p = __fmaf_rn(p, r, 8.3333337680e-03f);
+    p = __fmaf_rn(p, r, 4.1666667908e-02f);
+    p = __fmaf_rn(p, r, 1.6666667163e-01f);
+    p = __fmaf_rn(p, r, 0.5f);
+    p = __fmaf_rn(p, r, 1.0f);
+    p = __fmaf_rn(p, r, 1.0f);
+    int e = (int)n;
+    return __int_as_float(__float_as_int(p) + (e << 23));
+}
+
+// ---- L1 decoder: three raw maps [4*R+nc, H, W]; DFL softmax expectation, anchors (x+.5,y+.5),
+// stride = img/W, class score = sigmoid(logit)  (running_main_v2.py:743-775, dist2bbox :97-107).
+struct L1Decoder {
+    const float *map[3];  // already offset to image b
+    int off[4], w[3];
+    float stride[3];
+    int R, nc;
+    __device__ __forceinline__ int level(int n) const { return n >= off[2] ? 2 : (n >= off[1] ? 1 : 0); }
+    __device__ __forceinline__ void scores(int n, float (&best)[1], int (&lab)[1]) const {
+        int l = level(n);
+        int HW = off[l + 1] - off[l], pos = n - off[l];
+        const float *p = map[l] + (size_t)(4 * R) * HW + pos;
+        float b = -1.0f; int bi = 0;
+        for (int c = 0; c < nc; ++c) {
+            float lg = __ldg(p + (size_t)c * HW);
+            float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, bt_expf(-lg)));
+            if (c == 0 || s > b) { b = s; bi = c; }
+        }
+        best[0] = b; lab[0] = bi;
+    }
+    __device__ __forceinline__ void boxes(int n, float (&x1)[1], float (&y1)[1], float (&x2)[1], float (&y2)[1]) const {
+        int l = level(n);
+        int HW = off[l + 1] - off[l], pos = n - off[l];
+        int W = w[l];
+        int y = pos / W, x = pos - y * W;
+        float st = stride[l];
+        float d[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float *p = map[l] + (size_t)(s * R) * HW + pos;
+            float m = __ldg(p);
+            for (int k = 1; k < R; ++k) { float v = __ldg(p + (size_t)k * HW); if (v > m) m = v; }
+            float sum = 0.0f, acc = 0.0f;
+            for (int k = 0; k < R; ++k) {
+                float e = bt_expf(__fsub_rn(__ldg(p + (size_t)k * HW), m));
+                sum = __fadd_rn(sum, e);
+                acc = __fmaf_rn(e, (float)k, acc);
+            }
+            d[s] = __fdiv_rn(acc, sum);
+        }
+        float ax = __fmul_rn(__fadd_rn((float)x, 0.5f), st), ay = __fmul_rn(__fadd_rn((float)y, 0.5f), st);
+        x1[0] = __fsub_rn(ax, __fmul_rn(d[0], st));
+        y1[0] = __fsub_rn(ay, __fmul_rn(d[1], st));
+        x2[0] = __fadd_rn(ax, __fmul_rn(d[2], st));
+        y2[0] = __fadd_rn(ay, __fmul_rn(d[3], st));
+    }
+};
+
+template <int VEC, class Dec>
+__device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    __shared__ int s_warp[K1_WARPS];
+    __shared__ int s_ex;                 // this CTA's survivor count, read by peers through DSMEM
+    __shared__ float s_coord[K1_MAX_GT][4];
+    __shared__ float s_gtraw[K1_MAX_GT * 4];
+    __shared__ int s_gl[K1_MAX_GT];
+    __shared__ int s_G;
+    __shared__ int s_cm[BT_MAX_CLASSES * BT_MAX_CLASSES];
+    __shared__ int s_npos;
+
+    for (int i = tid; i < BT_MAX_CLASSES * BT_MAX_CLASSES; i += K1_THREADS) s_cm[i] = 0;
+    if (tid == 0) s_npos = 0;
+
+    // ---- GT prep: ordered gather of this image's rows, then the reference's cat/view layout.
+    {
+        const float S = P.img_w;  // reference multiplies every coordinate by the scalar img_size
+        int base = 0;
+        for (int r0 = 0; r0 < P.n_rows; r0 += K1_THREADS) {
+            int r = r0 + tid;
+            bool hit = false;
+            float row[6];
+            if (r < P.n_rows) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) row[k] = __ldg(P.gt_rows + (size_t)r * 6 + k);
+                hit = (row[0] == (float)b);
+            }
+            int tot;
+            int pos = base + block_excl_scan(hit ? 1 : 0, tot, s_warp);
+            if (hit && pos < P.max_gt) {
+                float cx = row[2], cy = row[3], w = row[4], h = row[5];
+                float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+                s_coord[pos][0] = __fmul_rn(__fsub_rn(cx, hw), S);
+                s_coord[pos][1] = __fmul_rn(__fsub_rn(cy, hh), S);
+                s_coord[pos][2] = __fmul_rn(__fadd_rn(cx, hw), S);
+                s_coord[pos][3] = __fmul_rn(__fadd_rn(cy, hh), S);
+                s_gl[pos] = (int)row[1];
+            }
+            base += tot;
+        }
+        if (tid == 0) s_G = base < P.max_gt ? base : P.max_gt;
+        __syncthreads();
+        const int G = s_G;
+        for (int i = tid; i < 4 * G; i += K1_THREADS) {
+            float v = (P.gt_mode == BT_GT_LITERAL) ? s_coord[i % G][i / G] : s_coord[i / 4][i % 4];
+            s_gtraw[i] = v;
+            if (rank == 0) {
+                P.gt_boxes_raw[(size_t)b * P.max_gt * 4 + i] = v;
+                P.gt_boxes[(size_t)b * P.max_gt * 4 + i] = fminf(fmaxf(v, 0.0f), S);
+            }
+        }
+        if (rank == 0) {
+            for (int i = tid; i < G; i += K1_THREADS) P.gt_labels[(size_t)b * P.max_gt + i] = s_gl[i];
+            if (tid == 0) { P.gt_count[b] = G; P.cm_pos[b] = 0; }
+        }
+        __syncthreads();
+    }
+    const int G = s_G;
+
+    // ---- anchor range of this CTA (in groups of VEC anchors)
+    const int groups = (P.N + VEC - 1) / VEC;
+    const int gp = (groups + K1_CLUSTER - 1) / K1_CLUSTER;
+    const int g0 = rank * gp, g1 = min(groups, g0 + gp);
+
+    // ---- pass 1: count survivors
+    int cnt = 0;
+    for (int g = g0 + tid; g < g1; g += K1_THREADS) {
+        float best[VEC]; int lab[VEC];
+        dec.scores(g * VEC, best, lab);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) cnt += (best[i] > P.conf) ? 1 : 0;
+    }
+    int my_total;
+    block_excl_scan(cnt, my_total, s_warp);
+    if (tid == 0) s_ex = my_total;
+    cluster.sync();
+    int base = 0, all = 0;
+    for (int r = 0; r < K1_CLUSTER; ++r) {
+        int v = *cluster.map_shared_rank(&s_ex, r);
+        if (r < rank) base += v;
+        all += v;
+    }
+    if (rank == 0 && tid == 0) P.n_cand[b] = all < P.cap ? all : P.cap;
+
+    // ---- pass 2: decode, CM matching on the raw boxes, ordered write of the survivors
+    int npos_thread = 0;
+    for (int gbase = g0; gbase < g1; gbase += K1_THREADS) {
+        const int g = gbase + tid;
+        const bool active = g < g1;
+        float best[VEC], x1[VEC], y1[VEC], x2[VEC], y2[VEC];
+        int lab[VEC];
+        int c = 0;
+        unsigned flags = 0;
+        if (active) {
+            dec.scores(g * VEC, best, lab);
+            dec.boxes(g * VEC, x1, y1, x2, y2);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                if (best[i] > P.conf) { flags |= 1u << i; ++c; }
+                if (G > 0) {
+                    // batch_bbox_iou (running_main_v2.py:68-94) against the unclamped GT copy
+                    float a1 = __fmul_rn(__fsub_rn(x2[i], x1[i]), __fsub_rn(y2[i], y1[i]));
+                    float bi = 0.0f; int bg = 0;
+                    for (int q = 0; q < G; ++q) {
+                        float qx1 = s_gtraw[4 * q], qy1 = s_gtraw[4 * q + 1], qx2 = s_gtraw[4 * q + 2], qy2 = s_gtraw[4 * q + 3];
+                        float ix1 = fmaxf(x1[i], qx1), iy1 = fmaxf(y1[i], qy1);
+                        float ix2 = fminf(x2[i], qx2), iy2 = fminf(y2[i], qy2);
+                        float iw = __fsub_rn(ix2, ix1); iw = iw < 0.0f ? 0.0f : iw;
+                        float ih = __fsub_rn(iy2, iy1); ih = ih < 0.0f ? 0.0f : ih;
+                        float inter = __fmul_rn(iw, ih);
+                        float a2 = __fmul_rn(__fsub_rn(qx2, qx1), __fsub_rn(qy2, qy1));
+                        float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
+                        float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-7f));
+                        if (q == 0 || iou > bi) { bi = iou; bg = q; }
+                    }
+                    if (bi > P.cm_thr) {
+                        int gc = s_gl[bg], pc = lab[i];
+                        if (gc >= 0 && gc < P.nc && pc >= 0 && pc < P.nc) atomicAdd(&s_cm[gc * P.nc + pc], 1);
+                        ++npos_thread;
+                    }
+                }
+            }
+        }
+        int tot;
+        int pos = base + block_excl_scan(c, tot, s_warp);
+        if (flags) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                if (!(flags & (1u << i))) continue;
+                if (pos < P.cap) {
+                    float bx1 = x1[i], by1 = y1[i], bx2 = x2[i], by2 = y2[i];
+                    if (P.clamp) {
+                        bx1 = fminf(fmaxf(bx1, 0.0f), P.img_w); bx2 = fminf(fmaxf(bx2, 0.0f), P.img_w);
+                        by1 = fminf(fmaxf(by1, 0.0f), P.img_h); by2 = fminf(fmaxf(by2, 0.0f), P.img_h);
+                    }
+                    size_t o = (size_t)b * P.cap + pos;
+                    P.cand_box[o] = make_float4(bx1, by1, bx2, by2);
+                    P.cand_score[o] = best[i];
+                    P.cand_label[o] = lab[i];
+                    P.cand_anchor[o] = g * VEC + i;
+                }
+                ++pos;
+            }
+        }
+        base += tot;
+    }
+    // ---- flush confusion-matrix counts (integers: order-independent)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) npos_thread += __shfl_down_sync(0xffffffffu, npos_thread, d);
+    if (lane == 0 && npos_thread) atomicAdd(&s_npos, npos_thread);
+    __syncthreads();
+    for (int i = tid; i < P.nc * P.nc; i += K1_THREADS)
+        if (s_cm[i]) atomicAdd(&P.cm[i], (unsigned long long)s_cm[i]);
+    if (tid == 0 && s_npos) atomicAdd(&P.cm_pos[b], s_npos);
+    cluster.sync();  // peers may still be reading s_ex through DSMEM
+}
+
+template <int VEC>
+__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_THREADS)
+decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
+    const int b = blockIdx.y;
+    L2Decoder<VEC> dec{P.head + (size_t)b * P.C * P.N, P.N, P.nc};
+    k1_body<VEC>(P, dec, b);
+}
+
+__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_THREADS)
+decode_filter_l1_kernel(const __grid_constant__ K1Params P) {
+    const int b = blockIdx.y;
+    L1Decoder dec;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        int HW = P.lvl_off[l + 1] - P.lvl_off[l];
+        dec.map[l] = P.maps[l] + (size_t)b * P.C * HW;
+        dec.off[l] = P.lvl_off[l];
+        dec.w[l] = P.lvl_w[l];
+        dec.stride[l] = P.lvl_stride[l];
+    }
+    dec.off[3] = P.lvl_off[3];
+    dec.R = P.reg_max;
+    dec.nc = P.nc;
+    k1_body<1>(P, dec, b);
+}
+
+int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
+    K1Params P{};
+    P.N = p.num_anchors; P.nc = p.nc; P.nm = p.nm;
+    P.conf = p.conf_thres; P.clamp = p.clamp_boxes;
+    P.img_w = (float)p.img_w; P.img_h = (float)p.img_h;
+    P.cap = cand_capacity(&p);
+    P.gt_rows = io.det_boxes_gt; P.n_rows = io.det_boxes_gt ? p.num_gt_rows : 0;
+    P.gt_mode = p.gt_mode; P.max_gt = p.max_gt; P.cm_thr = p.iou_match_thresh;
+    P.cand_box = w.cand_box; P.cand_score = w.cand_score; P.cand_label = w.cand_label;
+    P.cand_anchor = w.cand_anchor; P.n_cand = io.n_cand;
+    P.gt_count = io.gt_count; P.gt_boxes = io.gt_boxes; P.gt_boxes_raw = io.gt_boxes_raw;
+    P.gt_labels = io.gt_labels;
+    P.cm = reinterpret_cast<unsigned long long *>(io.cm); P.cm_pos = io.cm_pos;
+    dim3 grid(K1_CLUSTER, p.batch), block(K1_THREADS);
+    if (p.layout == BT_LAYOUT_L2) {
+        P.head = io.head; P.C = 4 + p.nc + p.nm;
+        bool vec = (p.num_anchors % 4 == 0) && ((reinterpret_cast<uintptr_t>(io.head) & 15) == 0);
+        if (vec) decode_filter_l2_kernel<4><<<grid, block, 0, s>>>(P);
+        else decode_filter_l2_kernel<1><<<grid, block, 0, s>>>(P);
+    } else {
+        P.C = 4 * p.reg_max + p.nc; P.reg_max = p.reg_max;
+        int off = 0;
+        const int strides[3] = {8, 16, 32};
+        for (int l = 0; l < 3; ++l) {
+            int W = p.img_w / strides[l], H = p.img_h / strides[l];
+            P.maps[l] = io.maps[l];
+            P.lvl_off[l] = off; P.lvl_w[l] = W;
+            P.lvl_stride[l] = (float)p.img_w / (float)W;  // running_main_v2.py:726
+            off += W * H;
+        }
+        P.lvl_off[3] = off;
+        decode_filter_l1_kernel<<<grid, block, 0, s>>>(P);
+    }
+    return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
+}
+
+}  // namespace bt

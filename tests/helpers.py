@@ -1,0 +1,72 @@
+"""Shared test helpers: run the CUDA library and the CPU oracle on the same synthetic batch."""
+import numpy as np
+import torch
+
+from btpost import PostConfig, PostProcessor, _lib, synth
+from oracle import oracle
+
+
+def to_dev(batch, dev, gt_f32=False):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    m = batch["masks_gt"].astype(np.float32) if gt_f32 else batch["masks_gt"]
+    return dict(head=t(batch["head"]), protos=t(batch["protos"]), det_boxes_gt=t(batch["det_boxes_gt"]),
+                masks_gt=t(m), proj_weight=t(batch["proj_weight"]), proj_bias=float(batch["proj_bias"]))
+
+
+def run_cuda(batch, dev="cuda:0", gt_f32=False, **kw):
+    scfg = batch["cfg"]
+    cfg = PostConfig(batch=scfg.batch, img_size=scfg.img_size, nc=scfg.nc, nm=scfg.nm,
+                     conf_thres=kw.get("conf_thres", 0.05), iou_thres=kw.get("iou_thres", 0.6),
+                     max_det=kw.get("max_det", 300), max_cand=kw.get("max_cand", 0),
+                     class_mode=kw.get("class_mode", 0), clamp_boxes=bool(kw.get("clamp", 1)),
+                     gt_mode=kw.get("gt_mode", 0), crop=bool(kw.get("crop", 1)),
+                     iou_match_thresh=kw.get("iou_match_thresh", 0.5),
+                     gt_mask_dtype=_lib.MASK_F32 if gt_f32 else _lib.MASK_U8,
+                     with_seg_mask=True, with_seg_logits=True, with_uni_mask=True, with_coco=True)
+    pp = PostProcessor(cfg, dev)
+    d = to_dev(batch, dev, gt_f32)
+    out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}, pp
+
+
+def make(batch=2, img_size=640, seed=20261, l1=False, image_offset=0):
+    cfg = synth.SynthConfig(batch=batch, img_size=img_size, seed=seed, image_offset=image_offset)
+    b = synth.make_batch(cfg, l1=l1)
+    b["cfg"] = cfg
+    return b
+
+
+def assert_same(got, ref, B, max_det, check_masks=True):
+    """Bit-exact comparison of every output the oracle produces."""
+    np.testing.assert_array_equal(got["n_cand"], ref["n_cand"])
+    np.testing.assert_array_equal(got["det_count"], ref["det_count"])
+    np.testing.assert_array_equal(got["det_keep"], ref["det_keep"].astype(np.int64))
+    np.testing.assert_array_equal(got["det_anchor"], ref["det_anchor"])
+    assert got["dets"].tobytes() == ref["dets"].tobytes()
+    assert got["det_coeff"].tobytes() == ref["det_coeff"].tobytes()
+    np.testing.assert_array_equal(got["gt_count"], ref["gt_count"])
+    assert got["gt_boxes"].tobytes() == ref["gt_boxes"].tobytes()
+    assert got["gt_boxes_raw"].tobytes() == ref["gt_boxes_raw"].tobytes()
+    np.testing.assert_array_equal(got["gt_labels"], ref["gt_labels"])
+    np.testing.assert_array_equal(got["cm"], ref["cm"])
+    np.testing.assert_array_equal(got["cm_pos"], ref["cm_pos"])
+    np.testing.assert_array_equal(got["seg_cnt4"], ref["seg_cnt4"])
+    np.testing.assert_array_equal(got["seg_img3"], ref["seg_img3"])
+    np.testing.assert_allclose(got["seg_dice"], ref["seg_dice"], rtol=1e-5)   # north star: 1e-5 relative on floats
+    np.testing.assert_allclose(got["seg_iou"], ref["seg_iou"], rtol=1e-5)
+    if check_masks:
+        np.testing.assert_array_equal(got["seg_mask"], ref["seg_mask"])
+        assert got["seg_logits"].tobytes() == ref["seg_logits"].tobytes()
+    if ref["inst_masks"]:
+        np.testing.assert_array_equal(got["inst_area"], ref["inst_area"])
+        np.testing.assert_array_equal(got["inst_inter"], ref["inst_inter"])
+        np.testing.assert_array_equal(got["uni_img3"], ref["uni_img3"])
+        np.testing.assert_array_equal(got["uni_cnt4"], ref["uni_cnt4"])
+        np.testing.assert_allclose(got["uni_dice"], ref["uni_dice"], rtol=1e-5)
+        np.testing.assert_allclose(got["uni_iou"], ref["uni_iou"], rtol=1e-5)
+        if check_masks:
+            np.testing.assert_array_equal(got["uni_mask"], ref["uni_mask"])
+    np.testing.assert_array_equal(got["dt_match"], ref["dt_match"])
+    np.testing.assert_array_equal(got["dt_ignore"], ref["dt_ignore"])
+    np.testing.assert_array_equal(got["gt_ignore"], ref["gt_ignore"])

@@ -1,0 +1,68 @@
+"""-m gpu: the CUDA library (through the C ABI) against the CPU oracle on identical seeded inputs.
+Integer / index / byte outputs are compared bit-exactly; fp32 boxes, scores, coefficients and logits
+are compared as raw bytes (the kernels reproduce the oracle's rounding sequence); Dice / IoU floats
+within 1e-5 relative (north-star tolerance)."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),                                         # reference defaults (CONF_TH .05, NMS_IOU .6, TOP_K 300)
+    dict(max_det=100),                              # v3 TOP_K
+    dict(class_mode=1), dict(class_mode=2),         # class-aware variants
+    dict(gt_mode=1), dict(crop=0, max_det=20), dict(clamp=0),
+    dict(conf_thres=0.999),                         # nothing passes the filter
+    dict(conf_thres=0.5, iou_thres=0.3),
+    dict(max_cand=500),
+])
+def test_pipeline_matches_oracle_640(kw):
+    batch = helpers.make(batch=2, img_size=640)
+    ref = oracle.run_pipeline(batch, **kw)
+    got, _ = helpers.run_cuda(batch, **kw)
+    helpers.assert_same(got, ref, 2, kw.get("max_det", 300))
+
+
+def test_pipeline_dense_candidates():
+    """conf 0.001: every anchor is a candidate (8400 per image) -> exercises the global-memory sort."""
+    batch = helpers.make(batch=2, img_size=640, seed=20264)
+    kw = dict(conf_thres=0.001, max_det=300)
+    ref = oracle.run_pipeline(batch, with_instances=False, **kw)
+    got, _ = helpers.run_cuda(batch, **kw)
+    assert int(ref["n_cand"].min()) > 8000
+    helpers.assert_same(got, ref, 2, 300)
+
+
+def test_pipeline_1024():
+    batch = helpers.make(batch=1, img_size=1024, seed=20263)
+    kw = dict(max_det=50)
+    ref = oracle.run_pipeline(batch, img_size=1024, **kw)
+    got, _ = helpers.run_cuda(batch, **kw)
+    helpers.assert_same(got, ref, 1, 50)
+
+
+def test_gt_mask_f32():
+    batch = helpers.make(batch=2, img_size=640, seed=7)
+    kw = dict(max_det=30)
+    ref = oracle.run_pipeline(batch, **kw)
+    got, _ = helpers.run_cuda(batch, gt_f32=True, **kw)
+    helpers.assert_same(got, ref, 2, 30)
+
+
+def test_metrics_accumulate_and_reset():
+    batch = helpers.make(batch=2, img_size=640, seed=11)
+    kw = dict(max_det=20)
+    ref = oracle.run_pipeline(batch, **kw)
+    got, pp = helpers.run_cuda(batch, **kw)
+    d = helpers.to_dev(batch, "cuda:0")
+    out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    np.testing.assert_array_equal(out["cm"].cpu().numpy(), 2 * ref["cm"])
+    np.testing.assert_array_equal(out["seg_cnt4"].cpu().numpy(), 2 * ref["seg_cnt4"])
+    np.testing.assert_array_equal(out["seg_img3"].cpu().numpy(), ref["seg_img3"])       # per-batch, not accumulated
+    np.testing.assert_array_equal(out["inst_area"].cpu().numpy(), ref["inst_area"])
+    pp.reset_metrics()
+    assert int(out["cm"].sum()) == 0
