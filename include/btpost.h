@@ -23,6 +23,7 @@ extern "C" {
 #endif
 
 #define BTPOST_VERSION 100 /* 0.1.0 */
+#define BTPOST_API __attribute__((visibility("default")))
 
 enum {
     BT_OK = 0,
@@ -126,10 +127,10 @@ typedef struct BtIO {
 } BtIO;
 
 /* Library / build identification. */
-int btpost_version(void);
-const char *btpost_error_string(int code);
+BTPOST_API int btpost_version(void);
+BTPOST_API const char *btpost_error_string(int code);
 /* Fills *bytes with the workspace size btpost_* calls need for `p` (256-byte aligned pointer). */
-int btpost_workspace_bytes(const BtParams *p, size_t *bytes);
+BTPOST_API int btpost_workspace_bytes(const BtParams *p, size_t *bytes);
 
 /* Stage entry points.  They share one workspace layout, so they may be called in sequence on
  * the same stream (decode_filter -> nms_match -> masks) or through btpost_run. */
@@ -137,21 +138,21 @@ int btpost_workspace_bytes(const BtParams *p, size_t *bytes);
 /* a2+a3+a6+a10: box decode, max/argmax over classes, strict conf filter, clamp, ordered
  * compaction; GT prep; anchor<->GT confusion-matrix matching.
  * Replaces src/running_main_v2.py:743-795, :842-882, :402-449,:476-486 (+ batch_bbox_iou :68-94). */
-int btpost_decode_filter(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+BTPOST_API int btpost_decode_filter(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
 /* a4+a5+a9(match): stable descending sort, greedy NMS with early exit at max_det (keeps are
  * bit-exact against torchvision.ops.nms(...)[:TOP_K]), gather of kept detections, COCOeval
  * evaluateImg matching.  Replaces src/running_main_v2.py:817-839 and the per-image part of
  * torchmetrics MeanAveragePrecision (:884-892). */
-int btpost_nms_match(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+BTPOST_API int btpost_nms_match(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
 /* a7+a8: projector mask (Conv2d nm->1, bilinear x4, sigmoid>0.5) and instance masks
  * (coeff . protos, crop, bilinear x4, sigmoid>0.5), pixel counters, per-image Dice / IoU.
  * Replaces src/running_main_v2.py:689-713, src/test_model.py:15-23,80-89. */
-int btpost_masks(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+BTPOST_API int btpost_masks(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
 /* Whole hot path for one batch: the three stages above, back to back on `stream`. */
-int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+BTPOST_API int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }
