@@ -183,7 +183,7 @@ def coco_match(det_xyxy, gt_xyxy, thrs, area_rng=AREA_RANGES):
     return dm[:, :, :D], di[:, :, :D], gi[:, :G]
 
 
-def run_pipeline(batch, **kw):
+def run_pipeline(batch, pool=None, **kw):
     """Whole hot path on one batch (L2 head).  Returns numpy outputs in the CUDA library's layout."""
     p = dict(DEFAULTS)
     p.update(kw)
@@ -251,9 +251,16 @@ def run_pipeline(batch, **kw):
         # M2 instance masks
         if p["with_instances"]:
             im = np.zeros((k, S, S), np.uint8)
-            for i in range(k):
+
+            def _one(i, b=b, im=im, gtm=gtm):
                 im[i] = instance_mask(protos[b], out["det_coeff"][b, i], out["dets"][b, i, :4], S, p["crop"])
                 out["inst_area"][b, i] = int(im[i].sum()); out["inst_inter"][b, i] = int((im[i] & gtm).sum())
+
+            if pool is not None:          # ctypes releases the GIL: instances run on all host threads
+                list(pool.map(_one, range(k)))
+            else:
+                for i in range(k):
+                    _one(i)
             out["inst_masks"].append(im)
             # union of the instance masks = the image-level mask the per-image Dice / IoU is taken on
             um = im.any(0).astype(np.uint8) if k else np.zeros((S, S), np.uint8)
