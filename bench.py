@@ -220,9 +220,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- warm-up
+    # ---------------- warm-up; the step is captured once into a CUDA graph (3 kernels per replay)
+    graph = pp.capture(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], bias)
+    out = pp.out
     for _ in range(args.warmup):
-        out = step()
+        graph.replay()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -233,7 +235,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        out = step()
+        graph.replay()
     c = pack_counters(out)
     if world > 1:
         dist.all_reduce(c)  # the only collective: metric counters (NCCL over NVLink)
@@ -268,11 +270,13 @@ def main():
         res_host = {k: torch.empty_like(out[k], device="cpu").pin_memory()
                     for k in ("det_count", "dets", "seg_dice", "seg_iou", "uni_dice", "uni_iou", "cm", "seg_cnt4")}
         dd = {k: torch.empty_like(v) for k, v in d.items()}
+        graph2 = pp.capture(dd["head"], dd["protos"], dd["det_boxes_gt"], dd["masks_gt"], dd["proj_weight"], bias)
 
         def e2e_step():
             for k in dd:
                 dd[k].copy_(host[k], non_blocking=True)
-            o = step(dd)
+            graph2.replay()
+            o = pp.out
             for k, hbuf in res_host.items():
                 hbuf.copy_(o[k], non_blocking=True)
             torch.cuda.current_stream().synchronize()   # the caller reads the step's result

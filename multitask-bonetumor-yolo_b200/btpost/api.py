@@ -192,6 +192,17 @@ class PostProcessor:
         _lib.check(rc, f"btpost_{stage}")
         return self.out
 
+    def capture(self, head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias=0.0, **kw):
+        """Capture one step on these (static) buffers into a CUDA graph; returns the graph, whose
+        ``replay()`` re-runs the whole hot path with one host call (the library is capture-safe:
+        no allocation, no synchronisation, caller's stream only)."""
+        self.run(head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias, **kw)   # warm-up: attributes, module load
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias, **kw)
+        return g
+
     # -- reference-shaped views -----------------------------------------------------------------
     def to_reference_lists(self, out=None):
         """(map_preds, map_targets, det_log_preds, det_log_gts) exactly as

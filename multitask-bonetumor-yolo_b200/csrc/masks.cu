@@ -15,13 +15,16 @@
 // shared memory with 32 bulk async copies (TMA, cp.async.bulk + mbarrier complete_tx) issued by
 // one warp, and while they are in flight zeroes its bit tiles, packs the GT mask strip to bits
 // and builds the list of detections whose crop box touches the strip.  From shared memory it then
-// (1) projects + upsamples + thresholds the M1 mask, (2) for every listed detection contracts
-// its 32 coefficients against the prototype pixels inside the crop box (sequential fp32 FMA, the
+// (1) projects + upsamples + thresholds the M1 mask, (2) contracts the 32 coefficients of every
+// listed detection against the prototype pixels inside its crop box (sequential fp32 FMA, the
 // same summation order as the oracle; TF32 tensor cores would break bit parity and the op is
 // ~0.5 FLOP/B), upsamples and thresholds per cell, ORs the result into the strip's union tile and
-// counts area / intersection with GT, (3) reduces the bit tiles to integer counters.  Output
-// ownership per strip is exclusive, so there are no global atomics on pixels; the last strip of
-// an image to finish turns the integer counters into Dice / IoU.
+// counts area / intersection with GT, (3) reduces the bit tiles to integer counters.  The M2 work
+// of a strip is flattened over the whole CTA -- (detection, pixel) and (detection, cell) items
+// found by a prefix-sum search -- so small boxes do not waste lanes (ncu r01a: one warp per
+// detection ran at 17 active lanes and 107 M warp instructions).  Output ownership per strip is
+// exclusive, so there are no global atomics on pixels; the last strip of an image to finish
+// turns the integer counters into Dice / IoU.
 #include "common.cuh"
 
 namespace bt {
@@ -29,7 +32,9 @@ namespace bt {
 constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int NM = 32;
-constexpr int SCR_COLS = 64;  // prototype columns per warp scratch chunk (63 cells)
+constexpr int CHUNK = 32;        // detections per M2 chunk
+constexpr int CF_PITCH = NM + 1; // coefficient row pitch in shared memory (bank-conflict free)
+constexpr int SCR_CAP = 3072;    // scratch pixels per M2 batch (+ one maximal piece of slack)
 
 struct K3Params {
     int B, S_h, S_w, PH, PW, R, K, crop, gt_f32, nstrips;
@@ -44,7 +49,7 @@ struct K3Params {
     uint8_t *seg_mask, *uni_mask;
     float *seg_logits;
     // shared-memory offsets (bytes)
-    int off_lm, off_scr, off_gt, off_m1, off_un, off_list, wpr;
+    int off_lm, off_scr, off_gtrow, off_gtc, off_m1c, off_unc, off_list, off_cf, wpr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,9 +86,8 @@ __device__ __forceinline__ float lerp_row(float a, float b, float w0, float w1) 
     return __fmaf_rn(w0, a, __fmul_rn(w1, b));
 }
 
-// Evaluate one cell: 4 corner values -> up to 4x4 thresholded output pixels.
-// Returns a 16-bit mask, bit (ry*4+rx).  `nry`/`nrx` = valid rows/cols (2 or 4); border cells
-// (index -1) use interpolation weight 0 (source coordinate clamped to 0).
+// Evaluate one cell: 4 corner values -> 4x4 thresholded output pixels, bit (ry*4+rx).
+// Border cells (index -1) use interpolation weight 0 (source coordinate clamped to 0).
 template <bool LOG>
 __device__ __forceinline__ unsigned cell_bits(float v00, float v01, float v10, float v11, bool border_y, bool border_x,
                                               float (&logits)[16]) {
@@ -110,6 +114,35 @@ __device__ __forceinline__ unsigned cell_bits(float v00, float v01, float v10, f
     return bits;
 }
 
+// Valid-pixel mask of a cell: border cells (-1) own output rows/cols {0,1}; the last cell row/col
+// owns only the two pixels left before the image edge.
+__device__ __forceinline__ unsigned cell_valid(int ci, int cj, int S_h, int S_w) {
+    const int nry = (ci < 0) ? 2 : min(4, S_h - (4 * ci + 2));
+    const int nrx = (cj < 0) ? 2 : min(4, S_w - (4 * cj + 2));
+    const unsigned rowm = (1u << nrx) - 1u;
+    unsigned m = 0;
+    for (int r = 0; r < nry; ++r) m |= rowm << (4 * r);
+    return m;
+}
+
+// Crop region of a detection at prototype resolution: pixels with r>=y1 & r<y2 & c>=x1 & c<x2
+// on the box scaled by proto/img (Ultralytics crop_mask).  Returns false for an empty region.
+__device__ __forceinline__ bool crop_region(const float *o, int crop, float rx, float ry, int PW, int PH, int &r_lo,
+                                            int &r_hi, int &c_lo, int &c_hi) {
+    r_lo = 0; r_hi = PH - 1; c_lo = 0; c_hi = PW - 1;
+    if (!crop) return true;
+    float x1 = __fmul_rn(o[0], rx), y1 = __fmul_rn(o[1], ry), x2 = __fmul_rn(o[2], rx), y2 = __fmul_rn(o[3], ry);
+    if (!((x1 == x1) && (y1 == y1) && (x2 == x2) && (y2 == y2))) return false;
+    c_lo = max(0, (int)ceilf(fmaxf(x1, -1.0f)));
+    r_lo = max(0, (int)ceilf(fmaxf(y1, -1.0f)));
+    c_hi = min(PW - 1, (int)ceilf(fminf(x2, (float)PW + 1.0f)) - 1);
+    r_hi = min(PH - 1, (int)ceilf(fminf(y2, (float)PH + 1.0f)) - 1);
+    return c_lo <= c_hi && r_lo <= r_hi;
+}
+
+// TPW / TR > 0: compile-time prototype width / strip height (shared-memory strides become
+// immediates); 0: run-time values.
+template <int TPW, int TR>
 __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_constant__ K3Params P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -117,24 +150,37 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     __shared__ int s_nlist;
     __shared__ int s_red[K3_WARPS][6];
     __shared__ int s_last;
+    // per-chunk piece tables
+    __shared__ int s_pxoff[CHUNK + 1], s_celloff[CHUNK + 1];
+    __shared__ short s_rlo[CHUNK], s_rhi[CHUNK], s_clo[CHUNK], s_chi[CHUNK];
+    __shared__ short s_pra[CHUNK], s_pa[CHUNK], s_npc[CHUNK], s_cia[CHUNK], s_ncc[CHUNK];
+    __shared__ float s_inpc[CHUNK], s_incc[CHUNK];
+    __shared__ int s_area[CHUNK], s_inter[CHUNK];
+    __shared__ int s_e0, s_e1;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
-    const int PW = P.PW, PH = P.PH, R = P.R, S_w = P.S_w, S_h = P.S_h, K = P.K;
+    const int PW = TPW > 0 ? TPW : P.PW, R = TR > 0 ? TR : P.R;
+    const int PH = P.PH, S_w = P.S_w, S_h = P.S_h, K = P.K;
     const int rowsmax = R + 1;
+    const int CS = rowsmax * PW;   // channel stride in s_pro (floats)
+    const int ncc_all = PW + 1;    // cells per cell row (incl. the border column -1)
 
-    float *s_pro = reinterpret_cast<float *>(smem);                       // [NM][R+1][PW]
-    float *s_lm = reinterpret_cast<float *>(smem + P.off_lm);             // [R+1][PW]
-    float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);           // [warps][R+1][SCR_COLS]
-    uint32_t *s_gt = reinterpret_cast<uint32_t *>(smem + P.off_gt);       // [4R+2][wpr+1] raw bits (bit x)
-    uint32_t *s_m1 = reinterpret_cast<uint32_t *>(smem + P.off_m1);       // [4R+2][wpr+1] shifted bits (bit x+2)
-    uint32_t *s_un = reinterpret_cast<uint32_t *>(smem + P.off_un);       // [4R+2][wpr+1]
+    float *s_pro = reinterpret_cast<float *>(smem);                            // [NM][R+1][PW]
+    float *s_lm = reinterpret_cast<float *>(smem + P.off_lm);                  // [R+1][PW]
+    float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);                // [SCR_CAP + (R+1)*PW]
+    uint32_t *s_gtrow = reinterpret_cast<uint32_t *>(smem + P.off_gtrow);      // [4R+2][wpr+1] row bits (bit x)
+    uint32_t *s_gtc = reinterpret_cast<uint32_t *>(smem + P.off_gtc);          // [R+1][PW+1] cell bits
+    uint32_t *s_m1c = reinterpret_cast<uint32_t *>(smem + P.off_m1c);          // [R+1][PW+1]
+    uint32_t *s_unc = reinterpret_cast<uint32_t *>(smem + P.off_unc);          // [R+1][PW+1]
     unsigned short *s_list = reinterpret_cast<unsigned short *>(smem + P.off_list);  // [K]
-    const int wpr = P.wpr, tp = wpr + 1;  // words per output row, tile pitch
+    float *s_cf = reinterpret_cast<float *>(smem + P.off_cf);                  // [CHUNK][CF_PITCH]
+    const int wpr = P.wpr, tp = wpr + 1;
 
     // ---- strip geometry
     const int ci_lo = (s == 0) ? -1 : s * R;
     const int ci_hi = min(s * R + R - 1, PH - 1);
+    const int ncr_all = ci_hi - ci_lo + 1;
     const int p_lo = s * R;
     const int p_hi = min(ci_hi + 1, PH - 1);
     const int nrows = p_hi - p_lo + 1;
@@ -153,58 +199,66 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
         if (lane == 0) mbar_expect_tx(&s_bar, bytes * NM);
         __syncwarp();
         const float *src = P.protos + (((size_t)b * NM + lane) * PH + p_lo) * PW;
-        bulk_g2s(s_pro + (size_t)lane * rowsmax * PW, src, bytes, &s_bar);
+        bulk_g2s(s_pro + (size_t)lane * CS, src, bytes, &s_bar);
     }
 
     // ---- (b) overlap with the copies: weights, tiles, GT bits, detection list
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
     if (tid == 0) s_nlist = 0;
-    for (int i = tid; i < (4 * R + 2) * tp; i += K3_THREADS) { s_gt[i] = 0; s_m1[i] = 0; s_un[i] = 0; }
-    __syncthreads();
-    for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
-        const int yr = q / wpr, w = q - yr * wpr;
-        const size_t base = ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32;
+    for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) { s_m1c[i] = 0; s_unc[i] = 0; }
+    for (int q = tid; q < nyrows * tp; q += K3_THREADS) {
+        const int yr = q / tp, w = q - yr * tp;
         uint32_t bits = 0;
-        if (P.gt_f32) {
-            const float4 *g = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) + base);
+        if (w < wpr) {
+            const size_t base = ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32;
+            if (P.gt_f32) {
+                const float4 *g = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) + base);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 v = __ldg(g + i);
-                bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
-                        ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
-            }
-        } else {
-            const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) + base);
+                for (int i = 0; i < 8; ++i) {
+                    float4 v = __ldg(g + i);
+                    bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
+                            ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
+                }
+            } else {
+                const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) + base);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                uint4 v = __ldg(g + i);
-                uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                for (int i = 0; i < 2; ++i) {
+                    uint4 v = __ldg(g + i);
+                    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        bits |= (((wv[j] >> (8 * k)) & 0xffu) ? 1u : 0u) << (16 * i + 4 * j + k);
+                    for (int j = 0; j < 4; ++j) {
+                        // byte != 0 -> bit: fold each byte to its low bit, then gather the four low bits
+                        uint32_t x = wv[j];
+                        x = (x | (x >> 4)) & 0x0f0f0f0fu;
+                        x = (x | (x >> 2)) & 0x03030303u;
+                        x = (x | (x >> 1)) & 0x01010101u;
+                        bits |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (16 * i + 4 * j);
+                    }
+                }
             }
         }
-        s_gt[yr * tp + w] = bits;
+        s_gtrow[q] = bits;
     }
     const int D = min(P.det_count[b], K);
+    __syncthreads();
     for (int k = tid; k < D; k += K3_THREADS) {
-        const float *o = P.dets + ((size_t)b * K + k) * 6;
-        int r_lo = 0, r_hi = PH - 1, c_lo = 0, c_hi = PW - 1;
-        bool ok = true;
-        if (P.crop) {
-            float x1 = __fmul_rn(o[0], P.rx), y1 = __fmul_rn(o[1], P.ry), x2 = __fmul_rn(o[2], P.rx), y2 = __fmul_rn(o[3], P.ry);
-            ok = (x1 == x1) && (y1 == y1) && (x2 == x2) && (y2 == y2);
-            if (ok) {
-                c_lo = max(0, (int)ceilf(fmaxf(x1, -1.0f)));
-                r_lo = max(0, (int)ceilf(fmaxf(y1, -1.0f)));
-                c_hi = min(PW - 1, (int)ceilf(fminf(x2, (float)PW + 1.0f)) - 1);
-                r_hi = min(PH - 1, (int)ceilf(fminf(y2, (float)PH + 1.0f)) - 1);
-            }
-        }
-        ok = ok && c_lo <= c_hi && r_lo <= r_hi && max(r_lo - 1, ci_lo) <= min(r_hi, ci_hi);
+        int r_lo, r_hi, c_lo, c_hi;
+        bool ok = crop_region(P.dets + ((size_t)b * K + k) * 6, P.crop, P.rx, P.ry, PW, PH, r_lo, r_hi, c_lo, c_hi);
+        ok = ok && max(r_lo - 1, ci_lo) <= min(r_hi, ci_hi);
         if (ok) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)k;
+    }
+    // GT cells from the row bits (bit x of output row y  ->  bit ry*4+rx of cell (ci, cj))
+    for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+        const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
+        const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
+        const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+        unsigned bits = 0;
+        for (int ry = 0; ry < nry; ++ry) {
+            const uint32_t *row = s_gtrow + (ybase + ry - y_lo) * tp + (xbase >> 5);
+            unsigned g = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
+            bits |= g << (4 * ry);
+        }
+        s_gtc[q] = bits;
     }
 
     // ---- (c) wait for the prototypes
@@ -215,153 +269,165 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     for (int q = tid; q < nrows * PW; q += K3_THREADS) {
         float acc = P.bias;
 #pragma unroll
-        for (int k = 0; k < NM; ++k) acc = __fmaf_rn(s_w[k], s_pro[(size_t)k * rowsmax * PW + q], acc);
+        for (int k = 0; k < NM; ++k) acc = __fmaf_rn(s_w[k], s_pro[k * CS + q], acc);
         s_lm[q] = acc;
     }
     __syncthreads();
 
-    // ---- (e) M1 cells -> shifted bit tile (+ optional logits)
-    {
-        const int ncr = ci_hi - ci_lo + 1, ncc = PW + 1;
-        for (int q = tid; q < ncr * ncc; q += K3_THREADS) {
-            const int ci = ci_lo + q / ncc, cj = (q % ncc) - 1;
-            const int r0 = max(ci, 0) - p_lo, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
-            const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
-            float lg[16];
-            const float v00 = s_lm[r0 * PW + c0], v01 = s_lm[r0 * PW + c1], v10 = s_lm[r1 * PW + c0], v11 = s_lm[r1 * PW + c1];
-            unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
-                                         : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
+    // ---- (e) M1 cells -> cell tile (+ optional logits)
+    for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+        const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
+        const int r0 = max(ci, 0) - p_lo, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
+        const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
+        float lg[16];
+        const float v00 = s_lm[r0 * PW + c0], v01 = s_lm[r0 * PW + c1], v10 = s_lm[r1 * PW + c0], v11 = s_lm[r1 * PW + c1];
+        unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
+                                     : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
+        if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+        s_m1c[q] = bits;
+        if (P.seg_logits) {
             const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
             const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-            const unsigned colmask = (1u << nrx) - 1u;
-            const int xs = xbase + 2;
             for (int ry = 0; ry < nry; ++ry) {
-                unsigned nib = (bits >> (4 * ry)) & colmask;
-                if (nib) atomicOr(&s_m1[(ybase + ry - y_lo) * tp + (xs >> 5)], nib << (xs & 31));
-                if (P.seg_logits) {
-                    float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
-                    for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
-                }
+                float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
+                for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
             }
         }
     }
 
-    // ---- (f) M2 instance masks: one warp per listed detection
+    // ---- (f) M2 instance masks, CHUNK detections at a time, work flattened over the CTA
     const int nlist = s_nlist;
-    float *scr = s_scr + (size_t)wid * rowsmax * SCR_COLS;
-    for (int li = wid; li < nlist; li += K3_WARPS) {
-        const int k = s_list[li];
-        const float *o = P.dets + ((size_t)b * K + k) * 6;
-        int r_lo = 0, r_hi = PH - 1, c_lo = 0, c_hi = PW - 1;
-        if (P.crop) {
-            float x1 = __fmul_rn(o[0], P.rx), y1 = __fmul_rn(o[1], P.ry), x2 = __fmul_rn(o[2], P.rx), y2 = __fmul_rn(o[3], P.ry);
-            c_lo = max(0, (int)ceilf(fmaxf(x1, -1.0f)));
-            r_lo = max(0, (int)ceilf(fmaxf(y1, -1.0f)));
-            c_hi = min(PW - 1, (int)ceilf(fminf(x2, (float)PW + 1.0f)) - 1);
-            r_hi = min(PH - 1, (int)ceilf(fminf(y2, (float)PH + 1.0f)) - 1);
-        }
-        float cf[NM];
-        const float *cp = P.det_coeff + ((size_t)b * K + k) * NM;
-#pragma unroll
-        for (int i = 0; i < NM; ++i) cf[i] = __ldg(cp + i);
-        // cell rows of this detection inside the strip, and the prototype rows they touch
-        const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
-        const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
-        const int npr = pr_b - pr_a + 1;
-        int area = 0, inter = 0;
-        for (int ja = c_lo - 1; ja <= c_hi; ja += SCR_COLS - 1) {
-            const int jb = min(ja + SCR_COLS - 2, c_hi);
-            const int pa = max(ja, 0), pb = min(jb + 1, PW - 1);
-            const int npc = pb - pa + 1;
-            // cropped logits of the chunk
-            for (int q = lane; q < npr * npc; q += 32) {
-                const int rr = q / npc, cc = q - rr * npc;
-                const int r = pr_a + rr, c = pa + cc;
-                float acc = 0.0f;
-                if (r >= r_lo && r <= r_hi && c >= c_lo && c <= c_hi) {
-                    const float *pp = s_pro + (size_t)(r - p_lo) * PW + c;
-#pragma unroll
-                    for (int i = 0; i < NM; ++i) acc = __fmaf_rn(cf[i], pp[(size_t)i * rowsmax * PW], acc);
-                }
-                scr[rr * SCR_COLS + cc] = acc;
+    for (int ch0 = 0; ch0 < nlist; ch0 += CHUNK) {
+        const int nch = min(CHUNK, nlist - ch0);
+        __syncthreads();   // previous chunk fully consumed (tables, scratch, counters)
+        // piece tables + coefficient staging
+        if (wid == 0) {
+            int npx = 0, ncell = 0;
+            if (lane < nch) {
+                const int k = s_list[ch0 + lane];
+                int r_lo, r_hi, c_lo, c_hi;
+                crop_region(P.dets + ((size_t)b * K + k) * 6, P.crop, P.rx, P.ry, PW, PH, r_lo, r_hi, c_lo, c_hi);
+                const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
+                const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
+                const int ja = c_lo - 1;
+                const int pa = max(ja, 0), pb = min(c_hi + 1, PW - 1);
+                const int npr = pr_b - pr_a + 1, npc = pb - pa + 1;
+                const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
+                s_rlo[lane] = r_lo; s_rhi[lane] = r_hi; s_clo[lane] = c_lo; s_chi[lane] = c_hi;
+                s_pra[lane] = pr_a; s_pa[lane] = pa; s_npc[lane] = npc; s_cia[lane] = ci_a; s_ncc[lane] = ncc;
+                s_inpc[lane] = 1.0f / (float)npc; s_incc[lane] = 1.0f / (float)ncc;
+                s_area[lane] = 0; s_inter[lane] = 0;
+                npx = npr * npc; ncell = ncr * ncc;
             }
-            __syncwarp();
-            const int ncr = ci_b - ci_a + 1, ncc = jb - ja + 1;
-            for (int q = lane; q < ncr * ncc; q += 32) {
-                const int ci = ci_a + q / ncc, cj = ja + (q % ncc);
-                const int r0 = max(ci, 0) - pr_a, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
-                const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
-                float unused[16];
-                unsigned bits = cell_bits<false>(scr[r0 * SCR_COLS + c0], scr[r0 * SCR_COLS + c1], scr[r1 * SCR_COLS + c0],
-                                                 scr[r1 * SCR_COLS + c1], ci < 0, cj < 0, unused);
-                if (bits == 0) continue;
-                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                const unsigned colmask = (1u << nrx) - 1u;
-                const int xs = xbase + 2;
-                for (int ry = 0; ry < nry; ++ry) {
-                    unsigned nib = (bits >> (4 * ry)) & colmask;
-                    if (!nib) continue;
-                    const int yr = ybase + ry - y_lo;
-                    atomicOr(&s_un[yr * tp + (xs >> 5)], nib << (xs & 31));
-                    unsigned g = __funnelshift_r(s_gt[yr * tp + (xbase >> 5)], s_gt[yr * tp + (xbase >> 5) + 1], xbase & 31);
-                    area += __popc(nib);
-                    inter += __popc(nib & g);
+            int ipx = npx, icell = ncell;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, ipx, d), u = __shfl_up_sync(0xffffffffu, icell, d);
+                if (lane >= d) { ipx += v; icell += u; }
+            }
+            s_pxoff[lane + 1] = ipx; s_celloff[lane + 1] = icell;
+            if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
+        }
+        for (int q = tid; q < nch * NM; q += K3_THREADS) {
+            const int e = q >> 5, i = q & 31;
+            s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[ch0 + e]) * NM + i);
+        }
+        __syncthreads();
+        const int nbatch = (s_pxoff[nch] + SCR_CAP - 1) / SCR_CAP;
+        for (int bi = 0; bi < nbatch; ++bi) {
+            // entries whose first scratch pixel falls into [bi*CAP, (bi+1)*CAP) form the batch
+            if (wid == 0) {
+                const bool in = lane < nch && (s_pxoff[lane] / SCR_CAP) == bi;
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (lane == 0) { s_e0 = m ? (__ffs(m) - 1) : 0; s_e1 = m ? (32 - __clz(m)) : 0; }
+            }
+            __syncthreads();
+            const int e0 = s_e0, e1 = s_e1;
+            if (e1 > e0) {
+                const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
+                // cropped logits of every (detection, pixel) item of the batch
+                for (int q = tid; q < npx; q += K3_THREADS) {
+                    int lo = e0, hi = e1;   // last entry with pxoff <= px0 + q
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= q) lo = mid; else hi = mid; }
+                    const int e = lo, loc = q - (s_pxoff[e] - px0);
+                    const int npc = s_npc[e];
+                    const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), cc = loc - rr * npc;
+                    const int r = s_pra[e] + rr, c = s_pa[e] + cc;
+                    float acc = 0.0f;
+                    if (r >= s_rlo[e] && r <= s_rhi[e] && c >= s_clo[e] && c <= s_chi[e]) {
+                        const float *pp = s_pro + (r - p_lo) * PW + c;
+                        const float *cf = s_cf + e * CF_PITCH;
+#pragma unroll
+                        for (int i = 0; i < NM; ++i) acc = __fmaf_rn(cf[i], pp[i * CS], acc);
+                    }
+                    s_scr[q] = acc;
+                }
+                __syncthreads();
+                const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
+                for (int q = tid; q < ncell; q += K3_THREADS) {
+                    int lo = e0, hi = e1;
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
+                    const int e = lo, loc = q - (s_celloff[e] - cl0);
+                    const int ncc = s_ncc[e], npc = s_npc[e];
+                    const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
+                    const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
+                    const int pr_a = s_pra[e], pa = s_pa[e];
+                    const float *scr = s_scr + (s_pxoff[e] - px0);
+                    const int r0 = max(ci, 0) - pr_a, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
+                    const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
+                    float unused[16];
+                    unsigned bits = cell_bits<false>(scr[r0 * npc + c0], scr[r0 * npc + c1], scr[r1 * npc + c0],
+                                                     scr[r1 * npc + c1], ci < 0, cj < 0, unused);
+                    if (bits == 0) continue;
+                    if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+                    if (bits == 0) continue;
+                    const int cell = (ci - ci_lo) * ncc_all + cj + 1;
+                    atomicOr(&s_unc[cell], bits);
+                    atomicAdd(&s_area[e], __popc(bits));
+                    const int it = __popc(bits & s_gtc[cell]);
+                    if (it) atomicAdd(&s_inter[e], it);
                 }
             }
-            __syncwarp();
+            __syncthreads();
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            area += __shfl_down_sync(0xffffffffu, area, d);
-            inter += __shfl_down_sync(0xffffffffu, inter, d);
-        }
-        if (lane == 0) {
-            if (area && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], area);
-            if (inter && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], inter);
+        if (tid < nch) {
+            const int k = s_list[ch0 + tid];
+            if (s_area[tid] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[tid]);
+            if (s_inter[tid] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[tid]);
         }
     }
     __syncthreads();
 
     // ---- (g) integer counters of the strip + optional dense mask output
-    int c6[6] = {0, 0, 0, 0, 0, 0};  // seg inter, seg P, G, uni inter, uni P, (unused)
-    for (int q = tid; q < nyrows * tp; q += K3_THREADS) {
-        const int yr = q / tp, w = q - yr * tp;
-        const uint32_t lo = (w > 0) ? s_gt[yr * tp + w - 1] : 0u;
-        const uint32_t hi = s_gt[yr * tp + w];  // pad word is zero
-        const uint32_t g = __funnelshift_l(lo, hi, 2);
-        const uint32_t m1 = s_m1[q], un = s_un[q];
-        c6[0] += __popc(m1 & g); c6[1] += __popc(m1); c6[2] += __popc(g);
-        c6[3] += __popc(un & g); c6[4] += __popc(un);
+    int c5[5] = {0, 0, 0, 0, 0};  // seg inter, seg P, G, uni inter, uni P
+    for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+        const uint32_t g = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
+        c5[0] += __popc(m1 & g); c5[1] += __popc(m1); c5[2] += __popc(g);
+        c5[3] += __popc(un & g); c5[4] += __popc(un);
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        int v = c6[i];
+        int v = c5[i];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
         if (lane == 0) s_red[wid][i] = v;
     }
     if (P.seg_mask || P.uni_mask) {
-        for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
-            const int yr = q / wpr, w = q - yr * wpr;
-            const size_t base = ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32;
+        // cell tiles -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
+        for (int q = tid; q < nyrows * ncc_all; q += K3_THREADS) {
+            const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
+            const int y = y_lo + yr;
+            const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+            const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+            const int cell = (ci - ci_lo) * ncc_all + cj + 1;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
                 uint8_t *dst = which ? P.uni_mask : P.seg_mask;
                 if (!dst) continue;
-                const uint32_t *t = which ? s_un : s_m1;
-                const uint32_t bits = __funnelshift_r(t[yr * tp + w], t[yr * tp + w + 1], 2);
-                uint4 *o = reinterpret_cast<uint4 *>(dst + base);
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    uint32_t wv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t nib = (bits >> (16 * i + 4 * j)) & 0xfu;
-                        wv[j] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-                    }
-                    o[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                }
+                const unsigned nib = ((which ? s_unc : s_m1c)[cell] >> (4 * ry)) & 0xfu;
+                uint8_t *o = dst + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
+                *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
+                if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
             }
         }
     }
@@ -379,10 +445,8 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     __syncthreads();
     if (s_last && tid < 2) {
         __threadfence();
-        const int *a = P.acc + b * 8 + 3 * tid;
-        // word 2 (|G|) is shared by both masks
-        long long inter = atomicAdd((int *)&a[0], 0), pp = atomicAdd((int *)&a[1], 0);
-        long long gg = atomicAdd((int *)&P.acc[b * 8 + 2], 0);
+        long long inter = atomicAdd(&P.acc[b * 8 + 3 * tid], 0), pp = atomicAdd(&P.acc[b * 8 + 3 * tid + 1], 0);
+        long long gg = atomicAdd(&P.acc[b * 8 + 2], 0);   // |G| is shared by both masks
         long long total = (long long)S_h * S_w;
         long long *img3 = tid ? P.uni_img3 : P.seg_img3;
         long long *cnt4 = tid ? P.uni_cnt4 : P.seg_cnt4;
@@ -404,14 +468,24 @@ static size_t k3_layout(K3Params &P, int R) {
     const int rowsmax = R + 1;
     size_t off = (size_t)NM * rowsmax * P.PW * sizeof(float);
     P.wpr = P.S_w / 32;
-    const size_t tile = (size_t)(4 * R + 2) * (P.wpr + 1) * sizeof(uint32_t);
+    const size_t celltile = align_up((size_t)rowsmax * (P.PW + 1) * sizeof(uint32_t), 16);
     P.off_lm = (int)off; off += (size_t)rowsmax * P.PW * sizeof(float);
-    P.off_scr = (int)off; off += (size_t)K3_WARPS * rowsmax * SCR_COLS * sizeof(float);
-    P.off_gt = (int)off; off += tile;
-    P.off_m1 = (int)off; off += tile;
-    P.off_un = (int)off; off += tile;
+    P.off_scr = (int)off; off += (size_t)(SCR_CAP + rowsmax * P.PW) * sizeof(float);
+    P.off_gtrow = (int)off; off += align_up((size_t)(4 * R + 2) * (P.wpr + 1) * sizeof(uint32_t), 16);
+    P.off_gtc = (int)off; off += celltile;
+    P.off_m1c = (int)off; off += celltile;
+    P.off_unc = (int)off; off += celltile;
     P.off_list = (int)off; off += align_up((size_t)P.K * sizeof(unsigned short), 16);
+    P.off_cf = (int)off; off += (size_t)CHUNK * CF_PITCH * sizeof(float);
     return off;
+}
+
+template <int TPW, int TR>
+static int launch_k3(const K3Params &P, dim3 grid, size_t smem, cudaStream_t s) {
+    if (cudaFuncSetAttribute(masks_kernel<TPW, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return BT_ERR_CUDA;
+    masks_kernel<TPW, TR><<<grid, K3_THREADS, smem, s>>>(P);
+    return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
 int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
@@ -432,17 +506,18 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     int R = 1;
     for (int r = 8; r >= 1; --r) {
         K3Params tmp = P;
-        if (k3_layout(tmp, r) <= 112 * 1024) { R = r; break; }
+        if (k3_layout(tmp, r) <= 114000) { R = r; break; }
     }
     P.R = R;
     size_t smem = k3_layout(P, R);
     if (smem > 220 * 1024) return BT_ERR_UNSUPPORTED;
     P.nstrips = (p.proto_h + R - 1) / R;
-    if (cudaFuncSetAttribute(masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return BT_ERR_CUDA;
     dim3 grid(P.nstrips, p.batch);
-    masks_kernel<<<grid, K3_THREADS, smem, s>>>(P);
-    return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
+    if (P.PW == 160 && R == 2) return launch_k3<160, 2>(P, grid, smem, s);
+    if (P.PW == 160 && R == 3) return launch_k3<160, 3>(P, grid, smem, s);
+    if (P.PW == 256 && R == 1) return launch_k3<256, 1>(P, grid, smem, s);
+    if (P.PW == 256 && R == 2) return launch_k3<256, 2>(P, grid, smem, s);
+    return launch_k3<0, 0>(P, grid, smem, s);
 }
 
 }  // namespace bt
