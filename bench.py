@@ -18,7 +18,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -48,51 +47,56 @@ def workload_name(args):
 
 
 # --------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region with the recipe's own
+    `nvidia-smi --query-gpu=... -lms` line, run as a SEPARATE process (NVML calls made from a thread
+    of this process serialise against CUDA launches and were measured to double the step time)."""
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop_evt = threading.Event()
-        self.ok = False
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception:
-            self.ok = False
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def run(self):
-        if not self.ok:
+    def __init__(self, index, period_ms=100):
+        import shutil
+        import subprocess
+        import tempfile
+        self.proc, self.path = None, None
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
             return
-        nv = self.nv
-        names = {
-            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-        }
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.02)
+        f = tempfile.NamedTemporaryFile(prefix="btpost_clocks_", suffix=".csv", delete=False)
+        self.path = f.name
+        self.proc = subprocess.Popen([exe, "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-lms", str(period_ms)], stdout=f, stderr=subprocess.DEVNULL)
+
+    def start(self):
+        return self
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "nvidia-smi not found"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path).read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6 or not parts[0].isdigit():
+                continue
+            mhz.append(int(parts[0]))
+            mx = int(parts[1]) if parts[1].isdigit() else mx
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -162,7 +166,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)

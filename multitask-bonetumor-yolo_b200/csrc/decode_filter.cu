@@ -23,8 +23,8 @@ namespace cg = cooperative_groups;
 
 namespace bt {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_MAX_THREADS = 1024;   // block size is chosen per launch so that one pass covers the CTA's anchors
+constexpr int K1_MAX_WARPS = K1_MAX_THREADS / 32;
 constexpr int K1_CLUSTER = 8;
 constexpr int K1_MAX_GT = 32;
 
@@ -65,8 +65,8 @@ __device__ __forceinline__ int block_excl_scan(int c, int &total, int *s_warp) {
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     int off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < K1_WARPS; ++w) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) {
         int v = s_warp[w];
         if (w < wid) off += v;
         tot += v;
@@ -142,13 +142,13 @@ __device__ __forceinline__ float bt_expf(float x) {
 
 // ---- L1 decoder: three raw maps [4*R+nc, H, W]; DFL softmax expectation, anchors (x+.5,y+.5),
 // stride = img/W, class score = sigmoid(logit)  (running_main_v2.py:743-775, dist2bbox :97-107).
-struct L1Decoder {
+struct L1DecoderBase {
     const float *map[3];  // already offset to image b
     int off[4], w[3];
     float stride[3];
-    int R, nc;
+    int R, nc, N;
     __device__ __forceinline__ int level(int n) const { return n >= off[2] ? 2 : (n >= off[1] ? 1 : 0); }
-    __device__ __forceinline__ void scores(int n, float (&best)[1], int (&lab)[1]) const {
+    __device__ __forceinline__ void scores1(int n, float (&best)[1], int (&lab)[1]) const {
         int l = level(n);
         int HW = off[l + 1] - off[l], pos = n - off[l];
         const float *p = map[l] + (size_t)(4 * R) * HW + pos;
@@ -160,7 +160,7 @@ struct L1Decoder {
         }
         best[0] = b; lab[0] = bi;
     }
-    __device__ __forceinline__ void boxes(int n, float (&x1)[1], float (&y1)[1], float (&x2)[1], float (&y2)[1]) const {
+    __device__ __forceinline__ void boxes1(int n, float (&x1)[1], float (&y1)[1], float (&x2)[1], float (&y2)[1]) const {
         int l = level(n);
         int HW = off[l + 1] - off[l], pos = n - off[l];
         int W = w[l];
@@ -188,13 +188,33 @@ struct L1Decoder {
     }
 };
 
+template <int VEC>
+struct L1Decoder : L1DecoderBase {
+    __device__ __forceinline__ void scores(int n, float (&best)[VEC], int (&lab)[VEC]) const {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float b1[1] = {0.0f}; int l1[1] = {0};
+            if (n + i < N) scores1(n + i, b1, l1);
+            best[i] = b1[0]; lab[i] = l1[0];
+        }
+    }
+    __device__ __forceinline__ void boxes(int n, float (&x1)[VEC], float (&y1)[VEC], float (&x2)[VEC], float (&y2)[VEC]) const {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float a[1] = {0.0f}, b[1] = {0.0f}, c[1] = {0.0f}, d[1] = {0.0f};
+            if (n + i < N) boxes1(n + i, a, b, c, d);
+            x1[i] = a[0]; y1[i] = b[0]; x2[i] = c[0]; y2[i] = d[0];
+        }
+    }
+};
+
 template <int VEC, class Dec>
 __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31;
 
-    __shared__ int s_warp[K1_WARPS];
+    __shared__ int s_warp[K1_MAX_WARPS];
     __shared__ int s_ex;                 // this CTA's survivor count, read by peers through DSMEM
     __shared__ float s_coord[K1_MAX_GT][4];
     __shared__ float s_gtraw[K1_MAX_GT * 4];
@@ -203,14 +223,33 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
     __shared__ int s_cm[BT_MAX_CLASSES * BT_MAX_CLASSES];
     __shared__ int s_npos;
 
-    for (int i = tid; i < BT_MAX_CLASSES * BT_MAX_CLASSES; i += K1_THREADS) s_cm[i] = 0;
+    for (int i = tid; i < BT_MAX_CLASSES * BT_MAX_CLASSES; i += blockDim.x) s_cm[i] = 0;
     if (tid == 0) s_npos = 0;
+
+    // ---- anchor range of this CTA (in groups of VEC anchors); the block is sized so that every
+    // group has its own thread: ONE pass, the decoded values stay in registers across the
+    // cluster exchange (ncu r01b: the two-pass / two-iteration version spent its time in barriers
+    // waiting for a second round of loads that only 7 threads needed).
+    const int groups = (P.N + VEC - 1) / VEC;
+    const int gp = (groups + K1_CLUSTER - 1) / K1_CLUSTER;
+    const int g0 = rank * gp, g1 = min(groups, g0 + gp);
+    const int nthreads = blockDim.x;
+
+    // issue the head loads first: they are in flight while the GT rows are gathered
+    float best[VEC], x1[VEC], y1[VEC], x2[VEC], y2[VEC];
+    int lab[VEC];
+    const int g = g0 + tid;
+    const bool active = g < g1;
+    if (active) {
+        dec.scores(g * VEC, best, lab);
+        dec.boxes(g * VEC, x1, y1, x2, y2);
+    }
 
     // ---- GT prep: ordered gather of this image's rows, then the reference's cat/view layout.
     {
         const float S = P.img_w;  // reference multiplies every coordinate by the scalar img_size
         int base = 0;
-        for (int r0 = 0; r0 < P.n_rows; r0 += K1_THREADS) {
+        for (int r0 = 0; r0 < P.n_rows; r0 += nthreads) {
             int r = r0 + tid;
             bool hit = false;
             float row[6];
@@ -235,7 +274,7 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
         if (tid == 0) s_G = base < P.max_gt ? base : P.max_gt;
         __syncthreads();
         const int G = s_G;
-        for (int i = tid; i < 4 * G; i += K1_THREADS) {
+        for (int i = tid; i < 4 * G; i += nthreads) {
             float v = (P.gt_mode == BT_GT_LITERAL) ? s_coord[i % G][i / G] : s_coord[i / 4][i % 4];
             s_gtraw[i] = v;
             if (rank == 0) {
@@ -244,28 +283,61 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
             }
         }
         if (rank == 0) {
-            for (int i = tid; i < G; i += K1_THREADS) P.gt_labels[(size_t)b * P.max_gt + i] = s_gl[i];
-            if (tid == 0) { P.gt_count[b] = G; P.cm_pos[b] = 0; }
+            for (int i = tid; i < G; i += nthreads) P.gt_labels[(size_t)b * P.max_gt + i] = s_gl[i];
+            if (tid == 0) P.gt_count[b] = G;
         }
         __syncthreads();
     }
     const int G = s_G;
 
-    // ---- anchor range of this CTA (in groups of VEC anchors)
-    const int groups = (P.N + VEC - 1) / VEC;
-    const int gp = (groups + K1_CLUSTER - 1) / K1_CLUSTER;
-    const int g0 = rank * gp, g1 = min(groups, g0 + gp);
-
-    // ---- pass 1: count survivors
-    int cnt = 0;
-    for (int g = g0 + tid; g < g1; g += K1_THREADS) {
-        float best[VEC]; int lab[VEC];
-        dec.scores(g * VEC, best, lab);
+    // ---- filter flags + anchor<->GT confusion-matrix matching on the raw boxes
+    int c = 0, npos_thread = 0;
+    unsigned flags = 0;
+    if (active) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) cnt += (best[i] > P.conf) ? 1 : 0;
+        for (int i = 0; i < VEC; ++i) {
+            if (g * VEC + i >= P.N) continue;
+            if (best[i] > P.conf) { flags |= 1u << i; ++c; }
+            if (G > 0) {
+                // batch_bbox_iou (running_main_v2.py:68-94) against the unclamped GT copy.  With a
+                // non-negative threshold an anchor that intersects no GT box can never be positive
+                // (every IoU is 0/x), so the divisions are skipped for it; otherwise the full
+                // max / first-argmax over GT is evaluated exactly as the reference does.
+                bool any = P.cm_thr < 0.0f;
+                for (int q = 0; q < G && !any; ++q) {
+                    float iw = __fsub_rn(fminf(x2[i], s_gtraw[4 * q + 2]), fmaxf(x1[i], s_gtraw[4 * q]));
+                    float ih = __fsub_rn(fminf(y2[i], s_gtraw[4 * q + 3]), fmaxf(y1[i], s_gtraw[4 * q + 1]));
+                    any = (iw > 0.0f) && (ih > 0.0f);
+                }
+                if (!any) continue;
+                float a1 = __fmul_rn(__fsub_rn(x2[i], x1[i]), __fsub_rn(y2[i], y1[i]));
+                float bi = 0.0f; int bg = 0;
+                for (int q = 0; q < G; ++q) {
+                    float qx1 = s_gtraw[4 * q], qy1 = s_gtraw[4 * q + 1], qx2 = s_gtraw[4 * q + 2], qy2 = s_gtraw[4 * q + 3];
+                    float ix1 = fmaxf(x1[i], qx1), iy1 = fmaxf(y1[i], qy1);
+                    float ix2 = fminf(x2[i], qx2), iy2 = fminf(y2[i], qy2);
+                    float iw = __fsub_rn(ix2, ix1); iw = iw < 0.0f ? 0.0f : iw;
+                    float ih = __fsub_rn(iy2, iy1); ih = ih < 0.0f ? 0.0f : ih;
+                    float inter = __fmul_rn(iw, ih);
+                    float a2 = __fmul_rn(__fsub_rn(qx2, qx1), __fsub_rn(qy2, qy1));
+                    float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
+                    float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-7f));
+                    if (q == 0 || iou > bi) { bi = iou; bg = q; }
+                }
+                if (bi > P.cm_thr) {
+                    int gc = s_gl[bg], pc = lab[i];
+                    if (gc >= 0 && gc < P.nc && pc >= 0 && pc < P.nc) atomicAdd(&s_cm[gc * P.nc + pc], 1);
+                    ++npos_thread;
+                }
+            }
+        }
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) npos_thread += __shfl_down_sync(0xffffffffu, npos_thread, d);
+    if (lane == 0 && npos_thread) atomicAdd(&s_npos, npos_thread);
+    // ---- ordered offsets: block scan, then the eight CTA totals through distributed shared memory
     int my_total;
-    block_excl_scan(cnt, my_total, s_warp);
+    const int excl = block_excl_scan(c, my_total, s_warp);
     if (tid == 0) s_ex = my_total;
     cluster.sync();
     int base = 0, all = 0;
@@ -275,92 +347,57 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
         all += v;
     }
     if (rank == 0 && tid == 0) P.n_cand[b] = all < P.cap ? all : P.cap;
-
-    // ---- pass 2: decode, CM matching on the raw boxes, ordered write of the survivors
-    int npos_thread = 0;
-    for (int gbase = g0; gbase < g1; gbase += K1_THREADS) {
-        const int g = gbase + tid;
-        const bool active = g < g1;
-        float best[VEC], x1[VEC], y1[VEC], x2[VEC], y2[VEC];
-        int lab[VEC];
-        int c = 0;
-        unsigned flags = 0;
-        if (active) {
-            dec.scores(g * VEC, best, lab);
-            dec.boxes(g * VEC, x1, y1, x2, y2);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                if (best[i] > P.conf) { flags |= 1u << i; ++c; }
-                if (G > 0) {
-                    // batch_bbox_iou (running_main_v2.py:68-94) against the unclamped GT copy
-                    float a1 = __fmul_rn(__fsub_rn(x2[i], x1[i]), __fsub_rn(y2[i], y1[i]));
-                    float bi = 0.0f; int bg = 0;
-                    for (int q = 0; q < G; ++q) {
-                        float qx1 = s_gtraw[4 * q], qy1 = s_gtraw[4 * q + 1], qx2 = s_gtraw[4 * q + 2], qy2 = s_gtraw[4 * q + 3];
-                        float ix1 = fmaxf(x1[i], qx1), iy1 = fmaxf(y1[i], qy1);
-                        float ix2 = fminf(x2[i], qx2), iy2 = fminf(y2[i], qy2);
-                        float iw = __fsub_rn(ix2, ix1); iw = iw < 0.0f ? 0.0f : iw;
-                        float ih = __fsub_rn(iy2, iy1); ih = ih < 0.0f ? 0.0f : ih;
-                        float inter = __fmul_rn(iw, ih);
-                        float a2 = __fmul_rn(__fsub_rn(qx2, qx1), __fsub_rn(qy2, qy1));
-                        float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
-                        float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-7f));
-                        if (q == 0 || iou > bi) { bi = iou; bg = q; }
-                    }
-                    if (bi > P.cm_thr) {
-                        int gc = s_gl[bg], pc = lab[i];
-                        if (gc >= 0 && gc < P.nc && pc >= 0 && pc < P.nc) atomicAdd(&s_cm[gc * P.nc + pc], 1);
-                        ++npos_thread;
-                    }
-                }
-            }
+    // confusion-matrix counts: rank 0 folds the eight CTAs' shared-memory histograms (DSMEM reads)
+    // and issues ONE global atomic per non-zero cell and image (512 CTAs hammering the same nine
+    // addresses serialised in L2 and dominated the first version of this kernel).
+    if (rank == 0) {
+        for (int i = tid; i < P.nc * P.nc; i += nthreads) {
+            int v = 0;
+            for (int r = 0; r < K1_CLUSTER; ++r) v += cluster.map_shared_rank(s_cm, r)[i];
+            if (v) atomicAdd(&P.cm[i], (unsigned long long)v);
         }
-        int tot;
-        int pos = base + block_excl_scan(c, tot, s_warp);
-        if (flags) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                if (!(flags & (1u << i))) continue;
-                if (pos < P.cap) {
-                    float bx1 = x1[i], by1 = y1[i], bx2 = x2[i], by2 = y2[i];
-                    if (P.clamp) {
-                        bx1 = fminf(fmaxf(bx1, 0.0f), P.img_w); bx2 = fminf(fmaxf(bx2, 0.0f), P.img_w);
-                        by1 = fminf(fmaxf(by1, 0.0f), P.img_h); by2 = fminf(fmaxf(by2, 0.0f), P.img_h);
-                    }
-                    size_t o = (size_t)b * P.cap + pos;
-                    P.cand_box[o] = make_float4(bx1, by1, bx2, by2);
-                    P.cand_score[o] = best[i];
-                    P.cand_label[o] = lab[i];
-                    P.cand_anchor[o] = g * VEC + i;
-                }
-                ++pos;
-            }
+        if (tid == 0) {
+            int v = 0;
+            for (int r = 0; r < K1_CLUSTER; ++r) v += *cluster.map_shared_rank(&s_npos, r);
+            P.cm_pos[b] = v;
         }
-        base += tot;
     }
-    // ---- flush confusion-matrix counts (integers: order-independent)
+    if (flags) {
+        int pos = base + excl;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) npos_thread += __shfl_down_sync(0xffffffffu, npos_thread, d);
-    if (lane == 0 && npos_thread) atomicAdd(&s_npos, npos_thread);
-    __syncthreads();
-    for (int i = tid; i < P.nc * P.nc; i += K1_THREADS)
-        if (s_cm[i]) atomicAdd(&P.cm[i], (unsigned long long)s_cm[i]);
-    if (tid == 0 && s_npos) atomicAdd(&P.cm_pos[b], s_npos);
-    cluster.sync();  // peers may still be reading s_ex through DSMEM
+        for (int i = 0; i < VEC; ++i) {
+            if (!(flags & (1u << i))) continue;
+            if (pos < P.cap) {
+                float bx1 = x1[i], by1 = y1[i], bx2 = x2[i], by2 = y2[i];
+                if (P.clamp) {
+                    bx1 = fminf(fmaxf(bx1, 0.0f), P.img_w); bx2 = fminf(fmaxf(bx2, 0.0f), P.img_w);
+                    by1 = fminf(fmaxf(by1, 0.0f), P.img_h); by2 = fminf(fmaxf(by2, 0.0f), P.img_h);
+                }
+                size_t o = (size_t)b * P.cap + pos;
+                P.cand_box[o] = make_float4(bx1, by1, bx2, by2);
+                P.cand_score[o] = best[i];
+                P.cand_label[o] = lab[i];
+                P.cand_anchor[o] = g * VEC + i;
+            }
+            ++pos;
+        }
+    }
+    cluster.sync();  // peers may still be reading s_ex / s_cm through DSMEM
 }
 
 template <int VEC>
-__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_THREADS)
+__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_MAX_THREADS, 1)
 decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
     L2Decoder<VEC> dec{P.head + (size_t)b * P.C * P.N, P.N, P.nc};
     k1_body<VEC>(P, dec, b);
 }
 
-__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_THREADS)
+template <int VEC>
+__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_MAX_THREADS, 1)
 decode_filter_l1_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
-    L1Decoder dec;
+    L1Decoder<VEC> dec;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         int HW = P.lvl_off[l + 1] - P.lvl_off[l];
@@ -372,7 +409,8 @@ decode_filter_l1_kernel(const __grid_constant__ K1Params P) {
     dec.off[3] = P.lvl_off[3];
     dec.R = P.reg_max;
     dec.nc = P.nc;
-    k1_body<1>(P, dec, b);
+    dec.N = P.N;
+    k1_body<VEC>(P, dec, b);
 }
 
 int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
@@ -388,10 +426,17 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
     P.gt_count = io.gt_count; P.gt_boxes = io.gt_boxes; P.gt_boxes_raw = io.gt_boxes_raw;
     P.gt_labels = io.gt_labels;
     P.cm = reinterpret_cast<unsigned long long *>(io.cm); P.cm_pos = io.cm_pos;
-    dim3 grid(K1_CLUSTER, p.batch), block(K1_THREADS);
+    auto block_for = [&](int vecw) {
+        int groups = (p.num_anchors + vecw - 1) / vecw;
+        int gp = (groups + K1_CLUSTER - 1) / K1_CLUSTER;
+        return (gp + 31) / 32 * 32;
+    };
+    dim3 grid(K1_CLUSTER, p.batch);
     if (p.layout == BT_LAYOUT_L2) {
         P.head = io.head; P.C = 4 + p.nc + p.nm;
         bool vec = (p.num_anchors % 4 == 0) && ((reinterpret_cast<uintptr_t>(io.head) & 15) == 0);
+        if (block_for(vec ? 4 : 1) > K1_MAX_THREADS) return BT_ERR_UNSUPPORTED;  // > 32768 (262144 vectorised) anchors
+        dim3 block(block_for(vec ? 4 : 1));
         if (vec) decode_filter_l2_kernel<4><<<grid, block, 0, s>>>(P);
         else decode_filter_l2_kernel<1><<<grid, block, 0, s>>>(P);
     } else {
@@ -406,7 +451,10 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
             off += W * H;
         }
         P.lvl_off[3] = off;
-        decode_filter_l1_kernel<<<grid, block, 0, s>>>(P);
+        if (block_for(1) <= K1_MAX_THREADS) decode_filter_l1_kernel<1><<<grid, dim3(block_for(1)), 0, s>>>(P);
+        else if (block_for(2) <= K1_MAX_THREADS) decode_filter_l1_kernel<2><<<grid, dim3(block_for(2)), 0, s>>>(P);
+        else if (block_for(4) <= K1_MAX_THREADS) decode_filter_l1_kernel<4><<<grid, dim3(block_for(4)), 0, s>>>(P);
+        else return BT_ERR_UNSUPPORTED;
     }
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }

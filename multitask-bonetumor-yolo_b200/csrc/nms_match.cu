@@ -14,7 +14,8 @@
 // B200 mapping: one 1024-thread CTA per image.  The sorted candidate list is consumed in chunks
 // of 64: (A) the chunk is tested against the boxes kept so far (kept list staged in shared
 // memory, 16 threads per candidate, warp ballot to merge), (B) a 64x64 intra-chunk suppression
-// bitmask is built with warp ballots, (C) one thread sweeps the bitmask.  Because keeps are
+// bitmask is built with warp ballots, (C) one warp sweeps the bitmask as a fixpoint (rows in
+// registers, warp-wide OR reductions) instead of one dependent load per keep.  Because keeps are
 // emitted in score order, `[:TOP_K]` is an early exit: at most max_det * M IoUs are evaluated
 // instead of M^2/2, which is what makes the 30k-candidate configuration tractable.
 #include "common.cuh"
@@ -53,6 +54,8 @@ struct K2Params {
     // accumulators of the mask kernel, zeroed here
     int32_t *strip_done, *acc, *inst_area, *inst_inter;
     int smem_keys;  // number of 64-bit slots in the shared key region
+    int win;        // sorted-candidate window staged in shared memory (multiple of NMS_CHUNK)
+    int centre_cull; // iou_thres >= 0.55: a pair can only suppress if the later box's centre lies in the earlier box
 };
 
 __device__ __forceinline__ uint32_t desc_key(float s) {
@@ -65,9 +68,16 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
 
 // i = earlier (kept) box, j = later candidate; operand order of std::max/std::min as in
 // torchvision's nms_kernel_impl so NaN coordinates behave identically.
+//
+// centre_cull: IoU > 0.5 means the intersection covers more than half of EACH box, hence contains
+// each box's centre.  With iou_thres >= 0.55 (margin >> fp32 rounding of the IoU) a pair whose
+// later centre (cxj, cyj) is outside the earlier box can be skipped without evaluating the IoU;
+// every pair that is evaluated uses the exact expression, so the keep set does not change.
 __device__ __forceinline__ bool suppresses(const float4 &bi, float ai, int li, const float4 &bj, float aj, int lj,
-                                           float thr_up, int early_out, int class_mode) {
+                                           float thr_up, int early_out, int class_mode, int centre_cull = 0,
+                                           float cxj = 0.0f, float cyj = 0.0f) {
     if (class_mode == BT_CLASS_AWARE && li != lj) return false;
+    if (centre_cull && !(cxj >= bi.x && cxj <= bi.z && cyj >= bi.y && cyj <= bi.w)) return false;
     float xx1 = (bi.x < bj.x) ? bj.x : bi.x;
     float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
     float xx2 = (bj.z < bi.z) ? bj.z : bi.z;
@@ -97,14 +107,13 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
 
     // ---- shared-memory carve-up
     unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem_raw);          // [smem_keys]
-    float4 *s_kbox = reinterpret_cast<float4 *>(s_keys + P.smem_keys);                       // [K]
-    float4 *s_cbox = s_kbox + K;                                                             // [64]
-    float *s_karea = reinterpret_cast<float *>(s_cbox + NMS_CHUNK);                          // [K]
-    float *s_carea = s_karea + K;                                                            // [64]
-    int *s_klabel = reinterpret_cast<int *>(s_carea + NMS_CHUNK);                            // [K]
+    float4 *s_kbox = reinterpret_cast<float4 *>(s_keys + P.smem_keys);                       // [K]   kept boxes
+    float4 *s_sbox = s_kbox + K;                                                             // [win] sorted boxes (window)
+    float *s_karea = reinterpret_cast<float *>(s_sbox + P.win);                              // [K]
+    float *s_sarea = s_karea + K;                                                            // [win]
+    int *s_klabel = reinterpret_cast<int *>(s_sarea + P.win);                                // [K]
     int *s_kidx = s_klabel + K;                                                              // [K]
-    int *s_clabel = s_kidx + K;                                                              // [64]
-    int *s_cidx = s_clabel + NMS_CHUNK;                                                      // [64]
+    int *s_slabel = s_kidx + K;                                                              // [win]
     __shared__ unsigned int s_mask32[NMS_CHUNK * 2];
     __shared__ unsigned int s_supA[2];
     __shared__ unsigned long long s_keepm;
@@ -143,38 +152,45 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             __syncthreads();
         }
 
-    // ---- 2. chunked greedy NMS
+    // ---- 2. chunked greedy NMS over the sorted list, staged through shared memory in windows
     int nkept = 0;
     for (int c0 = 0; c0 < M && nkept < K; c0 += NMS_CHUNK) {
         const int n_in = min(NMS_CHUNK, M - c0);
-        if (tid < NMS_CHUNK) {
-            if (tid < n_in) {
-                int idx = (int)(unsigned)keys[c0 + tid];
+        const int w0 = (c0 / P.win) * P.win;      // window holding this chunk (win is a multiple of 64)
+        if (c0 == w0) {
+            // gather the next window of sorted candidates: boxes (class-offset if asked), areas, labels
+            const int wn = min(P.win, M - w0);
+            for (int t = tid; t < wn; t += K2_THREADS) {
+                const int idx = (int)(unsigned)keys[w0 + t];
                 float4 bx = cbox[idx];
-                int lb = clabel[idx];
+                const int lb = clabel[idx];
                 if (P.class_mode == BT_CLASS_OFFSET) {
-                    float off = __fmul_rn((float)lb, P.max_wh);
+                    const float off = __fmul_rn((float)lb, P.max_wh);
                     bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
                     bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
                 }
-                s_cbox[tid] = bx;
-                s_carea[tid] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-                s_clabel[tid] = lb;
-                s_cidx[tid] = idx;
+                s_sbox[t] = bx;
+                s_sarea[t] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+                s_slabel[t] = lb;
             }
         }
         if (tid < 2) s_supA[tid] = 0;
         __syncthreads();
+        const float4 *cb = s_sbox + (c0 - w0);
+        const float *ca = s_sarea + (c0 - w0);
+        const int *cl = s_slabel + (c0 - w0);
         // (A) chunk vs boxes kept so far: 16 threads per candidate
         {
             const int ci = tid >> 4, sub = tid & 15;
             bool f = false;
             if (ci < n_in) {
-                const float4 bj = s_cbox[ci];
-                const float aj = s_carea[ci];
-                const int lj = s_clabel[ci];
+                const float4 bj = cb[ci];
+                const float aj = ca[ci];
+                const int lj = cl[ci];
+                const float cxj = __fmul_rn(__fadd_rn(bj.x, bj.z), 0.5f), cyj = __fmul_rn(__fadd_rn(bj.y, bj.w), 0.5f);
                 for (int j = sub; j < nkept; j += 16)
-                    f |= suppresses(s_kbox[j], s_karea[j], s_klabel[j], bj, aj, lj, P.thr_up, P.early_out, P.class_mode);
+                    f |= suppresses(s_kbox[j], s_karea[j], s_klabel[j], bj, aj, lj, P.thr_up, P.early_out, P.class_mode,
+                                    P.centre_cull, cxj, cyj);
             }
             unsigned m = __ballot_sync(0xffffffffu, f);
             if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
@@ -185,36 +201,54 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             const int q = r * K2_THREADS + tid;
             const int i = q >> 6, j = q & 63;
             bool f = false;
-            if (j > i && j < n_in)
-                f = suppresses(s_cbox[i], s_carea[i], s_clabel[i], s_cbox[j], s_carea[j], s_clabel[j], P.thr_up,
-                               P.early_out, P.class_mode);
+            if (j > i && j < n_in) {
+                const float4 bj = cb[j];
+                f = suppresses(cb[i], ca[i], cl[i], bj, ca[j], cl[j], P.thr_up, P.early_out, P.class_mode, P.centre_cull,
+                               __fmul_rn(__fadd_rn(bj.x, bj.z), 0.5f), __fmul_rn(__fadd_rn(bj.y, bj.w), 0.5f));
+            }
             unsigned m = __ballot_sync(0xffffffffu, f);
             if (lane == 0) s_mask32[i * 2 + (j >> 5)] = m;
         }
         __syncthreads();
-        // (C) serial sweep over the chunk
-        if (tid == 0) {
-            unsigned long long valid = (n_in == 64) ? ~0ull : ((1ull << n_in) - 1ull);
-            unsigned long long alive = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
+        // (C) warp-level suppression sweep as a fixpoint: a candidate no undecided earlier candidate
+        // can suppress is final; its row removes its victims.  Resolves sparse chunks in 1-3 rounds
+        // instead of one dependent shared-memory load per keep.
+        if (wid == 0) {
+            const unsigned long long row_a = ((unsigned long long)s_mask32[lane * 2 + 1] << 32) | s_mask32[lane * 2];
+            const unsigned long long row_b = ((unsigned long long)s_mask32[(lane + 32) * 2 + 1] << 32) | s_mask32[(lane + 32) * 2];
+            const unsigned long long valid = (n_in == 64) ? ~0ull : ((1ull << n_in) - 1ull);
+            unsigned long long und = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
             unsigned long long keepm = 0ull;
-            int room = K - nkept, cnt = 0;
-            while (alive && cnt < room) {
-                int j = __ffsll((long long)alive) - 1;
-                keepm |= 1ull << j;
-                ++cnt;
-                unsigned long long row = ((unsigned long long)s_mask32[j * 2 + 1] << 32) | s_mask32[j * 2];
-                alive &= ~(row | (1ull << j));
+            while (und) {
+                const bool ua = (und >> lane) & 1ull, ub = (und >> (lane + 32)) & 1ull;
+                const unsigned long long r = (ua ? row_a : 0ull) | (ub ? row_b : 0ull);
+                const unsigned long long S = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(r >> 32)) << 32) |
+                                             __reduce_or_sync(0xffffffffu, (unsigned)r);
+                const unsigned long long def = und & ~S;
+                keepm |= def;
+                const bool da = (def >> lane) & 1ull, db = (def >> (lane + 32)) & 1ull;
+                const unsigned long long d = (da ? row_a : 0ull) | (db ? row_b : 0ull);
+                const unsigned long long Dm = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(d >> 32)) << 32) |
+                                              __reduce_or_sync(0xffffffffu, (unsigned)d);
+                und &= ~(def | Dm);
             }
-            s_keepm = keepm;
+            // [:TOP_K]: only the first `room` keeps survive (later ones cannot affect earlier ones)
+            int room = K - nkept;
+            if (__popcll(keepm) > room) {
+                unsigned long long t = keepm, kept = 0ull;
+                for (int i = 0; i < room; ++i) { unsigned long long low = t & (~t + 1ull); kept |= low; t ^= low; }
+                keepm = kept;
+            }
+            if (lane == 0) s_keepm = keepm;
         }
         __syncthreads();
         const unsigned long long keepm = s_keepm;
         if (tid < NMS_CHUNK && ((keepm >> tid) & 1ull)) {
             int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
-            s_kbox[slot] = s_cbox[tid];
-            s_karea[slot] = s_carea[tid];
-            s_klabel[slot] = s_clabel[tid];
-            s_kidx[slot] = s_cidx[tid];
+            s_kbox[slot] = cb[tid];
+            s_karea[slot] = ca[tid];
+            s_klabel[slot] = cl[tid];
+            s_kidx[slot] = (int)(unsigned)keys[c0 + tid];
         }
         nkept += __popcll(keepm);
         __syncthreads();
@@ -238,15 +272,15 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             P.det_anchor[(size_t)b * K + k] = -1;
         }
     }
-    for (int q = tid; q < K * P.nm; q += K2_THREADS) {
-        int k = q / P.nm, m = q - k * P.nm;
+    for (int q = tid; q < K * 32; q += K2_THREADS) {   // nm == 32 (validated by check_params)
+        int k = q >> 5, m = q & 31;
         float v = 0.0f;
         if (k < nkept) {
             int a = canchor[s_kidx[k]];
             v = (P.layout == BT_LAYOUT_L2) ? __ldg(P.head + ((size_t)b * P.C + 4 + P.nc + m) * P.N + a)
                                            : __ldg(P.coeffs + ((size_t)b * P.nm + m) * P.N + a);
         }
-        P.det_coeff[((size_t)b * K + k) * P.nm + m] = v;
+        P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
     }
 
     // ---- 4. COCOeval.evaluateImg for every (class, area range, IoU threshold)
@@ -263,8 +297,6 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
     int *s_dl = s_klabel;                                   // det labels (already there, K entries)
     __shared__ int s_gl[32];
     __shared__ unsigned s_gign[BT_NUM_AREA];
-    __shared__ float s_maxiou_f[1];                          // placeholder to keep layout explicit
-    (void)s_maxiou_f;
     float *s_maxiou = s_karea;                               // [K] reuse: max IoU over same-class GT (as float of double, rounded up)
     int *s_list = s_kidx;                                    // [K] reuse: compacted list of dets that can match anything
     __shared__ int s_nlist;
@@ -382,10 +414,9 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
     }
 }
 
-size_t k2_smem_bytes(const BtParams &p, int smem_keys) {
+size_t k2_smem_bytes(const BtParams &p, int smem_keys, int win) {
     size_t K = (size_t)p.max_det;
-    return (size_t)smem_keys * 8 + (K + NMS_CHUNK) * sizeof(float4) + (K + NMS_CHUNK) * sizeof(float) +
-           (2 * K + 2 * NMS_CHUNK) * sizeof(int);
+    return (size_t)smem_keys * 8 + (K + win) * sizeof(float4) + (K + win) * sizeof(float) + (2 * K + win) * sizeof(int);
 }
 
 int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
@@ -413,7 +444,12 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     int keys = next_pow2(P.cap) < SORT_SMEM_MAX ? next_pow2(P.cap) : SORT_SMEM_MAX;
     if (keys < need_coco) keys = need_coco;
     P.smem_keys = keys;
-    size_t smem = k2_smem_bytes(p, keys);
+    // window of sorted candidates kept in shared memory: the whole list when it is small
+    int win = (P.cap + NMS_CHUNK - 1) / NMS_CHUNK * NMS_CHUNK;
+    if (win > 4096) win = 4096;
+    P.win = win;
+    P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
+    size_t smem = k2_smem_bytes(p, keys, win);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(nms_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
