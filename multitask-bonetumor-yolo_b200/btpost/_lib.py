@@ -9,7 +9,10 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libbtpost.so"
+import os
+
+# BTPOST_LIB lets developer scripts load the instrumented debug build (scripts/phase_timing.py)
+LIB_PATH = Path(os.environ.get("BTPOST_LIB", _HERE / "libbtpost.so"))
 
 BT_NUM_AREA = 4
 BT_MAX_IOU_THRS = 16

@@ -71,6 +71,18 @@ static int check_stage3(const BtParams *p, const BtIO *io) {
 
 using namespace bt;
 
+#ifdef BT_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[3][16];
+extern "C" BTPOST_API int btpost_debug_phase_cycles(unsigned long long *out48, int reset) {
+    if (cudaMemcpyFromSymbol(out48, g_phase_cycles, sizeof(unsigned long long) * 48) != cudaSuccess) return BT_ERR_CUDA;
+    if (reset) {
+        static unsigned long long zeros[48];
+        if (cudaMemcpyToSymbol(g_phase_cycles, zeros, sizeof(zeros)) != cudaSuccess) return BT_ERR_CUDA;
+    }
+    return BT_OK;
+}
+#endif
+
 extern "C" {
 
 int btpost_version(void) { return BTPOST_VERSION; }

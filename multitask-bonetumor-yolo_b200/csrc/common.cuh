@@ -9,11 +9,44 @@
 #error "libbtpost is written for sm_100a (B200) only"
 #endif
 
+// Optional per-phase cycle accounting (debug builds only: make dbg).  Thread 0 of every CTA adds the
+// cycles it spent between marks into a global table read back by btpost_debug_phase_cycles().
+#ifdef BT_PHASE_TIMING
+extern __device__ unsigned long long g_phase_cycles[3][16];
+#define BT_PHASE_INIT() long long _pt = clock64()
+#define BT_PHASE_MARK(kern, idx)                                                           \
+    do {                                                                                   \
+        if (threadIdx.x == 0) {                                                            \
+            long long _n = clock64();                                                      \
+            atomicAdd(&g_phase_cycles[kern][idx], (unsigned long long)(_n - _pt));         \
+            _pt = _n;                                                                      \
+        }                                                                                  \
+    } while (0)
+#else
+#define BT_PHASE_INIT() do {} while (0)
+#define BT_PHASE_MARK(kern, idx) do {} while (0)
+#endif
+
 namespace bt {
 
 // sigmoid(x) > 0.5 in fp32 (src/running_main_v2.py:702-703, src/test_model.py:85) holds exactly
 // for x > 1.5 * 2^-24 (pinned against torch in tests/golden/make_golden.py).
 __device__ __forceinline__ bool sigmoid_gt_half(float x) { return x > 8.940696716308594e-08f; }
+
+// Crop region of a detection at prototype resolution: pixels with r>=y1 & r<y2 & c>=x1 & c<x2
+// on the box scaled by proto/img (Ultralytics crop_mask).  Returns false for an empty region.
+__device__ __forceinline__ bool crop_region(const float *o, int crop, float rx, float ry, int PW, int PH, int &r_lo,
+                                            int &r_hi, int &c_lo, int &c_hi) {
+    r_lo = 0; r_hi = PH - 1; c_lo = 0; c_hi = PW - 1;
+    if (!crop) return true;
+    float x1 = __fmul_rn(o[0], rx), y1 = __fmul_rn(o[1], ry), x2 = __fmul_rn(o[2], rx), y2 = __fmul_rn(o[3], ry);
+    if (!((x1 == x1) && (y1 == y1) && (x2 == x2) && (y2 == y2))) return false;
+    c_lo = max(0, (int)ceilf(fmaxf(x1, -1.0f)));
+    r_lo = max(0, (int)ceilf(fmaxf(y1, -1.0f)));
+    c_hi = min(PW - 1, (int)ceilf(fminf(x2, (float)PW + 1.0f)) - 1);
+    r_hi = min(PH - 1, (int)ceilf(fminf(y2, (float)PH + 1.0f)) - 1);
+    return c_lo <= c_hi && r_lo <= r_hi;
+}
 
 // Workspace carve-up (all offsets 256-byte aligned).
 struct Workspace {
@@ -24,6 +57,7 @@ struct Workspace {
     unsigned long long *sort_keys;  // [B, cap_pow2] (only used when the list exceeds shared memory)
     int32_t *strip_done;  // [B] strips finished per image (mask kernel)
     int32_t *acc;         // [B, 8] per-image int counters: seg inter,P,G ; uni inter,P,G
+    short4 *det_region;   // [B, K] crop region of each kept detection at prototype resolution (r_lo, r_hi, c_lo, c_hi)
     size_t bytes;
 };
 
@@ -56,6 +90,7 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.sort_keys = reinterpret_cast<unsigned long long *>(take(B * (size_t)next_pow2((int)cap) * 8));
     w.strip_done = reinterpret_cast<int32_t *>(take(B * sizeof(int32_t)));
     w.acc = reinterpret_cast<int32_t *>(take(B * 8 * sizeof(int32_t)));
+    w.det_region = reinterpret_cast<short4 *>(take(B * (size_t)p->max_det * sizeof(short4)));
     w.bytes = off;
     return w;
 }

@@ -385,8 +385,11 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
     cluster.sync();  // peers may still be reading s_ex / s_cm through DSMEM
 }
 
-template <int VEC>
-__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_MAX_THREADS, 1)
+// MAXT = 320: blocks of <= 320 threads, at least 4 resident per SM so that the 8 x B CTAs of a
+// 64-image batch form a single wave (ncu r01c: 64 registers -> 3 CTAs/SM -> a second wave doubled
+// the kernel time).  MAXT = 1024: large anchor counts.
+template <int VEC, int MAXT>
+__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(MAXT, MAXT <= 320 ? 4 : 1)
 decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
     L2Decoder<VEC> dec{P.head + (size_t)b * P.C * P.N, P.N, P.nc};
@@ -437,8 +440,11 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
         bool vec = (p.num_anchors % 4 == 0) && ((reinterpret_cast<uintptr_t>(io.head) & 15) == 0);
         if (block_for(vec ? 4 : 1) > K1_MAX_THREADS) return BT_ERR_UNSUPPORTED;  // > 32768 (262144 vectorised) anchors
         dim3 block(block_for(vec ? 4 : 1));
-        if (vec) decode_filter_l2_kernel<4><<<grid, block, 0, s>>>(P);
-        else decode_filter_l2_kernel<1><<<grid, block, 0, s>>>(P);
+        const bool small = block.x <= 320;
+        if (vec && small) decode_filter_l2_kernel<4, 320><<<grid, block, 0, s>>>(P);
+        else if (vec) decode_filter_l2_kernel<4, 1024><<<grid, block, 0, s>>>(P);
+        else if (small) decode_filter_l2_kernel<1, 320><<<grid, block, 0, s>>>(P);
+        else decode_filter_l2_kernel<1, 1024><<<grid, block, 0, s>>>(P);
     } else {
         P.C = 4 * p.reg_max + p.nc; P.reg_max = p.reg_max;
         int off = 0;

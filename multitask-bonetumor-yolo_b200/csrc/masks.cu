@@ -34,7 +34,8 @@ constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int NM = 32;
 constexpr int CHUNK = 32;        // detections per M2 chunk
 constexpr int CF_PITCH = NM + 1; // coefficient row pitch in shared memory (bank-conflict free)
-constexpr int SCR_CAP = 3072;    // scratch pixels per M2 batch (+ one maximal piece of slack)
+constexpr int SCR_CAP = 2048;    // scratch pixels per M2 batch (+ one maximal piece of slack)
+constexpr int SCR_GRP = SCR_CAP / 4;
 
 struct K3Params {
     int B, S_h, S_w, PH, PW, R, K, crop, gt_f32, nstrips;
@@ -42,6 +43,7 @@ struct K3Params {
     float bias;
     const float *protos, *proj_weight, *dets, *det_coeff;
     const int32_t *det_count;
+    const short4 *det_region;
     const void *masks_gt;
     int32_t *strip_done, *acc, *inst_area, *inst_inter;
     long long *seg_cnt4, *uni_cnt4, *seg_img3, *uni_img3;
@@ -49,7 +51,7 @@ struct K3Params {
     uint8_t *seg_mask, *uni_mask;
     float *seg_logits;
     // shared-memory offsets (bytes)
-    int off_lm, off_scr, off_gtrow, off_gtc, off_m1c, off_unc, off_list, off_cf, wpr;
+    int off_lm, off_scr, off_gtrow, off_gtc, off_m1c, off_unc, off_list, off_cf, off_reg, wpr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,21 +127,6 @@ __device__ __forceinline__ unsigned cell_valid(int ci, int cj, int S_h, int S_w)
     return m;
 }
 
-// Crop region of a detection at prototype resolution: pixels with r>=y1 & r<y2 & c>=x1 & c<x2
-// on the box scaled by proto/img (Ultralytics crop_mask).  Returns false for an empty region.
-__device__ __forceinline__ bool crop_region(const float *o, int crop, float rx, float ry, int PW, int PH, int &r_lo,
-                                            int &r_hi, int &c_lo, int &c_hi) {
-    r_lo = 0; r_hi = PH - 1; c_lo = 0; c_hi = PW - 1;
-    if (!crop) return true;
-    float x1 = __fmul_rn(o[0], rx), y1 = __fmul_rn(o[1], ry), x2 = __fmul_rn(o[2], rx), y2 = __fmul_rn(o[3], ry);
-    if (!((x1 == x1) && (y1 == y1) && (x2 == x2) && (y2 == y2))) return false;
-    c_lo = max(0, (int)ceilf(fmaxf(x1, -1.0f)));
-    r_lo = max(0, (int)ceilf(fmaxf(y1, -1.0f)));
-    c_hi = min(PW - 1, (int)ceilf(fminf(x2, (float)PW + 1.0f)) - 1);
-    r_hi = min(PH - 1, (int)ceilf(fminf(y2, (float)PH + 1.0f)) - 1);
-    return c_lo <= c_hi && r_lo <= r_hi;
-}
-
 // TPW / TR > 0: compile-time prototype width / strip height (shared-memory strides become
 // immediates); 0: run-time values.
 template <int TPW, int TR>
@@ -175,6 +162,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     uint32_t *s_unc = reinterpret_cast<uint32_t *>(smem + P.off_unc);          // [R+1][PW+1]
     unsigned short *s_list = reinterpret_cast<unsigned short *>(smem + P.off_list);  // [K]
     float *s_cf = reinterpret_cast<float *>(smem + P.off_cf);                  // [CHUNK][CF_PITCH]
+    short4 *s_reg = reinterpret_cast<short4 *>(smem + P.off_reg);              // [K] crop regions (from the NMS kernel)
     const int wpr = P.wpr, tp = wpr + 1;
 
     // ---- strip geometry
@@ -188,6 +176,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     const int y_hi = (ci_hi == PH - 1) ? S_h : 4 * (ci_hi + 1) + 2;
     const int nyrows = y_hi - y_lo;
 
+    BT_PHASE_INIT();
     // ---- (a) kick off the prototype strip: one bulk async copy per channel
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -202,51 +191,88 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
         bulk_g2s(s_pro + (size_t)lane * CS, src, bytes, &s_bar);
     }
 
-    // ---- (b) overlap with the copies: weights, tiles, GT bits, detection list
+    // ---- (b) overlap with the copies.  All global loads of the set-up are issued first (GT mask
+    // words, crop regions written by the NMS kernel) so that their latencies overlap instead of
+    // chaining (phase counters r01c: 29 % of the CTA time sat in this block).
+    constexpr int GT_PER_THREAD = 2, REG_PER_THREAD = 2;
+    uint4 gtv[GT_PER_THREAD][2];
+    short4 regv[REG_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < GT_PER_THREAD; ++u) {
+        const int q = tid + u * K3_THREADS;
+        gtv[u][0] = gtv[u][1] = make_uint4(0, 0, 0, 0);
+        if (!P.gt_f32 && q < nyrows * wpr) {
+            const int yr = q / wpr, w = q - yr * wpr;
+            const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
+                                                             ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
+            gtv[u][0] = __ldg(g); gtv[u][1] = __ldg(g + 1);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < REG_PER_THREAD; ++u) {
+        const int k = tid + u * K3_THREADS;
+        regv[u] = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
+    }
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
     if (tid == 0) s_nlist = 0;
     for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) { s_m1c[i] = 0; s_unc[i] = 0; }
     for (int q = tid; q < nyrows * tp; q += K3_THREADS) {
         const int yr = q / tp, w = q - yr * tp;
-        uint32_t bits = 0;
-        if (w < wpr) {
-            const size_t base = ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32;
-            if (P.gt_f32) {
-                const float4 *g = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) + base);
+        if (w == wpr) s_gtrow[q] = 0;   // pad word
+    }
+    auto pack_u8 = [](const uint4 &v, int half) {
+        uint32_t wv[4] = {v.x, v.y, v.z, v.w}, bits = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 v = __ldg(g + i);
-                    bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
-                            ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
-                }
-            } else {
-                const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) + base);
+        for (int j = 0; j < 4; ++j) {
+            uint32_t x = wv[j];   // byte != 0 -> bit: fold each byte to its low bit, then gather the four low bits
+            x = (x | (x >> 4)) & 0x0f0f0f0fu;
+            x = (x | (x >> 2)) & 0x03030303u;
+            x = (x | (x >> 1)) & 0x01010101u;
+            bits |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (16 * half + 4 * j);
+        }
+        return bits;
+    };
+    if (!P.gt_f32) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    uint4 v = __ldg(g + i);
-                    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // byte != 0 -> bit: fold each byte to its low bit, then gather the four low bits
-                        uint32_t x = wv[j];
-                        x = (x | (x >> 4)) & 0x0f0f0f0fu;
-                        x = (x | (x >> 2)) & 0x03030303u;
-                        x = (x | (x >> 1)) & 0x01010101u;
-                        bits |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (16 * i + 4 * j);
-                    }
-                }
+        for (int u = 0; u < GT_PER_THREAD; ++u) {
+            const int q = tid + u * K3_THREADS;
+            if (q < nyrows * wpr) {
+                const int yr = q / wpr, w = q - yr * wpr;
+                s_gtrow[yr * tp + w] = pack_u8(gtv[u][0], 0) | pack_u8(gtv[u][1], 1);
             }
         }
-        s_gtrow[q] = bits;
+        for (int q = tid + GT_PER_THREAD * K3_THREADS; q < nyrows * wpr; q += K3_THREADS) {   // very wide images
+            const int yr = q / wpr, w = q - yr * wpr;
+            const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
+                                                             ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
+            s_gtrow[yr * tp + w] = pack_u8(__ldg(g), 0) | pack_u8(__ldg(g + 1), 1);
+        }
+    } else {
+        for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
+            const int yr = q / wpr, w = q - yr * wpr;
+            const float4 *g = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) +
+                                                               ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 v = __ldg(g + i);
+                bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
+                        ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
+            }
+            s_gtrow[yr * tp + w] = bits;
+        }
     }
-    const int D = min(P.det_count[b], K);
     __syncthreads();
-    for (int k = tid; k < D; k += K3_THREADS) {
-        int r_lo, r_hi, c_lo, c_hi;
-        bool ok = crop_region(P.dets + ((size_t)b * K + k) * 6, P.crop, P.rx, P.ry, PW, PH, r_lo, r_hi, c_lo, c_hi);
-        ok = ok && max(r_lo - 1, ci_lo) <= min(r_hi, ci_hi);
+    // detection list of the strip (order is irrelevant: OR and integer adds commute)
+    auto consider = [&](int k, const short4 &rg) {
+        if (k >= K) return;
+        s_reg[k] = rg;
+        const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
         if (ok) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)k;
-    }
+    };
+#pragma unroll
+    for (int u = 0; u < REG_PER_THREAD; ++u) consider(tid + u * K3_THREADS, regv[u]);
+    for (int k = tid + REG_PER_THREAD * K3_THREADS; k < K; k += K3_THREADS) consider(k, __ldg(P.det_region + (size_t)b * K + k));
     // GT cells from the row bits (bit x of output row y  ->  bit ry*4+rx of cell (ci, cj))
     for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
         const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
@@ -260,20 +286,40 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
         }
         s_gtc[q] = bits;
     }
+    __syncthreads();
+    // coefficients of the first chunk of listed detections: in flight during the TMA wait and M1
+    {
+        const int nch0 = min(CHUNK, s_nlist);
+        for (int q = tid; q < nch0 * NM; q += K3_THREADS) {
+            const int e = q >> 5, i = q & 31;
+            s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[e]) * NM + i);
+        }
+    }
 
+    BT_PHASE_MARK(2, 0);   // setup: tiles, GT bits, det list
     // ---- (c) wait for the prototypes
     mbar_wait(&s_bar, 0);
     __syncthreads();
+    BT_PHASE_MARK(2, 1);   // wait for TMA
 
-    // ---- (d) M1 projection: bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned)
-    for (int q = tid; q < nrows * PW; q += K3_THREADS) {
-        float acc = P.bias;
+    // ---- (d) M1 projection: bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).
+    // Four neighbouring pixels per thread: one 16-byte shared load per channel feeds four
+    // independent FMA chains (ILP 4, a quarter of the load / address instructions).
+    for (int q = tid; q < (nrows * PW) >> 2; q += K3_THREADS) {
+        float4 acc = make_float4(P.bias, P.bias, P.bias, P.bias);
+        const float4 *pp = reinterpret_cast<const float4 *>(s_pro) + q;
 #pragma unroll
-        for (int k = 0; k < NM; ++k) acc = __fmaf_rn(s_w[k], s_pro[k * CS + q], acc);
-        s_lm[q] = acc;
+        for (int k = 0; k < NM; ++k) {
+            const float4 v = pp[k * (CS >> 2)];
+            const float w = s_w[k];
+            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+        }
+        reinterpret_cast<float4 *>(s_lm)[q] = acc;
     }
     __syncthreads();
 
+    BT_PHASE_MARK(2, 2);   // M1 projection
     // ---- (e) M1 cells -> cell tile (+ optional logits)
     for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
         const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
@@ -295,6 +341,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
         }
     }
 
+    BT_PHASE_MARK(2, 3);   // M1 cells
     // ---- (f) M2 instance masks, CHUNK detections at a time, work flattened over the CTA
     const int nlist = s_nlist;
     for (int ch0 = 0; ch0 < nlist; ch0 += CHUNK) {
@@ -304,20 +351,21 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
         if (wid == 0) {
             int npx = 0, ncell = 0;
             if (lane < nch) {
-                const int k = s_list[ch0 + lane];
-                int r_lo, r_hi, c_lo, c_hi;
-                crop_region(P.dets + ((size_t)b * K + k) * 6, P.crop, P.rx, P.ry, PW, PH, r_lo, r_hi, c_lo, c_hi);
+                const short4 rg = s_reg[s_list[ch0 + lane]];
+                const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w;
                 const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
                 const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
                 const int ja = c_lo - 1;
                 const int pa = max(ja, 0), pb = min(c_hi + 1, PW - 1);
-                const int npr = pr_b - pr_a + 1, npc = pb - pa + 1;
+                // scratch rows are stored in aligned groups of 4 prototype columns
+                const int ga = pa >> 2, ngrp = (pb >> 2) - ga + 1;
+                const int npr = pr_b - pr_a + 1;
                 const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
                 s_rlo[lane] = r_lo; s_rhi[lane] = r_hi; s_clo[lane] = c_lo; s_chi[lane] = c_hi;
-                s_pra[lane] = pr_a; s_pa[lane] = pa; s_npc[lane] = npc; s_cia[lane] = ci_a; s_ncc[lane] = ncc;
-                s_inpc[lane] = 1.0f / (float)npc; s_incc[lane] = 1.0f / (float)ncc;
+                s_pra[lane] = pr_a; s_pa[lane] = 4 * ga; s_npc[lane] = 4 * ngrp; s_cia[lane] = ci_a; s_ncc[lane] = ncc;
+                s_inpc[lane] = 1.0f / (float)ngrp; s_incc[lane] = 1.0f / (float)ncc;
                 s_area[lane] = 0; s_inter[lane] = 0;
-                npx = npr * npc; ncell = ncr * ncc;
+                npx = npr * ngrp; ncell = ncr * ncc;
             }
             int ipx = npx, icell = ncell;
 #pragma unroll
@@ -328,16 +376,18 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
             s_pxoff[lane + 1] = ipx; s_celloff[lane + 1] = icell;
             if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
         }
-        for (int q = tid; q < nch * NM; q += K3_THREADS) {
-            const int e = q >> 5, i = q & 31;
-            s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[ch0 + e]) * NM + i);
-        }
+        if (ch0 > 0)   // chunk 0 was staged during the set-up
+            for (int q = tid; q < nch * NM; q += K3_THREADS) {
+                const int e = q >> 5, i = q & 31;
+                s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[ch0 + e]) * NM + i);
+            }
         __syncthreads();
-        const int nbatch = (s_pxoff[nch] + SCR_CAP - 1) / SCR_CAP;
+        BT_PHASE_MARK(2, 8);   // M2: tables + coefficient staging
+        const int nbatch = (s_pxoff[nch] + SCR_GRP - 1) / SCR_GRP;   // offsets count 4-pixel groups
         for (int bi = 0; bi < nbatch; ++bi) {
             // entries whose first scratch pixel falls into [bi*CAP, (bi+1)*CAP) form the batch
             if (wid == 0) {
-                const bool in = lane < nch && (s_pxoff[lane] / SCR_CAP) == bi;
+                const bool in = lane < nch && (s_pxoff[lane] / SCR_GRP) == bi;
                 const unsigned m = __ballot_sync(0xffffffffu, in);
                 if (lane == 0) { s_e0 = m ? (__ffs(m) - 1) : 0; s_e1 = m ? (32 - __clz(m)) : 0; }
             }
@@ -345,24 +395,35 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
             const int e0 = s_e0, e1 = s_e1;
             if (e1 > e0) {
                 const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
-                // cropped logits of every (detection, pixel) item of the batch
+                // cropped logits of every (detection, row, 4-pixel group) item of the batch
                 for (int q = tid; q < npx; q += K3_THREADS) {
                     int lo = e0, hi = e1;   // last entry with pxoff <= px0 + q
                     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= q) lo = mid; else hi = mid; }
                     const int e = lo, loc = q - (s_pxoff[e] - px0);
-                    const int npc = s_npc[e];
-                    const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), cc = loc - rr * npc;
-                    const int r = s_pra[e] + rr, c = s_pa[e] + cc;
-                    float acc = 0.0f;
-                    if (r >= s_rlo[e] && r <= s_rhi[e] && c >= s_clo[e] && c <= s_chi[e]) {
-                        const float *pp = s_pro + (r - p_lo) * PW + c;
+                    const int ngrp = s_npc[e] >> 2;
+                    const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), gg = loc - rr * ngrp;
+                    const int r = s_pra[e] + rr, c = s_pa[e] + 4 * gg;
+                    const int c_lo = s_clo[e], c_hi = s_chi[e];
+                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (r >= s_rlo[e] && r <= s_rhi[e] && c + 3 >= c_lo && c <= c_hi) {
+                        const float4 *pp = reinterpret_cast<const float4 *>(s_pro + (r - p_lo) * PW + c);
                         const float *cf = s_cf + e * CF_PITCH;
 #pragma unroll
-                        for (int i = 0; i < NM; ++i) acc = __fmaf_rn(cf[i], pp[i * CS], acc);
+                        for (int i = 0; i < NM; ++i) {
+                            const float4 v = pp[i * (CS >> 2)];
+                            const float w = cf[i];
+                            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+                            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+                        }
+                        if (c < c_lo || c > c_hi) acc.x = 0.0f;
+                        if (c + 1 < c_lo || c + 1 > c_hi) acc.y = 0.0f;
+                        if (c + 2 < c_lo || c + 2 > c_hi) acc.z = 0.0f;
+                        if (c + 3 < c_lo || c + 3 > c_hi) acc.w = 0.0f;
                     }
-                    s_scr[q] = acc;
+                    reinterpret_cast<float4 *>(s_scr)[q] = acc;
                 }
                 __syncthreads();
+                BT_PHASE_MARK(2, 9);   // M2: logits
                 const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
                 for (int q = tid; q < ncell; q += K3_THREADS) {
                     int lo = e0, hi = e1;
@@ -372,7 +433,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
                     const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
                     const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
                     const int pr_a = s_pra[e], pa = s_pa[e];
-                    const float *scr = s_scr + (s_pxoff[e] - px0);
+                    const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
                     const int r0 = max(ci, 0) - pr_a, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
                     const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
                     float unused[16];
@@ -389,6 +450,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
                 }
             }
             __syncthreads();
+            BT_PHASE_MARK(2, 10);  // M2: cells
         }
         if (tid < nch) {
             const int k = s_list[ch0 + tid];
@@ -398,6 +460,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     }
     __syncthreads();
 
+    BT_PHASE_MARK(2, 4);   // M2
     // ---- (g) integer counters of the strip + optional dense mask output
     int c5[5] = {0, 0, 0, 0, 0};  // seg inter, seg P, G, uni inter, uni P
     for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
@@ -438,6 +501,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
         for (int w = 0; w < K3_WARPS; ++w) v += s_red[w][tid];
         if (v) atomicAdd(&P.acc[b * 8 + tid], v);
     }
+    BT_PHASE_MARK(2, 5);   // counters + flush
     // ---- (h) the last strip of the image finalises Dice / IoU (test_model.py:15-23)
     __threadfence();
     __syncthreads();
@@ -476,7 +540,8 @@ static size_t k3_layout(K3Params &P, int R) {
     P.off_m1c = (int)off; off += celltile;
     P.off_unc = (int)off; off += celltile;
     P.off_list = (int)off; off += align_up((size_t)P.K * sizeof(unsigned short), 16);
-    P.off_cf = (int)off; off += (size_t)CHUNK * CF_PITCH * sizeof(float);
+    P.off_cf = (int)off; off += align_up((size_t)CHUNK * CF_PITCH * sizeof(float), 16);
+    P.off_reg = (int)off; off += align_up((size_t)P.K * sizeof(short4), 16);
     return off;
 }
 
@@ -496,7 +561,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.ry = (float)((double)p.proto_h / (double)p.img_h);
     P.bias = p.proj_bias;
     P.protos = io.protos; P.proj_weight = io.proj_weight; P.dets = io.dets; P.det_coeff = io.det_coeff;
-    P.det_count = io.det_count; P.masks_gt = io.masks_gt;
+    P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region;
     P.strip_done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;

@@ -55,6 +55,7 @@ struct K2Params {
     int32_t *strip_done, *acc, *inst_area, *inst_inter;
     int smem_keys;  // number of 64-bit slots in the shared key region
     int win;        // sorted-candidate window staged in shared memory (multiple of NMS_CHUNK)
+    int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
     int centre_cull; // iou_thres >= 0.55: a pair can only suppress if the later box's centre lies in the earlier box
 };
 
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
     __shared__ unsigned long long s_keepm;
     __shared__ int s_warpcnt[K2_WARPS];
 
+    BT_PHASE_INIT();
     // ---- zero the per-image accumulators the mask kernel adds into
     if (tid < 8) P.acc[b * 8 + tid] = 0;
     if (tid == 8) P.strip_done[b] = 0;
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             __syncthreads();
         }
 
+    BT_PHASE_MARK(1, 0);   // sort
     // ---- 2. chunked greedy NMS over the sorted list, staged through shared memory in windows
     int nkept = 0;
     for (int c0 = 0; c0 < M && nkept < K; c0 += NMS_CHUNK) {
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             unsigned m = __ballot_sync(0xffffffffu, f);
             if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
         }
+        BT_PHASE_MARK(1, 8);   // chunk: load + phase A
         // (B) intra-chunk 64x64 upper-triangular suppression bitmask
 #pragma unroll
         for (int r = 0; r < (NMS_CHUNK * NMS_CHUNK) / K2_THREADS; ++r) {
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             if (lane == 0) s_mask32[i * 2 + (j >> 5)] = m;
         }
         __syncthreads();
+        BT_PHASE_MARK(1, 9);   // chunk: phase B
         // (C) warp-level suppression sweep as a fixpoint: a candidate no undecided earlier candidate
         // can suppress is final; its row removes its victims.  Resolves sparse chunks in 1-3 rounds
         // instead of one dependent shared-memory load per keep.
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             if (lane == 0) s_keepm = keepm;
         }
         __syncthreads();
+        BT_PHASE_MARK(1, 10);  // chunk: phase C
         const unsigned long long keepm = s_keepm;
         if (tid < NMS_CHUNK && ((keepm >> tid) & 1ull)) {
             int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
@@ -254,6 +260,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
         __syncthreads();
     }
 
+    BT_PHASE_MARK(1, 1);   // NMS chunks
     // ---- 3. package kept detections (running_main_v2.py:818-839); zero-fill the padding
     if (tid == 0) P.det_count[b] = nkept;
     for (int k = tid; k < K; k += K2_THREADS) {
@@ -266,7 +273,13 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             o[5] = (float)clabel[idx];
             P.det_keep[(size_t)b * K + k] = idx;
             P.det_anchor[(size_t)b * K + k] = canchor[idx];
+            int r_lo, r_hi, c_lo, c_hi;
+            const float bb[4] = {bx.x, bx.y, bx.z, bx.w};
+            const bool ok = crop_region(bb, P.crop, P.rx, P.ry, P.PW, P.PH, r_lo, r_hi, c_lo, c_hi);
+            P.det_region[(size_t)b * K + k] = ok ? make_short4((short)r_lo, (short)r_hi, (short)c_lo, (short)c_hi)
+                                                 : make_short4(1, 0, 1, 0);
         } else {
+            P.det_region[(size_t)b * K + k] = make_short4(1, 0, 1, 0);
             o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.0f;
             P.det_keep[(size_t)b * K + k] = -1;
             P.det_anchor[(size_t)b * K + k] = -1;
@@ -283,6 +296,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
         P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
     }
 
+    BT_PHASE_MARK(1, 2);   // package
     // ---- 4. COCOeval.evaluateImg for every (class, area range, IoU threshold)
     if (P.dt_match == nullptr) return;
     __syncthreads();  // key region is free from here on: reuse it for the double-precision tables
@@ -449,6 +463,10 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     if (win > 4096) win = 4096;
     P.win = win;
     P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
+    P.crop = p.crop; P.PW = p.proto_w; P.PH = p.proto_h;
+    P.rx = (float)((double)p.proto_w / (double)p.img_w);
+    P.ry = (float)((double)p.proto_h / (double)p.img_h);
+    P.det_region = w.det_region;
     size_t smem = k2_smem_bytes(p, keys, win);
     static bool attr_set = false;
     if (!attr_set) {
