@@ -1,0 +1,206 @@
+"""Sweep-level metric state: what `on_validation_epoch_end` / `evaluate()` compute from the per-batch
+outputs (`/root/reference/src/running_main_v2.py:959-1177`, `evaluate_model.py:240-355`).
+
+Per batch the CUDA library leaves integer counters and per-detection COCO match bits on the device.
+`SweepState.add` appends them to device-resident buffers (no host sync).  At the end of the sweep:
+
+  * `all_reduce(group)` -- ONE `all_reduce(SUM)` of a packed int64 counter vector (confusion matrix,
+    pixel tp/fp/fn/tn, GT counts, image count) and one of an fp64 vector (sums of per-image Dice/IoU):
+    the only collective on the path (NCCL over NVLink on the GPU box, gloo in the CPU tests);
+  * `gather(group)` -- COCO AP is not a sum of counters (it needs the globally score-sorted record
+    list), so the compact per-detection records are all-gathered (padded to the largest shard);
+  * `compute()` -- COCOeval.accumulate + summarize on the gathered records.  The stable
+    global order pycocotools gets from concatenating images in order and a mergesort on -score is
+    reproduced with the sort key (score desc, global image index, rank in image), so the result does
+    not depend on how images were sharded.
+
+The aggregation runs as tensor ops on whatever device the state lives on (the GPU in production, the
+CPU in the gloo tests); it is epoch-end bookkeeping over a few MB, not part of the per-batch hot path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+AREA_NAMES = ("all", "small", "medium", "large")
+
+
+class SweepState:
+    def __init__(self, nc: int, num_thrs: int, iou_thrs, max_dets=(1, 10, 100), device="cpu"):
+        self.nc, self.T, self.A = nc, num_thrs, 4
+        self.iou_thrs = [float(t) for t in iou_thrs]
+        self.max_dets = tuple(max_dets)
+        self.device = torch.device(device)
+        self.reset()
+
+    def reset(self):
+        d = self.device
+        self.cm = torch.zeros(self.nc, self.nc, dtype=torch.int64, device=d)
+        self.seg_cnt4 = torch.zeros(4, dtype=torch.int64, device=d)
+        self.uni_cnt4 = torch.zeros(4, dtype=torch.int64, device=d)
+        self.n_images = torch.zeros(1, dtype=torch.int64, device=d)
+        self.npig = torch.zeros(self.A, self.nc, dtype=torch.int64, device=d)      # non-ignored GT per (area, class)
+        self.fsum = torch.zeros(4, dtype=torch.float64, device=d)                   # sum seg dice, seg iou, uni dice, uni iou
+        self._rec = []                                                              # per-batch record tensors
+
+    # ------------------------------------------------------------------ per batch
+    @torch.no_grad()
+    def add(self, out: dict, image_offset: int, accumulate_counters: bool = False):
+        """Append one batch.  `out` = PostProcessor.run(...) outputs (device tensors, padded).  The
+        library accumulates cm / seg_cnt4 / uni_cnt4 itself across calls, so by default they are
+        taken once at the end through `take_counters`; pass accumulate_counters=True when `out`
+        holds per-batch values (the oracle's layout)."""
+        dets, cnt = out["dets"], out["det_count"].long()
+        B, K, _ = dets.shape
+        valid = torch.arange(K, device=dets.device)[None, :] < cnt[:, None]                        # [B,K]
+        labels = dets[..., 5].long()
+        onehot = torch.nn.functional.one_hot(labels.clamp(0, self.nc - 1), self.nc) * valid[..., None]
+        class_rank = (onehot.cumsum(1) - onehot).gather(2, labels.clamp(0, self.nc - 1)[..., None])[..., 0]   # earlier same-class dets
+        img = (torch.arange(B, device=dets.device) + image_offset)[:, None].expand(B, K)
+        rank = torch.arange(K, device=dets.device)[None, :].expand(B, K)
+        matched = (out["dt_match"] > 0).permute(0, 3, 1, 2)                                         # [B,K,A,T]
+        ignored = (out["dt_ignore"] > 0).permute(0, 3, 1, 2)
+        self._rec.append({
+            "score": dets[..., 4][valid], "label": labels[valid], "img": img[valid], "rank": rank[valid],
+            "class_rank": class_rank[valid], "matched": matched[valid], "ignored": ignored[valid],
+        })
+        G = out["gt_labels"].shape[1]
+        gvalid = torch.arange(G, device=dets.device)[None, :] < out["gt_count"].long()[:, None]     # [B,G]
+        gl = out["gt_labels"].long()
+        inrange = gvalid & (gl >= 0) & (gl < self.nc)
+        keep = inrange[:, None, :] & ~(out["gt_ignore"] > 0)                                         # [B,A,G]
+        goh = torch.nn.functional.one_hot(gl.clamp(0, self.nc - 1), self.nc)                        # [B,G,nc]
+        self.npig += torch.einsum("bag,bgc->ac", keep.long(), goh.long())
+        self.n_images += B
+        self.fsum += torch.stack([out["seg_dice"].double().sum(), out["seg_iou"].double().sum(),
+                                  out["uni_dice"].double().sum(), out["uni_iou"].double().sum()])
+        if accumulate_counters:
+            self.cm += out["cm"].long(); self.seg_cnt4 += out["seg_cnt4"].long(); self.uni_cnt4 += out["uni_cnt4"].long()
+
+    @torch.no_grad()
+    def take_counters(self, out: dict):
+        """Copy the counters the library accumulated over the whole sweep (cm, seg_cnt4, uni_cnt4)."""
+        self.cm.copy_(out["cm"]); self.seg_cnt4.copy_(out["seg_cnt4"]); self.uni_cnt4.copy_(out["uni_cnt4"])
+
+    # ------------------------------------------------------------------ collectives
+    def _pack_i64(self):
+        return torch.cat([self.cm.flatten(), self.seg_cnt4, self.uni_cnt4, self.n_images, self.npig.flatten()])
+
+    def _unpack_i64(self, v):
+        n = self.nc * self.nc
+        self.cm = v[:n].view(self.nc, self.nc).clone(); self.seg_cnt4 = v[n:n + 4].clone()
+        self.uni_cnt4 = v[n + 4:n + 8].clone(); self.n_images = v[n + 8:n + 9].clone()
+        self.npig = v[n + 9:].view(self.A, self.nc).clone()
+
+    @torch.no_grad()
+    def all_reduce(self, group=None):
+        """The metric-counter all-reduce (north star: the only NCCL traffic on the path)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        v = self._pack_i64()
+        dist.all_reduce(v, group=group)
+        self._unpack_i64(v)
+        dist.all_reduce(self.fsum, group=group)
+
+    def _records(self):
+        if not self._rec:
+            z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=self.device)
+            return {"score": z(0, dt=torch.float32), "label": z(0, dt=torch.int64), "img": z(0, dt=torch.int64),
+                    "rank": z(0, dt=torch.int64), "class_rank": z(0, dt=torch.int64),
+                    "matched": z(0, self.A, self.T, dt=torch.bool), "ignored": z(0, self.A, self.T, dt=torch.bool)}
+        return {k: torch.cat([r[k] for r in self._rec]) for k in self._rec[0]}
+
+    @torch.no_grad()
+    def gather(self, group=None):
+        """All-gather of the ragged record lists (padded to the largest shard, then trimmed)."""
+        rec = self._records()
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            self._rec = [rec]
+            return
+        W = dist.get_world_size(group)
+        n = torch.tensor([rec["score"].shape[0]], dtype=torch.int64, device=self.device)
+        ns = [torch.zeros_like(n) for _ in range(W)]
+        dist.all_gather(ns, n, group=group)
+        ns = [int(x.item()) for x in ns]
+        cap = max(max(ns), 1)
+        out = {}
+        for k, t in rec.items():
+            pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=torch.uint8 if t.dtype == torch.bool else t.dtype, device=self.device)
+            pad[: t.shape[0]] = t.to(pad.dtype)
+            parts = [torch.zeros_like(pad) for _ in range(W)]
+            dist.all_gather(parts, pad, group=group)
+            cat = torch.cat([p[:m] for p, m in zip(parts, ns)])
+            out[k] = cat.bool() if t.dtype == torch.bool else cat
+        self._rec = [out]
+
+    # ------------------------------------------------------------------ epoch end
+    @torch.no_grad()
+    def compute(self) -> dict:
+        rec = self._records()
+        T, A, nc, M = self.T, self.A, self.nc, len(self.max_dets)
+        dev = self.device
+        # global stable order: score desc, then image index, then rank inside the image
+        key2 = rec["img"] * 65536 + rec["rank"]
+        order = torch.argsort(key2, stable=True)
+        order = order[torch.argsort(-rec["score"][order].double(), stable=True)]
+        rec = {k: v[order] for k, v in rec.items()}
+        rec_thrs = torch.linspace(0.0, 1.0, 101, dtype=torch.float64, device=dev)
+        precision = -torch.ones(T, 101, nc, A, M, dtype=torch.float64, device=dev)
+        recall = -torch.ones(T, nc, A, M, dtype=torch.float64, device=dev)
+        eps = torch.finfo(torch.float64).eps
+        for c in range(nc):
+            in_c = rec["label"] == c
+            for mi, md in enumerate(self.max_dets):
+                sel = in_c & (rec["class_rank"] < md)
+                mt, ig = rec["matched"][sel], rec["ignored"][sel]                 # [R,A,T]
+                tps = (mt & ~ig).permute(1, 2, 0).double().cumsum(-1)             # [A,T,R]
+                fps = (~mt & ~ig).permute(1, 2, 0).double().cumsum(-1)
+                R = tps.shape[-1]
+                for a in range(A):
+                    npig = int(self.npig[a, c].item())
+                    if npig == 0:
+                        continue
+                    if R == 0:
+                        recall[:, c, a, mi] = 0.0
+                        precision[:, :, c, a, mi] = 0.0
+                        continue
+                    rc = tps[a] / npig                                            # [T,R]
+                    pr = tps[a] / (fps[a] + tps[a] + eps)
+                    pr = torch.flip(torch.cummax(torch.flip(pr, [-1]), -1).values, [-1])   # right-to-left running max
+                    recall[:, c, a, mi] = rc[:, -1]
+                    idx = torch.searchsorted(rc.contiguous(), rec_thrs[None, :].expand(T, 101).contiguous(), right=False)
+                    q = torch.where(idx < R, pr.gather(1, idx.clamp(max=R - 1)), torch.zeros((), dtype=torch.float64, device=dev))
+                    precision[:, :, c, a, mi] = q
+
+        def mean(x):
+            x = x[x > -1]
+            return float(x.mean().item()) if x.numel() else -1.0
+
+        def thr_idx(v):
+            for i, t in enumerate(self.iou_thrs):
+                if abs(t - v) < 1e-6:
+                    return i
+            return None
+        res = {"map": mean(precision[:, :, :, 0, -1])}
+        for name, v in (("map_50", 0.5), ("map_75", 0.75)):
+            ti = thr_idx(v)
+            res[name] = mean(precision[ti, :, :, 0, -1]) if ti is not None else -1.0
+        for ai in (1, 2, 3):
+            res[f"map_{AREA_NAMES[ai]}"] = mean(precision[:, :, :, ai, -1])
+            res[f"mar_{AREA_NAMES[ai]}"] = mean(recall[:, :, ai, -1])
+        for mi, md in enumerate(self.max_dets):
+            res[f"mar_{md}"] = mean(recall[:, :, 0, mi])
+        res["map_per_class"] = [mean(precision[:, :, c, 0, -1]) for c in range(nc)]
+        res[f"mar_{self.max_dets[-1]}_per_class"] = [mean(recall[:, c, 0, -1]) for c in range(nc)]
+        n = max(int(self.n_images.item()), 1)
+        tp, fp, fn, tn = [int(v) for v in self.seg_cnt4.tolist()]
+        res.update({
+            "n_images": int(self.n_images.item()), "cm": self.cm.clone(),
+            "seg_f1": 2 * tp / (2 * tp + fp + fn) if (2 * tp + fp + fn) else 0.0,
+            "seg_precision": tp / (tp + fp) if (tp + fp) else 0.0, "seg_recall": tp / (tp + fn) if (tp + fn) else 0.0,
+            "seg_accuracy": (tp + tn) / max(tp + tn + fp + fn, 1),
+            "seg_dice": float(self.fsum[0].item()) / n, "seg_iou": float(self.fsum[1].item()) / n,
+            "uni_dice": float(self.fsum[2].item()) / n, "uni_iou": float(self.fsum[3].item()) / n,
+            "precision": precision, "recall": recall,
+        })
+        return res

@@ -239,6 +239,7 @@ def make_batch(cfg: SynthConfig, l1: bool = False) -> dict:
            "det_boxes_gt": gt, "masks_gt": masks}
     if l1:
         out["maps"] = make_maps_l1(cfg, tab)
+        out["coeffs"] = np.ascontiguousarray(out["head"][:, 4 + cfg.nc:, :])   # Segment `mc` [B, nm, N]
     key = stream_key(cfg.seed, 99, 0)
     h = hash_elems(key, np.arange(cfg.nm + 1))
     out["proj_weight"] = gauss16(h[:cfg.nm]) * np.float32(0.25)

@@ -187,9 +187,14 @@ def run_pipeline(batch, pool=None, **kw):
     """Whole hot path on one batch (L2 head).  Returns numpy outputs in the CUDA library's layout."""
     p = dict(DEFAULTS)
     p.update(kw)
-    head, protos = batch["head"], batch["protos"]
+    l1 = p.get("layout", "l2") == "l1"
+    head, protos = (None if l1 else batch["head"]), batch["protos"]
     gt_rows, masks_gt = batch["det_boxes_gt"], batch["masks_gt"]
-    B, _, N = head.shape
+    if l1:   # reference layout: three raw maps + Segment `mc` coefficients [B, nm, N]
+        maps, coeffs = batch["maps"], batch["coeffs"]
+        B, N = maps[0].shape[0], sum(m.shape[2] * m.shape[3] for m in maps)
+    else:
+        B, _, N = head.shape
     nc, nm, S, max_det = p["nc"], p["nm"], p["img_size"], p["max_det"]
     max_cand = p["max_cand"] or N
     out = {
@@ -217,7 +222,12 @@ def run_pipeline(batch, pool=None, **kw):
     out["dt_ignore"] = np.zeros((B, A, T, max_det), np.uint8)
     out["gt_ignore"] = np.zeros((B, A, p["max_gt"]), np.uint8)
     for b in range(B):
-        boxes, score, label = decode_l2(head[b], nc)
+        if l1:
+            boxes, sc_all = decode_l1([m[b] for m in maps], S, nc, p.get("reg_max", 16))
+            label = np.argmax(sc_all, axis=1).astype(np.int32)          # first max on ties (torch .max(dim=1))
+            score = np.ascontiguousarray(sc_all[np.arange(N), label])
+        else:
+            boxes, score, label = decode_l2(head[b], nc)
         cb = np.empty((N, 4), np.float32); cs = np.empty(N, np.float32)
         cl = np.empty(N, np.int32); ca = np.empty(N, np.int32)
         m = lib().bto_filter(boxes, score, label, N, np.float32(p["conf_thres"]), p["clamp"], np.float32(S), np.float32(S), cb, cs, cl, ca)
@@ -230,7 +240,8 @@ def run_pipeline(batch, pool=None, **kw):
         out["det_count"][b] = k
         out["dets"][b, :k, :4] = cb[keep]; out["dets"][b, :k, 4] = cs[keep]; out["dets"][b, :k, 5] = cl[keep].astype(np.float32)
         out["det_anchor"][b, :k] = ca[keep]; out["det_keep"][b, :k] = keep
-        out["det_coeff"][b, :k] = head[b, 4 + nc:, ca[keep]].reshape(k, nm) if k else 0
+        csrc = coeffs[b] if l1 else head[b, 4 + nc:]
+        out["det_coeff"][b, :k] = csrc[:, ca[keep]].T.reshape(k, nm) if k else 0
         # GT (mAP copy clamped, loss copy unclamped) + CM matching on raw decoded boxes
         gb, gl = gt_prep(gt_rows, b, S, p["gt_mode"], 1, p["max_gt"])
         gbr, _ = gt_prep(gt_rows, b, S, p["gt_mode"], 0, p["max_gt"])

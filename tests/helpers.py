@@ -13,9 +13,10 @@ def to_dev(batch, dev, gt_f32=False):
                 masks_gt=t(m), proj_weight=t(batch["proj_weight"]), proj_bias=float(batch["proj_bias"]))
 
 
-def run_cuda(batch, dev="cuda:0", gt_f32=False, **kw):
+def run_cuda(batch, dev="cuda:0", gt_f32=False, l1=False, **kw):
     scfg = batch["cfg"]
     cfg = PostConfig(batch=scfg.batch, img_size=scfg.img_size, nc=scfg.nc, nm=scfg.nm,
+                     layout=_lib.LAYOUT_L1 if l1 else _lib.LAYOUT_L2,
                      conf_thres=kw.get("conf_thres", 0.05), iou_thres=kw.get("iou_thres", 0.6),
                      max_det=kw.get("max_det", 300), max_cand=kw.get("max_cand", 0),
                      class_mode=kw.get("class_mode", 0), clamp_boxes=bool(kw.get("clamp", 1)),
@@ -25,7 +26,11 @@ def run_cuda(batch, dev="cuda:0", gt_f32=False, **kw):
                      with_seg_mask=True, with_seg_logits=True, with_uni_mask=True, with_coco=True)
     pp = PostProcessor(cfg, dev)
     d = to_dev(batch, dev, gt_f32)
-    out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    extra = {}
+    if l1:
+        extra = dict(maps=[torch.from_numpy(m).to(dev) for m in batch["maps"]], coeffs=torch.from_numpy(batch["coeffs"]).to(dev))
+    out = pp.run(None if l1 else d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"],
+                 **extra)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}, pp
 
