@@ -54,7 +54,7 @@ struct Workspace {
     float *cand_score;    // [B, cap]
     int32_t *cand_label;  // [B, cap]
     int32_t *cand_anchor; // [B, cap]
-    unsigned long long *sort_keys;  // [B, cap_pow2] (only used when the list exceeds shared memory)
+    unsigned long long *sort_keys;  // [B, cap_pow2] (only used when the list exceeds the register sort)
     int32_t *strip_done;  // [B] strips finished per image (mask kernel)
     int32_t *acc;         // [B, 8] per-image int counters: seg inter,P,G ; uni inter,P,G
     short4 *det_region;   // [B, K] crop region of each kept detection at prototype resolution (r_lo, r_hi, c_lo, c_hi)
@@ -67,11 +67,15 @@ static inline int cand_capacity(const BtParams *p) {
     return (p->max_cand > 0 && p->max_cand < p->num_anchors) ? p->max_cand : p->num_anchors;
 }
 
+
 static inline int next_pow2(int v) {
     int r = 1;
     while (r < v) r <<= 1;
     return r;
 }
+
+// Sorted candidates are consumed by the NMS kernel in shared-memory windows of this many.
+constexpr int K2_TAIL_WIN = 1024;
 
 static inline Workspace carve(const BtParams *p, void *base) {
     Workspace w;

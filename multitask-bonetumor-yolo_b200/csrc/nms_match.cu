@@ -1,5 +1,5 @@
-// Kernel 2: per-image stable descending sort + greedy NMS with early exit at max_det + gather of
-// the kept detections + COCOeval per-image matching.
+// Kernel group 2: per-image stable descending sort, greedy NMS with early exit at max_det, gather
+// of the kept detections, COCOeval per-image matching.
 //
 // Reference statements replaced (paths under /root/reference/src):
 //   NMS       running_main_v2.py:817  torchvision.ops.nms(item_boxes, item_top_scores, NMS_IOU)[:TOP_K]
@@ -11,25 +11,94 @@
 //   matching  torchmetrics MeanAveragePrecision.update -> pycocotools COCOeval.evaluateImg
 //             (configured at running_main_v2.py:228-251, evaluate_model.py:81-94)
 //
-// B200 mapping: one 1024-thread CTA per image.  The sorted candidate list is consumed in chunks
-// of 64: (A) the chunk is tested against the boxes kept so far (kept list staged in shared
-// memory, 16 threads per candidate, warp ballot to merge), (B) a 64x64 intra-chunk suppression
-// bitmask is built with warp ballots, (C) one warp sweeps the bitmask as a fixpoint (rows in
-// registers, warp-wide OR reductions) instead of one dependent load per keep.  Because keeps are
-// emitted in score order, `[:TOP_K]` is an early exit: at most max_det * M IoUs are evaluated
-// instead of M^2/2, which is what makes the 30k-candidate configuration tractable.
+// B200 mapping.  nms_kernel, one 1024-thread CTA per image:
+//   1. sort    64-bit (score key, index) bitonic network with the keys in REGISTERS: strides
+//              inside a thread are plain compare-exchanges, strides inside a warp are shuffles,
+//              only the widest strides go through shared memory.
+//   2. sweep   the sorted list is staged in windows of 1024 and consumed 64 at a time:
+//              (A) chunk vs KEPT boxes -- kept boxes are binned by the cell of their centre, and
+//              for IoU thresholds >= 0.55 a suppressing pair has each centre inside the other
+//              box, so a candidate only meets the kept boxes in the cells under its own box;
+//              (B) "who suppresses me" rows among the candidates A left undecided (warp ballots;
+//              the exact IoU only runs when some lane passes the cheap necessary condition);
+//              (C) one warp resolves the chunk as a fixpoint over those rows.  Because keeps are
+//              emitted in score order `[:TOP_K]` is an early exit, and because only KEPT or still
+//              undecided boxes are ever tested against, a cluster of hundreds of candidates on one
+//              object costs ~n tests, not n^2 (r01f: an all-pairs bit matrix, even spatially
+//              culled, spent 365 k cycles per image there).
+//   3. package boxes / scores / labels / keep indices / crop regions of the kept detections.
+// The exact IoU decision uses a guarded approximate division (see suppresses()).
+// gather_match_kernel then spreads the mask-coefficient gather (K x 32 scattered 4-byte reads per
+// image: latency-bound on one SM, r01e 16 us) over the whole GPU and runs COCOeval's per-image
+// matching in one extra CTA per image beside it.
 #include "common.cuh"
 
 namespace bt {
 
 constexpr int K2_THREADS = 1024;
-constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int NMS_CHUNK = 64;
-constexpr int SORT_SMEM_MAX = 8192;  // 64-bit keys sorted in shared memory up to this many
+constexpr int SORT_REG_MAX = 16384;  // keys sorted in registers (16 per thread) up to this many
+constexpr int GM_THREADS = 256;      // gather_match_kernel block: 8 detections x 32 coefficients
+constexpr int MAX_CELLS = 256;
+
+__device__ __forceinline__ uint32_t desc_key(float s) {
+    uint32_t u = __float_as_uint(s);
+    if (s != s) return 0u;                                   // NaN sorts first
+    if (u == 0x80000000u) u = 0u;                            // -0.0 == +0.0
+    uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ~asc;                                             // smaller key = higher score
+}
+
+// i = earlier (kept) box, j = later candidate; operand order of std::max/std::min as in
+// torchvision's nms_kernel_impl so NaN coordinates behave identically.
+//
+// centre_cull: IoU > 0.5 means the intersection covers more than half of EACH box, hence contains
+// each box's centre.  With iou_thres >= 0.55 (margin >> fp32 rounding of the IoU) a pair whose
+// later centre (cxj, cyj) is outside the earlier box can be skipped without evaluating the IoU;
+// every pair that is evaluated uses the exact expression, so the keep set does not change.
+struct FastDiv { int on; float lo, hi; };
+__device__ __forceinline__ bool suppresses(const float4 &bi, float ai, int li, const float4 &bj, float aj, int lj,
+                                           float thr_up, int early_out, int class_mode, int centre_cull, float cxj,
+                                           float cyj, const FastDiv &g_fast) {
+    if (class_mode == BT_CLASS_AWARE && li != lj) return false;
+    if (centre_cull && !(cxj >= bi.x && cxj <= bi.z && cyj >= bi.y && cyj <= bi.w)) return false;
+    float xx1 = (bi.x < bj.x) ? bj.x : bi.x;
+    float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
+    float xx2 = (bj.z < bi.z) ? bj.z : bi.z;
+    float yy2 = (bj.w < bi.w) ? bj.w : bi.w;
+    float w = __fsub_rn(xx2, xx1), h = __fsub_rn(yy2, yy1);
+    w = (0.0f < w) ? w : 0.0f;
+    h = (0.0f < h) ? h : 0.0f;
+    float inter = __fmul_rn(w, h);
+    if (early_out && !(inter > 0.0f)) return false;
+    const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
+    // ovr = fl(inter / den) >= thr_up.  The approximate quotient (<= 2 ulp off for den < 2^126)
+    // settles every pair that is not within 1e-6 (relative) of the threshold; only those pay for
+    // the IEEE division, so the decision is the exact one for every input.
+    if (g_fast.on && den < 1e37f && den > 1e-30f) {
+        const float q = __fdividef(inter, den);
+        if (q > g_fast.hi) return true;
+        if (q < g_fast.lo) return false;
+    }
+    return __fdiv_rn(inter, den) >= thr_up;
+}
+
+__device__ __forceinline__ float box_area(const float4 &b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+
+__device__ __forceinline__ double bb_iou(const double *d, const double *g) {
+    double w = fmin(d[0] + d[2], g[0] + g[2]) - fmax(d[0], g[0]);
+    if (w <= 0) return 0.0;
+    double h = fmin(d[1] + d[3], g[1] + g[3]) - fmax(d[1], g[1]);
+    if (h <= 0) return 0.0;
+    double i = w * h;
+    return i / (d[2] * d[3] + g[2] * g[3] - i);
+}
+
 
 struct K2Params {
     int N, nc, nm, C, cap, cap_pow2, max_det, max_gt, class_mode, layout;
     float thr_up;     // smallest float f with (double)f > iou_thres:  (double)ovr > thr  <=>  ovr >= thr_up
+    FastDiv fast;     // guarded approximate division (see suppresses)
     int early_out;    // iou_thres >= 0: pairs with zero intersection can never be suppressed
     float max_wh;
     const float *head;    // L2: coefficients are rows 4+nc.. of the head
@@ -53,82 +122,134 @@ struct K2Params {
     uint8_t *dt_ignore, *gt_ignore;
     // accumulators of the mask kernel, zeroed here
     int32_t *strip_done, *acc, *inst_area, *inst_inter;
-    int smem_keys;  // number of 64-bit slots in the shared key region
-    int win;        // sorted-candidate window staged in shared memory (multiple of NMS_CHUNK)
+    int region0_bytes;    // shared region 0: list of candidate indices in NMS order
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
-    int centre_cull; // iou_thres >= 0.55: a pair can only suppress if the later box's centre lies in the earlier box
+    int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
+    int gx, gy; float inv_cw, inv_ch;   // centre-cell grid
+    int coco_smem_doubles;
 };
 
-__device__ __forceinline__ uint32_t desc_key(float s) {
-    uint32_t u = __float_as_uint(s);
-    if (s != s) return 0u;                                   // NaN sorts first
-    if (u == 0x80000000u) u = 0u;                            // -0.0 == +0.0
-    uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    return ~asc;                                             // smaller key = higher score
+// =================================================================================================
+// sort
+// =================================================================================================
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
 }
 
-// i = earlier (kept) box, j = later candidate; operand order of std::max/std::min as in
-// torchvision's nms_kernel_impl so NaN coordinates behave identically.
-//
-// centre_cull: IoU > 0.5 means the intersection covers more than half of EACH box, hence contains
-// each box's centre.  With iou_thres >= 0.55 (margin >> fp32 rounding of the IoU) a pair whose
-// later centre (cxj, cyj) is outside the earlier box can be skipped without evaluating the IoU;
-// every pair that is evaluated uses the exact expression, so the keep set does not change.
-__device__ __forceinline__ bool suppresses(const float4 &bi, float ai, int li, const float4 &bj, float aj, int lj,
-                                           float thr_up, int early_out, int class_mode, int centre_cull = 0,
-                                           float cxj = 0.0f, float cyj = 0.0f) {
-    if (class_mode == BT_CLASS_AWARE && li != lj) return false;
-    if (centre_cull && !(cxj >= bi.x && cxj <= bi.z && cyj >= bi.y && cyj <= bi.w)) return false;
-    float xx1 = (bi.x < bj.x) ? bj.x : bi.x;
-    float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
-    float xx2 = (bj.z < bi.z) ? bj.z : bi.z;
-    float yy2 = (bj.w < bi.w) ? bj.w : bi.w;
-    float w = __fsub_rn(xx2, xx1), h = __fsub_rn(yy2, yy1);
-    w = (0.0f < w) ? w : 0.0f;
-    h = (0.0f < h) ? h : 0.0f;
-    float inter = __fmul_rn(w, h);
-    if (early_out && !(inter > 0.0f)) return false;
-    float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
-    return ovr >= thr_up;
+// Bitonic sort (ascending) of P2 = nthr * E keys; thread t < nthr holds elements t*E .. t*E+E-1.
+// Every thread of the block must call this (block barriers in the shared-memory steps).
+template <int E>
+__device__ __forceinline__ void bitonic_regs(unsigned long long (&v)[E], unsigned long long *s_x, int tid, int nthr) {
+    const bool active = tid < nthr;
+    const int P2 = nthr * E;
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32 * E) {
+                if (active) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) s_x[tid * E + e] = v[e];
+                }
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int i = tid * E + e;
+                        const unsigned long long o = s_x[i ^ j];
+                        const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                        v[e] = ((o < v[e]) == keep_min) ? o : v[e];
+                    }
+                }
+                __syncthreads();
+            } else if (j >= E) {
+                if (active) {
+                    const int tj = j / E;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int i = tid * E + e;
+                        const unsigned long long o = shfl_xor_u64(v[e], tj);
+                        const bool keep_min = ((tid & tj) == 0) == ((i & k) == 0);
+                        v[e] = ((o < v[e]) == keep_min) ? o : v[e];
+                    }
+                }
+            } else if (active) {
+#pragma unroll
+                for (int jj = E >> 1; jj >= 1; jj >>= 1) {
+                    if (jj != j) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if (e & jj) continue;
+                        const int i = tid * E + e;
+                        const bool asc = (i & k) == 0;
+                        const unsigned long long a = v[e], c = v[e | jj];
+                        if ((a > c) == asc) { v[e] = c; v[e | jj] = a; }
+                    }
+                }
+            }
+        }
+    }
 }
 
-__device__ __forceinline__ double bb_iou(const double *d, const double *g) {
-    double w = fmin(d[0] + d[2], g[0] + g[2]) - fmax(d[0], g[0]);
-    if (w <= 0) return 0.0;
-    double h = fmin(d[1] + d[3], g[1] + g[3]) - fmax(d[1], g[1]);
-    if (h <= 0) return 0.0;
-    double i = w * h;
-    return i / (d[2] * d[3] + g[2] * g[3] - i);
+// Sorts the image's candidates; on return s_sidx[i] (i < M) = index of the i-th candidate in NMS order.
+template <int E>
+__device__ __forceinline__ void sort_to_smem(const float *cscore, int M, int nthr, unsigned long long *s_x, uint32_t *s_sidx) {
+    const int tid = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        v[e] = (tid < nthr && i < M) ? (((unsigned long long)desc_key(__ldg(cscore + i)) << 32) | (unsigned)i) : ~0ull;
+    }
+    bitonic_regs<E>(v, s_x, tid, nthr);
+    __syncthreads();   // s_x (aliases s_sidx) is no longer read
+    if (tid < nthr) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) s_sidx[tid * E + e] = (uint32_t)v[e];
+    }
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_constant__ K2Params P) {
+// =================================================================================================
+// fused NMS kernel
+// =================================================================================================
+__global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = P.max_det;
+    constexpr int WIN = K2_TAIL_WIN;
 
-    // ---- shared-memory carve-up
-    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem_raw);          // [smem_keys]
-    float4 *s_kbox = reinterpret_cast<float4 *>(s_keys + P.smem_keys);                       // [K]   kept boxes
-    float4 *s_sbox = s_kbox + K;                                                             // [win] sorted boxes (window)
-    float *s_karea = reinterpret_cast<float *>(s_sbox + P.win);                              // [K]
-    float *s_sarea = s_karea + K;                                                            // [win]
-    int *s_klabel = reinterpret_cast<int *>(s_sarea + P.win);                                // [K]
-    int *s_kidx = s_klabel + K;                                                              // [K]
-    int *s_slabel = s_kidx + K;                                                              // [win]
-    __shared__ unsigned int s_mask32[NMS_CHUNK * 2];
+    // ---- shared-memory carve-up (the sort's exchange buffer / sorted-index list overlays it)
+    uint32_t *s_sidx = reinterpret_cast<uint32_t *>(smem_raw);
+    float4 *s_sbox = reinterpret_cast<float4 *>(smem_raw + P.region0_bytes);                 // [WIN] window, NMS coordinates
+    float4 *s_kbox = s_sbox + WIN;                                                           // [K] kept boxes
+    float2 *s_sctr = reinterpret_cast<float2 *>(s_kbox + K);                                 // [WIN] centres
+    float2 *s_kctr = s_sctr + WIN;                                                           // [K] kept centres
+    float *s_sarea = reinterpret_cast<float *>(s_kctr + K);                                  // [WIN]
+    float *s_sscore = s_sarea + WIN;                                                         // [WIN]
+    int *s_slabel = reinterpret_cast<int *>(s_sscore + WIN);                                 // [WIN]
+    int *s_sanchor = s_slabel + WIN;                                                         // [WIN]
+    int *s_sorig = s_sanchor + WIN;                                                          // [WIN] index into the filtered list
+    float *s_karea = reinterpret_cast<float *>(s_sorig + WIN);                               // [K]
+    float *s_kscore = s_karea + K;                                                           // [K]
+    int *s_klabel = reinterpret_cast<int *>(s_kscore + K);                                   // [K]
+    int *s_kanchor = s_klabel + K;                                                           // [K]
+    int *s_korig = s_kanchor + K;                                                            // [K]
+    int *s_knext = s_korig + K;                                                              // [K] next kept box of the same cell
+    int *s_scell = s_knext + K;                                                              // [WIN] packed cell range under the box
+    __shared__ unsigned int s_row32[NMS_CHUNK * 2];
+    __shared__ int s_cellhead[MAX_CELLS];
     __shared__ unsigned int s_supA[2];
     __shared__ unsigned long long s_keepm;
-    __shared__ int s_warpcnt[K2_WARPS];
 
     BT_PHASE_INIT();
-    // ---- zero the per-image accumulators the mask kernel adds into
+    // zero the per-image accumulators the mask kernel adds into
     if (tid < 8) P.acc[b * 8 + tid] = 0;
     if (tid == 8) P.strip_done[b] = 0;
     for (int i = tid; i < K; i += K2_THREADS) {
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
         if (P.inst_inter) P.inst_inter[(size_t)b * K + i] = 0;
     }
-
+    if (tid < MAX_CELLS) s_cellhead[tid] = -1;
     const int M = P.n_cand[b];
     const float4 *cbox = P.cand_box + (size_t)b * P.cap;
     const float *cscore = P.cand_score + (size_t)b * P.cap;
@@ -136,143 +257,220 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
     const int32_t *canchor = P.cand_anchor + (size_t)b * P.cap;
 
     // ---- 1. stable descending sort: key = (descending score key << 32) | candidate index
-    int P2 = 1;
-    while (P2 < M) P2 <<= 1;
-    unsigned long long *keys = (P2 <= P.smem_keys) ? s_keys : (P.sort_keys + (size_t)b * P.cap_pow2);
-    for (int i = tid; i < P2; i += K2_THREADS)
-        keys[i] = (i < M) ? (((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)i) : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= P2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P2 >> 1); t += K2_THREADS) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                unsigned long long a = keys[i], c = keys[l];
-                bool asc = (i & k) == 0;
-                if ((a > c) == asc) { keys[i] = c; keys[l] = a; }
+    const unsigned long long *gkeys = nullptr;
+    {
+        unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
+        if (M <= 1024) sort_to_smem<1>(cscore, M, 1024, s_x, s_sidx);
+        else if (M <= 2048) sort_to_smem<2>(cscore, M, 1024, s_x, s_sidx);
+        else if (M <= 4096) sort_to_smem<4>(cscore, M, 1024, s_x, s_sidx);
+        else if (M <= 8192) sort_to_smem<16>(cscore, M, 512, s_x, s_sidx);
+        else if (M <= SORT_REG_MAX) sort_to_smem<16>(cscore, M, 1024, s_x, s_sidx);
+        else {
+            // very long lists (30k-candidate stress case): bitonic network in global memory
+            int P2 = 1;
+            while (P2 < M) P2 <<= 1;
+            unsigned long long *keys = P.sort_keys + (size_t)b * P.cap_pow2;
+            for (int i = tid; i < P2; i += K2_THREADS)
+                keys[i] = (i < M) ? (((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)i) : ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= P2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (P2 >> 1); t += K2_THREADS) {
+                        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        int l = i | j;
+                        unsigned long long a = keys[i], c = keys[l];
+                        bool asc = (i & k) == 0;
+                        if ((a > c) == asc) { keys[i] = c; keys[l] = a; }
+                    }
+                    __syncthreads();
+                }
+            gkeys = keys;
+        }
+    }
+    BT_PHASE_MARK(1, 0);   // sort
+
+    auto cell_x = [&](float x) { return min(max(__float2int_rd(__fmul_rn(x, P.inv_cw)), 0), P.gx - 1); };
+    auto cell_y = [&](float y) { return min(max(__float2int_rd(__fmul_rn(y, P.inv_ch)), 0), P.gy - 1); };
+
+    // ---- 2. greedy sweep over windows of 1024 sorted candidates, 64 at a time
+    int nkept = 0;
+    for (int w0 = 0; w0 < M && nkept < K; w0 += WIN) {
+        const int wn = min(WIN, M - w0);
+        // (a) stage the window in NMS order; bucket its candidates by the cell of their centre
+        if (tid < wn) {
+            const int idx = gkeys ? (int)(unsigned)gkeys[w0 + tid] : (int)s_sidx[w0 + tid];
+            float4 bx = __ldg(cbox + idx);
+            const int lb = __ldg(clabel + idx);
+            s_sscore[tid] = __ldg(cscore + idx);
+            s_sanchor[tid] = __ldg(canchor + idx);
+            s_sorig[tid] = idx;
+            if (P.class_mode == BT_CLASS_OFFSET) {
+                const float off = __fmul_rn((float)lb, P.max_wh);
+                bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
+                bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+            }
+            s_sbox[tid] = bx;
+            s_sctr[tid] = make_float2(__fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f), __fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f));
+            {   // cells under the box: x0 | y0 << 4 | nx << 8 | ny << 13 (nx = 1, ny = 0 for an inverted box)
+                const int gx0 = cell_x(bx.x), gy0 = cell_y(bx.y);
+                const int ncx = max(cell_x(bx.z) - gx0 + 1, 1), ncy = max(cell_y(bx.w) - gy0 + 1, 0);
+                s_scell[tid] = gx0 | (gy0 << 4) | (ncx << 8) | (ncy << 13);
+            }
+            s_sarea[tid] = box_area(bx);
+            s_slabel[tid] = lb;
+        }
+        __syncthreads();
+        BT_PHASE_MARK(1, 1);   // stage window
+        // (c) the chunks, in order
+        for (int c0 = 0; c0 < wn && nkept < K; c0 += NMS_CHUNK) {
+            const int n_in = min(NMS_CHUNK, wn - c0);
+            if (tid < 2) s_supA[tid] = 0;
+            __syncthreads();
+            // (A) chunk vs kept boxes, 16 threads per candidate.  Centre-cull mode: only kept boxes
+            // whose centre lies in a cell under the candidate's box can suppress it (one cell per
+            // thread for boxes of up to 4 x 4 cells); otherwise the threads stride over all kept boxes.
+            {
+                const int ci = tid >> 4, sub = tid & 15;
+                bool f = false;
+                if (ci < n_in) {
+                    const float4 bj = s_sbox[c0 + ci];
+                    const float2 cj = s_sctr[c0 + ci];
+                    const float aj = s_sarea[c0 + ci];
+                    const int lj = s_slabel[c0 + ci];
+                    if (P.centre_cull) {
+                        const int pc = s_scell[c0 + ci];
+                        const int gx0 = pc & 15, gy0 = (pc >> 4) & 15, ncx = (pc >> 8) & 31, ncy = (pc >> 13) & 31;
+                        int qx = sub % ncx, qy = sub / ncx;   // cells q = sub, sub + 16, ... in row-major order (ncx >= 1)
+                        for (int q = sub; q < ncx * ncy; q += 16) {
+                            for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0; k = s_knext[k]) {
+                                const float2 ck = s_kctr[k];
+                                if (!(ck.x >= bj.x && ck.x <= bj.z && ck.y >= bj.y && ck.y <= bj.w)) continue;
+                                f |= suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                                P.class_mode, 1, cj.x, cj.y, P.fast);
+                            }
+                            qx += 16;
+                            while (qx >= ncx) { qx -= ncx; ++qy; }
+                        }
+                    } else {
+                        for (int k = sub; k < nkept; k += 16)
+                            f |= suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                            P.class_mode, 0, 0.0f, 0.0f, P.fast);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
             }
             __syncthreads();
-        }
-
-    BT_PHASE_MARK(1, 0);   // sort
-    // ---- 2. chunked greedy NMS over the sorted list, staged through shared memory in windows
-    int nkept = 0;
-    for (int c0 = 0; c0 < M && nkept < K; c0 += NMS_CHUNK) {
-        const int n_in = min(NMS_CHUNK, M - c0);
-        const int w0 = (c0 / P.win) * P.win;      // window holding this chunk (win is a multiple of 64)
-        if (c0 == w0) {
-            // gather the next window of sorted candidates: boxes (class-offset if asked), areas, labels
-            const int wn = min(P.win, M - w0);
-            for (int t = tid; t < wn; t += K2_THREADS) {
-                const int idx = (int)(unsigned)keys[w0 + t];
-                float4 bx = cbox[idx];
-                const int lb = clabel[idx];
-                if (P.class_mode == BT_CLASS_OFFSET) {
-                    const float off = __fmul_rn((float)lb, P.max_wh);
-                    bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
-                    bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
-                }
-                s_sbox[t] = bx;
-                s_sarea[t] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-                s_slabel[t] = lb;
-            }
-        }
-        if (tid < 2) s_supA[tid] = 0;
-        __syncthreads();
-        const float4 *cb = s_sbox + (c0 - w0);
-        const float *ca = s_sarea + (c0 - w0);
-        const int *cl = s_slabel + (c0 - w0);
-        // (A) chunk vs boxes kept so far: 16 threads per candidate
-        {
-            const int ci = tid >> 4, sub = tid & 15;
-            bool f = false;
-            if (ci < n_in) {
-                const float4 bj = cb[ci];
-                const float aj = ca[ci];
-                const int lj = cl[ci];
-                const float cxj = __fmul_rn(__fadd_rn(bj.x, bj.z), 0.5f), cyj = __fmul_rn(__fadd_rn(bj.y, bj.w), 0.5f);
-                for (int j = sub; j < nkept; j += 16)
-                    f |= suppresses(s_kbox[j], s_karea[j], s_klabel[j], bj, aj, lj, P.thr_up, P.early_out, P.class_mode,
-                                    P.centre_cull, cxj, cyj);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, f);
-            if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
-        }
-        BT_PHASE_MARK(1, 8);   // chunk: load + phase A
-        // (B) intra-chunk 64x64 upper-triangular suppression bitmask
-#pragma unroll
-        for (int r = 0; r < (NMS_CHUNK * NMS_CHUNK) / K2_THREADS; ++r) {
-            const int q = r * K2_THREADS + tid;
-            const int i = q >> 6, j = q & 63;
-            bool f = false;
-            if (j > i && j < n_in) {
-                const float4 bj = cb[j];
-                f = suppresses(cb[i], ca[i], cl[i], bj, ca[j], cl[j], P.thr_up, P.early_out, P.class_mode, P.centre_cull,
-                               __fmul_rn(__fadd_rn(bj.x, bj.z), 0.5f), __fmul_rn(__fadd_rn(bj.y, bj.w), 0.5f));
-            }
-            unsigned m = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) s_mask32[i * 2 + (j >> 5)] = m;
-        }
-        __syncthreads();
-        BT_PHASE_MARK(1, 9);   // chunk: phase B
-        // (C) warp-level suppression sweep as a fixpoint: a candidate no undecided earlier candidate
-        // can suppress is final; its row removes its victims.  Resolves sparse chunks in 1-3 rounds
-        // instead of one dependent shared-memory load per keep.
-        if (wid == 0) {
-            const unsigned long long row_a = ((unsigned long long)s_mask32[lane * 2 + 1] << 32) | s_mask32[lane * 2];
-            const unsigned long long row_b = ((unsigned long long)s_mask32[(lane + 32) * 2 + 1] << 32) | s_mask32[(lane + 32) * 2];
+            BT_PHASE_MARK(1, 8);   // chunk: A
+            // (B) "who suppresses me" rows of the candidates A left undecided, against the undecided
+            // earlier candidates of the chunk only (a cluster of hundreds of candidates on one object
+            // is settled by A as soon as its leader is kept).  Warp task = (row j, half of the chunk);
+            // lanes = earlier candidates i; the exact IoU runs only when some lane passes the cheap test.
             const unsigned long long valid = (n_in == 64) ? ~0ull : ((1ull << n_in) - 1ull);
-            unsigned long long und = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
-            unsigned long long keepm = 0ull;
-            while (und) {
-                const bool ua = (und >> lane) & 1ull, ub = (und >> (lane + 32)) & 1ull;
-                const unsigned long long r = (ua ? row_a : 0ull) | (ub ? row_b : 0ull);
-                const unsigned long long S = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(r >> 32)) << 32) |
-                                             __reduce_or_sync(0xffffffffu, (unsigned)r);
-                const unsigned long long def = und & ~S;
-                keepm |= def;
-                const bool da = (def >> lane) & 1ull, db = (def >> (lane + 32)) & 1ull;
-                const unsigned long long d = (da ? row_a : 0ull) | (db ? row_b : 0ull);
-                const unsigned long long Dm = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(d >> 32)) << 32) |
-                                              __reduce_or_sync(0xffffffffu, (unsigned)d);
-                und &= ~(def | Dm);
+            const unsigned long long und0 = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int task = wid * 4 + r, jo = task >> 1, half = task & 1;
+                const unsigned hm = (unsigned)(und0 >> (32 * half)) & ((jo >= 32 * half + 32) ? 0xffffffffu
+                                                : (jo > 32 * half ? ((1u << (jo - 32 * half)) - 1u) : 0u));
+                unsigned m = 0u;
+                if (((und0 >> jo) & 1ull) && hm) {
+                    const int j = c0 + jo, i = c0 + 32 * half + lane;
+                    const float4 bj = s_sbox[j];
+                    const float2 cj = s_sctr[j];
+                    bool pass = false;
+                    float4 bi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if ((hm >> lane) & 1u) {
+                        bi = s_sbox[i];
+                        if (P.centre_cull) {
+                            const float2 ci = s_sctr[i];
+                            pass = ci.x >= bj.x && ci.x <= bj.z && ci.y >= bj.y && ci.y <= bj.w &&
+                                   cj.x >= bi.x && cj.x <= bi.z && cj.y >= bi.y && cj.y <= bi.w;
+                        } else if (P.early_out) {
+                            pass = fminf(bi.z, bj.z) > fmaxf(bi.x, bj.x) && fminf(bi.w, bj.w) > fmaxf(bi.y, bj.y);
+                        } else {
+                            pass = true;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, pass)) {
+                        bool f = false;
+                        if (pass)
+                            f = suppresses(bi, s_sarea[i], s_slabel[i], bj, s_sarea[j], s_slabel[j], P.thr_up, P.early_out,
+                                           P.class_mode, P.centre_cull, cj.x, cj.y, P.fast);
+                        m = __ballot_sync(0xffffffffu, f);
+                    }
+                }
+                if (lane == 0) s_row32[jo * 2 + half] = m;
             }
-            // [:TOP_K]: only the first `room` keeps survive (later ones cannot affect earlier ones)
-            int room = K - nkept;
-            if (__popcll(keepm) > room) {
-                unsigned long long t = keepm, kept = 0ull;
-                for (int i = 0; i < room; ++i) { unsigned long long low = t & (~t + 1ull); kept |= low; t ^= low; }
-                keepm = kept;
+            __syncthreads();
+            BT_PHASE_MARK(1, 11);  // chunk: B
+            // (C) one warp resolves the chunk as a fixpoint over the rows (lane: rows lane, lane + 32)
+            if (wid == 0) {
+                const unsigned long long row_a = ((unsigned long long)s_row32[lane * 2 + 1] << 32) | s_row32[lane * 2];
+                const unsigned long long row_b = ((unsigned long long)s_row32[(lane + 32) * 2 + 1] << 32) | s_row32[(lane + 32) * 2];
+                unsigned long long und = und0, keepm = 0ull;
+                if (__any_sync(0xffffffffu, (row_a | row_b) != 0ull)) {
+                    while (und) {
+                        // kept: no undecided and no kept suppressor left; removed: a kept suppressor exists
+                        const bool ua = (und >> lane) & 1ull, ub = (und >> (lane + 32)) & 1ull;
+                        const unsigned long long live = und | keepm;
+                        const unsigned long long newk =
+                            ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & live) == 0ull) << 32) |
+                            __ballot_sync(0xffffffffu, ua && (row_a & live) == 0ull);
+                        keepm |= newk;
+                        und &= ~newk;
+                        const unsigned long long rem =
+                            ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & keepm) != 0ull) << 32) |
+                            __ballot_sync(0xffffffffu, ua && (row_a & keepm) != 0ull);
+                        und &= ~rem;
+                    }
+                } else {
+                    keepm = und;
+                }
+                // [:TOP_K]: only the first `room` keeps survive (later ones cannot affect earlier ones)
+                const int room = K - nkept;
+                if (__popcll(keepm) > room) {
+                    unsigned long long t = keepm, kept = 0ull;
+                    for (int i = 0; i < room; ++i) { unsigned long long low = t & (~t + 1ull); kept |= low; t ^= low; }
+                    keepm = kept;
+                }
+                if (lane == 0) s_keepm = keepm;
             }
-            if (lane == 0) s_keepm = keepm;
+            __syncthreads();
+            BT_PHASE_MARK(1, 9);   // chunk: C
+            const unsigned long long keepm = s_keepm;
+            if (tid < NMS_CHUNK && ((keepm >> tid) & 1ull)) {
+                const int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
+                const float2 ctr = s_sctr[c0 + tid];
+                s_kbox[slot] = s_sbox[c0 + tid];
+                s_kctr[slot] = ctr;
+                s_karea[slot] = s_sarea[c0 + tid];
+                s_klabel[slot] = s_slabel[c0 + tid];
+                s_kscore[slot] = s_sscore[c0 + tid];
+                s_kanchor[slot] = s_sanchor[c0 + tid];
+                s_korig[slot] = s_sorig[c0 + tid];
+                if (P.centre_cull) s_knext[slot] = atomicExch(&s_cellhead[cell_y(ctr.y) * P.gx + cell_x(ctr.x)], slot);
+            }
+            nkept += __popcll(keepm);
+            BT_PHASE_MARK(1, 10);  // chunk: insert
         }
-        __syncthreads();
-        BT_PHASE_MARK(1, 10);  // chunk: phase C
-        const unsigned long long keepm = s_keepm;
-        if (tid < NMS_CHUNK && ((keepm >> tid) & 1ull)) {
-            int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
-            s_kbox[slot] = cb[tid];
-            s_karea[slot] = ca[tid];
-            s_klabel[slot] = cl[tid];
-            s_kidx[slot] = (int)(unsigned)keys[c0 + tid];
-        }
-        nkept += __popcll(keepm);
-        __syncthreads();
+        __syncthreads();   // the window is re-staged next
+        BT_PHASE_MARK(1, 3);   // chunks
     }
 
-    BT_PHASE_MARK(1, 1);   // NMS chunks
     // ---- 3. package kept detections (running_main_v2.py:818-839); zero-fill the padding
     if (tid == 0) P.det_count[b] = nkept;
     for (int k = tid; k < K; k += K2_THREADS) {
         float *o = P.dets + ((size_t)b * K + k) * 6;
         if (k < nkept) {
-            int idx = s_kidx[k];
-            float4 bx = cbox[idx];
+            const int idx = s_korig[k];
+            float4 bx = s_kbox[k];
+            if (P.class_mode == BT_CLASS_OFFSET) bx = __ldg(cbox + idx);   // un-offset coordinates
             o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-            o[4] = cscore[idx];
-            o[5] = (float)clabel[idx];
+            o[4] = s_kscore[k];
+            o[5] = (float)s_klabel[k];
             P.det_keep[(size_t)b * K + k] = idx;
-            P.det_anchor[(size_t)b * K + k] = canchor[idx];
+            P.det_anchor[(size_t)b * K + k] = s_kanchor[k];
             int r_lo, r_hi, c_lo, c_hi;
             const float bb[4] = {bx.x, bx.y, bx.z, bx.w};
             const bool ok = crop_region(bb, P.crop, P.rx, P.ry, P.PW, P.PH, r_lo, r_hi, c_lo, c_hi);
@@ -285,37 +483,62 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             P.det_anchor[(size_t)b * K + k] = -1;
         }
     }
-    for (int q = tid; q < K * 32; q += K2_THREADS) {   // nm == 32 (validated by check_params)
-        int k = q >> 5, m = q & 31;
+    // clear the matching table (filled by gather_match_kernel)
+    if (P.dt_match) {
+        const size_t per_img = (size_t)BT_NUM_AREA * P.T * K;
+        int32_t *dm = P.dt_match + (size_t)b * per_img;
+        if ((per_img & 3) == 0) {
+            int4 *d4 = reinterpret_cast<int4 *>(dm);   // per-image base is 16-byte aligned when per_img % 4 == 0
+            for (int q = tid; q < (int)(per_img >> 2); q += K2_THREADS) d4[q] = make_int4(0, 0, 0, 0);
+        } else {
+            for (int q = tid; q < (int)per_img; q += K2_THREADS) dm[q] = 0;
+        }
+    }
+    BT_PHASE_MARK(1, 6);   // package
+}
+
+// =================================================================================================
+// mask-coefficient gather (grid-wide) + COCOeval.evaluateImg (one CTA per image)
+// =================================================================================================
+__global__ void __launch_bounds__(GM_THREADS) gather_match_kernel(const __grid_constant__ K2Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K = P.max_det;
+    const int ngather = (K + 7) / 8;
+    if ((int)blockIdx.x < ngather) {
+        // 8 detections x 32 coefficients per CTA: K x 32 independent scattered reads per image
+        const int k = blockIdx.x * 8 + wid, m = lane;
+        if (k >= K) return;
+        const int a = P.det_anchor[(size_t)b * K + k];
         float v = 0.0f;
-        if (k < nkept) {
-            int a = canchor[s_kidx[k]];
-            v = (P.layout == BT_LAYOUT_L2) ? __ldg(P.head + ((size_t)b * P.C + 4 + P.nc + m) * P.N + a)
-                                           : __ldg(P.coeffs + ((size_t)b * P.nm + m) * P.N + a);
+        if (a >= 0) {
+            const float *src = (P.layout == BT_LAYOUT_L2) ? P.head + ((size_t)b * P.C + 4 + P.nc) * P.N
+                                                          : P.coeffs + (size_t)b * P.nm * P.N;
+            v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
         }
         P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
+        return;
     }
-
-    BT_PHASE_MARK(1, 2);   // package
-    // ---- 4. COCOeval.evaluateImg for every (class, area range, IoU threshold)
     if (P.dt_match == nullptr) return;
-    __syncthreads();  // key region is free from here on: reuse it for the double-precision tables
+    BT_PHASE_INIT();
+    // ---- COCOeval.evaluateImg for every (class, area range, IoU threshold)
     const int G = P.gt_count[b];
-    const int D = nkept;
+    const int D = P.det_count[b];
     const int T = P.T;
     double *s_db = reinterpret_cast<double *>(smem_raw);   // [K][4] x, y, w, h
     double *s_gb = s_db + (size_t)K * 4;                   // [max_gt][4]
     double *s_iou = s_gb + (size_t)P.max_gt * 4;           // [D][G] if it fits
-    const int iou_room = P.smem_keys - K * 4 - P.max_gt * 4;
+    const int iou_room = P.coco_smem_doubles - K * 4 - P.max_gt * 4;
     const bool iou_in_smem = (D * G) <= iou_room;
-    int *s_dl = s_klabel;                                   // det labels (already there, K entries)
+    int *s_dl = reinterpret_cast<int *>(s_db + P.coco_smem_doubles);   // [K] det labels
+    int *s_can = s_dl + K;                                              // [K] 1 if the det can match at the loosest threshold
+    int *s_list = s_can + K;                                            // [K] compacted list of those dets
     __shared__ int s_gl[32];
     __shared__ unsigned s_gign[BT_NUM_AREA];
-    float *s_maxiou = s_karea;                               // [K] reuse: max IoU over same-class GT (as float of double, rounded up)
-    int *s_list = s_kidx;                                    // [K] reuse: compacted list of dets that can match anything
+    __shared__ int s_warpcnt[GM_THREADS / 32];
     __shared__ int s_nlist;
 
-    for (int k = tid; k < D; k += K2_THREADS) {
+    for (int k = tid; k < D; k += GM_THREADS) {
         const float *o = P.dets + ((size_t)b * K + k) * 6;
         s_db[k * 4 + 0] = (double)o[0];
         s_db[k * 4 + 1] = (double)o[1];
@@ -350,50 +573,49 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
     // IoU table + per-detection best IoU over same-class GT
     double thr_min = 1.0;
     for (int t = 0; t < T; ++t) thr_min = fmin(thr_min, fmin(P.thrs[t], 1 - 1e-10));
-    for (int k = tid; k < D; k += K2_THREADS) {
+    for (int k = tid; k < D; k += GM_THREADS) {
         double best = -1.0;
         for (int g = 0; g < G; ++g) {
             double v = bb_iou(s_db + k * 4, s_gb + g * 4);
             if (iou_in_smem) s_iou[k * G + g] = v;
             if (s_gl[g] == s_dl[k] && v > best) best = v;
         }
-        s_maxiou[k] = (best >= thr_min) ? 1.0f : 0.0f;
+        s_can[k] = (best >= thr_min) ? 1 : 0;
+    }
+    // default (unmatched) ignore flags for every (a, t, d), zero padding beyond D
+    if (P.dt_ignore) {
+        const size_t per_img = (size_t)BT_NUM_AREA * T * K;
+        uint8_t *di = P.dt_ignore + (size_t)b * per_img;
+        for (int d = tid; d < K; d += GM_THREADS) {
+            unsigned igm = 0;
+            if (d < D) {
+                const double ar = s_db[d * 4 + 2] * s_db[d * 4 + 3];
+#pragma unroll
+                for (int a = 0; a < BT_NUM_AREA; ++a) igm |= ((ar < area_lo[a] || ar > area_hi[a]) ? 1u : 0u) << a;
+            }
+            for (int a = 0; a < BT_NUM_AREA; ++a)
+                for (int t = 0; t < T; ++t) di[((size_t)a * T + t) * K + d] = (igm >> a) & 1u;
+        }
     }
     __syncthreads();
     // ordered compaction of the detections that can match at the loosest threshold
     {
         int base = 0;
-        for (int k0 = 0; k0 < D; k0 += K2_THREADS) {
+        for (int k0 = 0; k0 < D; k0 += GM_THREADS) {
             int k = k0 + tid;
-            bool f = (k < D) && s_maxiou[k] != 0.0f;
+            bool f = (k < D) && s_can[k] != 0;
             unsigned m = __ballot_sync(0xffffffffu, f);
             if (lane == 0) s_warpcnt[wid] = __popc(m);
             __syncthreads();
             int off = base, tot = 0;
-            for (int w = 0; w < K2_WARPS; ++w) { int v = s_warpcnt[w]; if (w < wid) off += v; tot += v; }
-            __syncthreads();   // everyone has read s_maxiou / s_warpcnt before s_list (aliases s_kidx) is written
+            for (int w = 0; w < GM_THREADS / 32; ++w) { int v = s_warpcnt[w]; if (w < wid) off += v; tot += v; }
+            __syncthreads();
             if (f) s_list[off + __popc(m & ((1u << lane) - 1u))] = k;
             base += tot;
         }
         if (tid == 0) s_nlist = base;
         __syncthreads();
     }
-    // default (unmatched) entries for every (a, t, d), zero padding beyond D
-    {
-        const size_t per_img = (size_t)BT_NUM_AREA * T * K;
-        for (size_t q = tid; q < per_img; q += K2_THREADS) {
-            int d = (int)(q % K);
-            int a = (int)(q / ((size_t)T * K));
-            uint8_t ig = 0;
-            if (d < D) {
-                double ar = s_db[d * 4 + 2] * s_db[d * 4 + 3];
-                ig = (ar < area_lo[a] || ar > area_hi[a]) ? 1 : 0;
-            }
-            P.dt_match[(size_t)b * per_img + q] = 0;
-            if (P.dt_ignore) P.dt_ignore[(size_t)b * per_img + q] = ig;
-        }
-    }
-    __syncthreads();
     // greedy matching, one thread per (area range, threshold), over the compacted list only
     if (tid < BT_NUM_AREA * T) {
         const int a = tid / T, t = tid - a * T;
@@ -426,11 +648,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_match_kernel(const __grid_cons
             }
         }
     }
-}
-
-size_t k2_smem_bytes(const BtParams &p, int smem_keys, int win) {
-    size_t K = (size_t)p.max_det;
-    return (size_t)smem_keys * 8 + (K + win) * sizeof(float4) + (K + win) * sizeof(float) + (2 * K + win) * sizeof(int);
+    BT_PHASE_MARK(1, 7);   // COCO matching
 }
 
 int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
@@ -441,6 +659,9 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     float t = (float)p.iou_thres;
     if (!((double)t > p.iou_thres)) t = nextafterf(t, INFINITY);
     P.thr_up = t;
+    P.fast.on = t >= 1e-3f ? 1 : 0;
+    P.fast.lo = (float)((double)t * (1.0 - 1e-6));
+    P.fast.hi = (float)((double)t * (1.0 + 1e-6));
     P.early_out = p.iou_thres >= 0.0 ? 1 : 0;
     P.max_wh = p.max_wh;
     P.head = io.head; P.coeffs = io.coeffs;
@@ -453,29 +674,39 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     for (int i = 0; i < p.num_iou_thrs; ++i) P.thrs[i] = p.iou_thrs[i];
     P.dt_match = io.dt_match; P.dt_ignore = io.dt_ignore; P.gt_ignore = io.gt_ignore;
     P.strip_done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
-    // shared key region: large enough for the sort of typical lists and for the COCO tables
-    int need_coco = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;  // boxes + room for a [K x 4] IoU table at least
-    int keys = next_pow2(P.cap) < SORT_SMEM_MAX ? next_pow2(P.cap) : SORT_SMEM_MAX;
-    if (keys < need_coco) keys = need_coco;
-    P.smem_keys = keys;
-    // window of sorted candidates kept in shared memory: the whole list when it is small
-    int win = (P.cap + NMS_CHUNK - 1) / NMS_CHUNK * NMS_CHUNK;
-    if (win > 4096) win = 4096;
-    P.win = win;
     P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
     P.crop = p.crop; P.PW = p.proto_w; P.PH = p.proto_h;
     P.rx = (float)((double)p.proto_w / (double)p.img_w);
     P.ry = (float)((double)p.proto_h / (double)p.img_h);
     P.det_region = w.det_region;
-    size_t smem = k2_smem_bytes(p, keys, win);
+    // centre-cell grid: cells of >= 64 px, at most 16 x 16
+    P.gx = p.img_w / 64 < 1 ? 1 : (p.img_w / 64 > 16 ? 16 : p.img_w / 64);
+    P.gy = p.img_h / 64 < 1 ? 1 : (p.img_h / 64 > 16 ? 16 : p.img_h / 64);
+    P.inv_cw = (float)P.gx / (float)p.img_w;
+    P.inv_ch = (float)P.gy / (float)p.img_h;
+
+    // shared memory of nms_kernel: [sorted-index list | window (48 B/candidate) + kept arrays (48 B/slot)];
+    // the sort's exchange buffer overlays everything.
+    const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > SORT_REG_MAX ? SORT_REG_MAX : P.cap_pow2);
+    const size_t region0 = align_up((size_t)sort_slots * 4, 16);
+    P.region0_bytes = (int)region0;
+    size_t smem_a = region0 + (size_t)K2_TAIL_WIN * 48 + (size_t)p.max_det * 48 + 64;
+    if (smem_a < (size_t)sort_slots * 8) smem_a = (size_t)sort_slots * 8;
+    if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
+    // gather_match_kernel: COCO tables
+    const int coco_doubles = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;   // boxes + room for a [K x 4] IoU block
+    P.coco_smem_doubles = coco_doubles;
+    const size_t smem_b = (size_t)coco_doubles * 8 + (size_t)p.max_det * 12;
+    if (smem_b > 220 * 1024) return BT_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(nms_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(gather_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
         attr_set = true;
     }
-    if (smem > 200 * 1024) return BT_ERR_UNSUPPORTED;
-    nms_match_kernel<<<p.batch, K2_THREADS, smem, s>>>(P);
+    nms_kernel<<<p.batch, K2_THREADS, smem_a, s>>>(P);
+    gather_match_kernel<<<dim3((p.max_det + 7) / 8 + 1, p.batch), GM_THREADS, smem_b, s>>>(P);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
