@@ -8,40 +8,41 @@
 //   counters       running_main_v2.py:704-713 (tp/fp/fn/tn, DiceScore) and test_model.py:15-23
 //                  (per-image IoU / Dice with eps 1e-7)
 //
-// B200 mapping.  The prototypes are 2/3 of the path's compulsory HBM bytes and every other
-// operand is tiny, so the kernel is organised around streaming them exactly once: a CTA owns a
-// strip of R "cell rows" of one image (a cell = the 4x4 output pixels interpolated between four
-// neighbouring prototype pixels), pulls the strip's R+1 prototype rows of all 32 channels into
-// shared memory with 32 bulk async copies (TMA, cp.async.bulk + mbarrier complete_tx) issued by
-// one warp, and while they are in flight zeroes its bit tiles, packs the GT mask strip to bits
-// and builds the list of detections whose crop box touches the strip.  From shared memory it then
-// (1) projects + upsamples + thresholds the M1 mask, (2) contracts the 32 coefficients of every
-// listed detection against the prototype pixels inside its crop box (sequential fp32 FMA, the
-// same summation order as the oracle; TF32 tensor cores would break bit parity and the op is
-// ~0.5 FLOP/B), upsamples and thresholds per cell, ORs the result into the strip's union tile and
-// counts area / intersection with GT, (3) reduces the bit tiles to integer counters.  The M2 work
-// of a strip is flattened over the whole CTA -- (detection, pixel) and (detection, cell) items
-// found by a prefix-sum search -- so small boxes do not waste lanes (ncu r01a: one warp per
-// detection ran at 17 active lanes and 107 M warp instructions).  Output ownership per strip is
-// exclusive, so there are no global atomics on pixels; the last strip of an image to finish
-// turns the integer counters into Dice / IoU.
+// B200 mapping.  The prototypes are 2/3 of the path's compulsory HBM bytes and every other operand
+// is tiny, so the kernel is a PERSISTENT streamer: one 1024-thread CTA per SM owns a contiguous
+// range of strips (a strip = R "cell rows" of one image, a cell = the 4x4 output pixels between four
+// neighbouring prototype pixels) and keeps the prototype rows it needs in a shared-memory RING of
+// NS row slots (32 channels x PW floats each).  One warp feeds the ring with bulk async copies
+// (TMA, cp.async.bulk + one mbarrier per slot) as soon as a strip has released its rows, so the
+// loads always run a whole strip ahead of the arithmetic, every prototype row is read from HBM
+// once (the row shared by two consecutive strips stays in the ring; r01d: the one-strip-per-CTA
+// version sat 40 % of its time waiting for its own loads) and the GT-mask words of the next strip
+// travel in registers meanwhile.
+// Per strip the work is flattened over the CTA as two item lists found by prefix sums:
+// (entry, row, 4-pixel group) for the K=32 contraction (sequential fp32 FMA, the oracle's
+// summation order; TF32 tensor cores would break bit parity and the op is ~0.5 FLOP/B) and
+// (entry, cell) for bilinear upsample + threshold.  An entry is a detection whose crop box
+// touches the strip -- or the projector mask itself, which is just entry 0 with the projector
+// weights, the bias as initial value and the whole strip as its box, so M1 costs no extra phases.
+// Integer counters stay in registers across the strips of an image; output ownership per strip is
+// exclusive, so there are no global atomics on pixels; the last CTA to finish an image turns the
+// counters into Dice / IoU.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bt {
 
-constexpr int K3_THREADS = 256;
-constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int NM = 32;
-constexpr int CHUNK = 32;        // detections per M2 chunk
+constexpr int CHUNK = 32;        // entries per chunk
 constexpr int CF_PITCH = NM + 1; // coefficient row pitch in shared memory (bank-conflict free)
-constexpr int SCR_CAP = 2048;    // scratch pixels per M2 batch (+ one maximal piece of slack)
-constexpr int SCR_GRP = SCR_CAP / 4;
+constexpr int NS_MAX = 12;       // ring slots
 
 struct K3Params {
-    int B, S_h, S_w, PH, PW, R, K, crop, gt_f32, nstrips;
-    float rx, ry;           // proto/img ratios as the oracle computes them
+    int B, S_h, S_w, PH, PW, R, NS, K, crop, gt_f32, nstrips, total_strips, scr_cap;
     float bias;
-    const float *protos, *proj_weight, *dets, *det_coeff;
+    const float *protos, *proj_weight, *det_coeff;
     const int32_t *det_count;
     const short4 *det_region;
     const void *masks_gt;
@@ -67,6 +68,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// One prototype row of all 32 channels ([NM][PW] box of the [B*NM, PH, PW] tensor) -> one ring slot.
+__device__ __forceinline__ void tma_row_g2s(void *dst, const CUtensorMap *tm, int row, int chan0, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(chan0), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -127,16 +136,51 @@ __device__ __forceinline__ unsigned cell_valid(int ci, int cj, int S_h, int S_w)
     return m;
 }
 
-// TPW / TR > 0: compile-time prototype width / strip height (shared-memory strides become
-// immediates); 0: run-time values.
-template <int TPW, int TR>
-__global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_constant__ K3Params P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_w[NM];
+__device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w}, bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t x = wv[j];   // byte != 0 -> bit: fold each byte to its low bit, then gather the four low bits
+        x = (x | (x >> 4)) & 0x0f0f0f0fu;
+        x = (x | (x >> 2)) & 0x03030303u;
+        x = (x | (x >> 1)) & 0x01010101u;
+        bits |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (16 * half + 4 * j);
+    }
+    return bits;
+}
+
+// Strip geometry (s = strip index inside its image).
+struct StripGeo {
+    int ci_lo, ci_hi, ncr_all, p_lo, p_hi, nrows, y_lo, nyrows;
+};
+__device__ __forceinline__ StripGeo strip_geo(int s, int R, int PH, int S_h) {
+    StripGeo g;
+    g.ci_lo = (s == 0) ? -1 : s * R;
+    g.ci_hi = min(s * R + R - 1, PH - 1);
+    g.ncr_all = g.ci_hi - g.ci_lo + 1;
+    g.p_lo = s * R;
+    g.p_hi = min(g.ci_hi + 1, PH - 1);
+    g.nrows = g.p_hi - g.p_lo + 1;
+    g.y_lo = (s == 0) ? 0 : 4 * s * R + 2;
+    const int y_hi = (g.ci_hi == PH - 1) ? S_h : 4 * (g.ci_hi + 1) + 2;
+    g.nyrows = y_hi - g.y_lo;
+    return g;
+}
+
+// TPW > 0: compile-time prototype width (shared-memory strides become immediates); 0: run-time.
+template <int TPW, int K3_THREADS>
+__global__ void __launch_bounds__(K3_THREADS, K3_THREADS <= 512 ? 2 : 1)
+masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int K3_WARPS = K3_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    // TMA destinations must be 128-byte aligned: align the dynamic region by hand (128 spare bytes are allocated)
+    unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    __shared__ __align__(8) uint64_t s_bar[NS_MAX];
     __shared__ int s_nlist;
-    __shared__ int s_red[K3_WARPS][6];
+    __shared__ float s_w[NM];
+    __shared__ int s_red[K3_WARPS][5];
     __shared__ int s_last;
+    __shared__ int s_rowoff[16];   // float offset of the strip's prototype rows inside the ring
     // per-chunk piece tables
     __shared__ int s_pxoff[CHUNK + 1], s_celloff[CHUNK + 1];
     __shared__ short s_rlo[CHUNK], s_rhi[CHUNK], s_clo[CHUNK], s_chi[CHUNK];
@@ -146,16 +190,16 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     __shared__ int s_e0, s_e1;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int s = blockIdx.x, b = blockIdx.y;
-    const int PW = TPW > 0 ? TPW : P.PW, R = TR > 0 ? TR : P.R;
+    const int PW = TPW > 0 ? TPW : P.PW, R = P.R, NS = P.NS;
     const int PH = P.PH, S_w = P.S_w, S_h = P.S_h, K = P.K;
     const int rowsmax = R + 1;
-    const int CS = rowsmax * PW;   // channel stride in s_pro (floats)
     const int ncc_all = PW + 1;    // cells per cell row (incl. the border column -1)
+    const int SLOT = NM * PW;      // floats per ring slot
 
-    float *s_pro = reinterpret_cast<float *>(smem);                            // [NM][R+1][PW]
-    float *s_lm = reinterpret_cast<float *>(smem + P.off_lm);                  // [R+1][PW]
-    float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);                // [SCR_CAP + (R+1)*PW]
+    float *s_ring = reinterpret_cast<float *>(smem);                           // [NS][NM][PW]
+    float *s_lm = reinterpret_cast<float *>(smem + P.off_lm);                  // [R+1][PW] projector logits
+    float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);                // [scr_cap + (R+1)*PW]
+    const int SCR_GRP = P.scr_cap >> 2;
     uint32_t *s_gtrow = reinterpret_cast<uint32_t *>(smem + P.off_gtrow);      // [4R+2][wpr+1] row bits (bit x)
     uint32_t *s_gtc = reinterpret_cast<uint32_t *>(smem + P.off_gtc);          // [R+1][PW+1] cell bits
     uint32_t *s_m1c = reinterpret_cast<uint32_t *>(smem + P.off_m1c);          // [R+1][PW+1]
@@ -165,377 +209,391 @@ __global__ void __launch_bounds__(K3_THREADS, 2) masks_kernel(const __grid_const
     short4 *s_reg = reinterpret_cast<short4 *>(smem + P.off_reg);              // [K] crop regions (from the NMS kernel)
     const int wpr = P.wpr, tp = wpr + 1;
 
-    // ---- strip geometry
-    const int ci_lo = (s == 0) ? -1 : s * R;
-    const int ci_hi = min(s * R + R - 1, PH - 1);
-    const int ncr_all = ci_hi - ci_lo + 1;
-    const int p_lo = s * R;
-    const int p_hi = min(ci_hi + 1, PH - 1);
-    const int nrows = p_hi - p_lo + 1;
-    const int y_lo = (s == 0) ? 0 : 4 * s * R + 2;
-    const int y_hi = (ci_hi == PH - 1) ? S_h : 4 * (ci_hi + 1) + 2;
-    const int nyrows = y_hi - y_lo;
+    // ---- this CTA's contiguous range of strips
+    const int g0 = (int)(((long long)blockIdx.x * P.total_strips) / gridDim.x);
+    const int g1 = (int)(((long long)(blockIdx.x + 1) * P.total_strips) / gridDim.x);
+    if (g0 >= g1) return;
 
     BT_PHASE_INIT();
-    // ---- (a) kick off the prototype strip: one bulk async copy per channel
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+        for (int i = 0; i < NS; ++i) mbar_init(&s_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (wid == 0) {
-        const uint32_t bytes = (uint32_t)(nrows * PW * sizeof(float));
-        if (lane == 0) mbar_expect_tx(&s_bar, bytes * NM);
-        __syncwarp();
-        const float *src = P.protos + (((size_t)b * NM + lane) * PH + p_lo) * PW;
-        bulk_g2s(s_pro + (size_t)lane * CS, src, bytes, &s_bar);
-    }
 
-    // ---- (b) overlap with the copies.  All global loads of the set-up are issued first (GT mask
-    // words, crop regions written by the NMS kernel) so that their latencies overlap instead of
-    // chaining (phase counters r01c: 29 % of the CTA time sat in this block).
-    constexpr int GT_PER_THREAD = 2, REG_PER_THREAD = 2;
-    uint4 gtv[GT_PER_THREAD][2];
-    short4 regv[REG_PER_THREAD];
-#pragma unroll
-    for (int u = 0; u < GT_PER_THREAD; ++u) {
-        const int q = tid + u * K3_THREADS;
-        gtv[u][0] = gtv[u][1] = make_uint4(0, 0, 0, 0);
-        if (!P.gt_f32 && q < nyrows * wpr) {
-            const int yr = q / wpr, w = q - yr * wpr;
-            const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
-                                                             ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
-            gtv[u][0] = __ldg(g); gtv[u][1] = __ldg(g + 1);
+    // ---- producer state (warp 0; every lane tracks the same values, lane = channel)
+    // Rows are loaded in the order the strips consume them; the row shared by two consecutive strips
+    // of an image is loaded once.  Row number q of this sequence lives in slot q % NS.
+    int pg = g0, pb = g0 / P.nstrips, ps = g0 - (g0 / P.nstrips) * P.nstrips, prow = ps * R, pseq = 0;
+    int seq_base = 0;   // sequence number of the current strip's first row
+    auto top_up = [&]() {
+        // lane 0 of warp 0: fill every free slot (rows before seq_base are released), one TMA per row
+        while (pseq < seq_base + NS && pg < g1) {
+            const int p_hi = min(min(ps * R + R - 1, PH - 1) + 1, PH - 1);
+            const int slot = pseq % NS;
+            mbar_expect_tx(&s_bar[slot], (uint32_t)(SLOT * sizeof(float)));
+            tma_row_g2s(s_ring + (size_t)slot * SLOT, &tmap, prow, pb * NM, &s_bar[slot]);
+            ++pseq;
+            if (prow < p_hi) {
+                ++prow;
+            } else {
+                // next strip that brings new rows (a last strip of one row only re-uses its predecessor's)
+                for (;;) {
+                    ++pg;
+                    if (++ps == P.nstrips) { ps = 0; ++pb; }
+                    if (pg >= g1) break;
+                    const int start = (ps == 0) ? 0 : ps * R + 1;   // same image: the strip's first row is already in the ring
+                    if (start <= min(min(ps * R + R - 1, PH - 1) + 1, PH - 1)) { prow = start; break; }
+                }
+            }
         }
-    }
-#pragma unroll
-    for (int u = 0; u < REG_PER_THREAD; ++u) {
-        const int k = tid + u * K3_THREADS;
-        regv[u] = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
-    }
+    };
+    if (tid == 0) top_up();
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
-    if (tid == 0) s_nlist = 0;
-    for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) { s_m1c[i] = 0; s_unc[i] = 0; }
-    for (int q = tid; q < nyrows * tp; q += K3_THREADS) {
-        const int yr = q / tp, w = q - yr * tp;
-        if (w == wpr) s_gtrow[q] = 0;   // pad word
-    }
-    auto pack_u8 = [](const uint4 &v, int half) {
-        uint32_t wv[4] = {v.x, v.y, v.z, v.w}, bits = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t x = wv[j];   // byte != 0 -> bit: fold each byte to its low bit, then gather the four low bits
-            x = (x | (x >> 4)) & 0x0f0f0f0fu;
-            x = (x | (x >> 2)) & 0x03030303u;
-            x = (x | (x >> 1)) & 0x01010101u;
-            bits |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (16 * half + 4 * j);
+
+    // ---- GT words of a strip: one 32-pixel word (two 16-byte loads) per thread, prefetched
+    uint4 gtv0 = make_uint4(0, 0, 0, 0), gtv1 = make_uint4(0, 0, 0, 0);
+    auto gt_load = [&](int g, int b, int s) {
+        gtv0 = gtv1 = make_uint4(0, 0, 0, 0);
+        if (P.gt_f32 || g >= g1) return;
+        const StripGeo G = strip_geo(s, R, PH, S_h);
+        if (tid < G.nyrows * wpr) {
+            const int yr = tid / wpr, w = tid - yr * wpr;
+            const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
+                                                              ((size_t)b * S_h + (G.y_lo + yr)) * S_w + (size_t)w * 32);
+            gtv0 = __ldg(gp); gtv1 = __ldg(gp + 1);
         }
-        return bits;
     };
-    if (!P.gt_f32) {
+    int b = g0 / P.nstrips, s = g0 - b * P.nstrips;
+    gt_load(g0, b, s);
+
+    int c5[5] = {0, 0, 0, 0, 0};   // seg inter, seg P, G, uni inter, uni P of the current image (this thread's share)
+    int cur_b = -1, strips_of_b = 0;
+
+    // counters of image `b` -> global accumulators; the CTA that completes the image finalises it
+    auto flush_image = [&](int b, int nstrips_done) {
 #pragma unroll
-        for (int u = 0; u < GT_PER_THREAD; ++u) {
-            const int q = tid + u * K3_THREADS;
-            if (q < nyrows * wpr) {
+        for (int i = 0; i < 5; ++i) {
+            int v = c5[i];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+            if (lane == 0) s_red[wid][i] = v;
+            c5[i] = 0;
+        }
+        __syncthreads();
+        if (tid < 5) {
+            int v = 0;
+#pragma unroll
+            for (int w = 0; w < K3_WARPS; ++w) v += s_red[w][tid];
+            if (v) atomicAdd(&P.acc[b * 8 + tid], v);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&P.strip_done[b], nstrips_done) + nstrips_done == P.nstrips);
+        __syncthreads();
+        if (s_last && tid < 2) {
+            // (test_model.py:15-23)
+            __threadfence();
+            long long inter = atomicAdd(&P.acc[b * 8 + 3 * tid], 0), pp = atomicAdd(&P.acc[b * 8 + 3 * tid + 1], 0);
+            long long gg = atomicAdd(&P.acc[b * 8 + 2], 0);   // |G| is shared by both masks
+            long long total = (long long)S_h * S_w;
+            long long *img3 = tid ? P.uni_img3 : P.seg_img3;
+            long long *cnt4 = tid ? P.uni_cnt4 : P.seg_cnt4;
+            float *dice = tid ? P.uni_dice : P.seg_dice, *iou = tid ? P.uni_iou : P.seg_iou;
+            if (img3) { img3[b * 3 + 0] = inter; img3[b * 3 + 1] = pp; img3[b * 3 + 2] = gg; }
+            if (cnt4) {
+                atomicAdd((unsigned long long *)&cnt4[0], (unsigned long long)inter);
+                atomicAdd((unsigned long long *)&cnt4[1], (unsigned long long)(pp - inter));
+                atomicAdd((unsigned long long *)&cnt4[2], (unsigned long long)(gg - inter));
+                atomicAdd((unsigned long long *)&cnt4[3], (unsigned long long)(total - pp - gg + inter));
+            }
+            const float fi = (float)inter, fu = (float)(pp + gg - inter);
+            if (iou) iou[b] = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
+            if (dice) dice[b] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gg), 1e-7f));
+        }
+        __syncthreads();
+    };
+
+    for (int g = g0; g < g1; ++g) {
+        const StripGeo G = strip_geo(s, R, PH, S_h);
+        const int nb = (s + 1 == P.nstrips) ? b + 1 : b, ns = (s + 1 == P.nstrips) ? 0 : s + 1;   // next strip
+        const int ci_lo = G.ci_lo, ci_hi = G.ci_hi, ncr_all = G.ncr_all, p_lo = G.p_lo, nrows = G.nrows;
+        const int y_lo = G.y_lo, nyrows = G.nyrows;
+
+        // ---- (a) new image: flush the previous one, fetch this image's crop regions
+        if (b != cur_b) {
+            if (cur_b >= 0) flush_image(cur_b, strips_of_b);
+            cur_b = b; strips_of_b = 0;
+            for (int k = tid; k < K; k += K3_THREADS) s_reg[k] = __ldg(P.det_region + (size_t)b * K + k);
+        }
+        ++strips_of_b;
+        // ---- (b) set-up: GT words (prefetched) -> row bits, tiles cleared, detection list of the strip
+        if (tid == 0) s_nlist = 0;
+        if (tid < rowsmax) s_rowoff[tid] = ((seq_base + tid) % NS) * SLOT;
+        for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) s_unc[i] = 0;
+        for (int q = tid; q < nyrows; q += K3_THREADS) s_gtrow[q * tp + wpr] = 0;   // pad word
+        if (!P.gt_f32) {
+            if (tid < nyrows * wpr) {
+                const int yr = tid / wpr, w = tid - yr * wpr;
+                s_gtrow[yr * tp + w] = pack_u8(gtv0, 0) | pack_u8(gtv1, 1);
+            }
+            for (int q = tid + K3_THREADS; q < nyrows * wpr; q += K3_THREADS) {   // very wide images
                 const int yr = q / wpr, w = q - yr * wpr;
-                s_gtrow[yr * tp + w] = pack_u8(gtv[u][0], 0) | pack_u8(gtv[u][1], 1);
+                const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
+                                                                  ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
+                s_gtrow[yr * tp + w] = pack_u8(__ldg(gp), 0) | pack_u8(__ldg(gp + 1), 1);
+            }
+        } else {
+            for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
+                const int yr = q / wpr, w = q - yr * wpr;
+                const float4 *gp = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) +
+                                                                    ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 v = __ldg(gp + i);
+                    bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
+                            ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
+                }
+                s_gtrow[yr * tp + w] = bits;
             }
         }
-        for (int q = tid + GT_PER_THREAD * K3_THREADS; q < nyrows * wpr; q += K3_THREADS) {   // very wide images
-            const int yr = q / wpr, w = q - yr * wpr;
-            const uint4 *g = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
-                                                             ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
-            s_gtrow[yr * tp + w] = pack_u8(__ldg(g), 0) | pack_u8(__ldg(g + 1), 1);
+        gt_load(g + 1, nb, ns);   // next strip's GT words: in flight during this strip's arithmetic
+        __syncthreads();
+        // detection list of the strip (order is irrelevant: OR and integer adds commute)
+        for (int k = tid; k < K; k += K3_THREADS) {
+            const short4 rg = s_reg[k];
+            const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
+            if (ok) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)k;
         }
-    } else {
-        for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
-            const int yr = q / wpr, w = q - yr * wpr;
-            const float4 *g = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) +
-                                                               ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
-            uint32_t bits = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 v = __ldg(g + i);
-                bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
-                        ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
-            }
-            s_gtrow[yr * tp + w] = bits;
-        }
-    }
-    __syncthreads();
-    // detection list of the strip (order is irrelevant: OR and integer adds commute)
-    auto consider = [&](int k, const short4 &rg) {
-        if (k >= K) return;
-        s_reg[k] = rg;
-        const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
-        if (ok) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)k;
-    };
-#pragma unroll
-    for (int u = 0; u < REG_PER_THREAD; ++u) consider(tid + u * K3_THREADS, regv[u]);
-    for (int k = tid + REG_PER_THREAD * K3_THREADS; k < K; k += K3_THREADS) consider(k, __ldg(P.det_region + (size_t)b * K + k));
-    // GT cells from the row bits (bit x of output row y  ->  bit ry*4+rx of cell (ci, cj))
-    for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-        const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
-        const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-        const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-        unsigned bits = 0;
-        for (int ry = 0; ry < nry; ++ry) {
-            const uint32_t *row = s_gtrow + (ybase + ry - y_lo) * tp + (xbase >> 5);
-            unsigned g = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
-            bits |= g << (4 * ry);
-        }
-        s_gtc[q] = bits;
-    }
-    __syncthreads();
-    // coefficients of the first chunk of listed detections: in flight during the TMA wait and M1
-    {
-        const int nch0 = min(CHUNK, s_nlist);
-        for (int q = tid; q < nch0 * NM; q += K3_THREADS) {
-            const int e = q >> 5, i = q & 31;
-            s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[e]) * NM + i);
-        }
-    }
-
-    BT_PHASE_MARK(2, 0);   // setup: tiles, GT bits, det list
-    // ---- (c) wait for the prototypes
-    mbar_wait(&s_bar, 0);
-    __syncthreads();
-    BT_PHASE_MARK(2, 1);   // wait for TMA
-
-    // ---- (d) M1 projection: bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).
-    // Four neighbouring pixels per thread: one 16-byte shared load per channel feeds four
-    // independent FMA chains (ILP 4, a quarter of the load / address instructions).
-    for (int q = tid; q < (nrows * PW) >> 2; q += K3_THREADS) {
-        float4 acc = make_float4(P.bias, P.bias, P.bias, P.bias);
-        const float4 *pp = reinterpret_cast<const float4 *>(s_pro) + q;
-#pragma unroll
-        for (int k = 0; k < NM; ++k) {
-            const float4 v = pp[k * (CS >> 2)];
-            const float w = s_w[k];
-            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-        }
-        reinterpret_cast<float4 *>(s_lm)[q] = acc;
-    }
-    __syncthreads();
-
-    BT_PHASE_MARK(2, 2);   // M1 projection
-    // ---- (e) M1 cells -> cell tile (+ optional logits)
-    for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-        const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
-        const int r0 = max(ci, 0) - p_lo, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
-        const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
-        float lg[16];
-        const float v00 = s_lm[r0 * PW + c0], v01 = s_lm[r0 * PW + c1], v10 = s_lm[r1 * PW + c0], v11 = s_lm[r1 * PW + c1];
-        unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
-                                     : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
-        if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-        s_m1c[q] = bits;
-        if (P.seg_logits) {
+        // GT cells from the row bits (bit x of output row y  ->  bit ry*4+rx of cell (ci, cj))
+        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+            const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
             const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
             const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+            unsigned bits = 0;
             for (int ry = 0; ry < nry; ++ry) {
-                float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
-                for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
+                const uint32_t *row = s_gtrow + (ybase + ry - y_lo) * tp + (xbase >> 5);
+                unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
+                bits |= gb << (4 * ry);
             }
+            s_gtc[q] = bits;
         }
-    }
+        __syncthreads();
+        BT_PHASE_MARK(2, 0);   // set-up
+        // ---- (c) the strip's prototype rows (normally long since landed)
+        for (int i = 0; i < nrows; ++i) mbar_wait(&s_bar[(seq_base + i) % NS], (uint32_t)(((seq_base + i) / NS) & 1));
+        BT_PHASE_MARK(2, 1);   // wait for TMA
 
-    BT_PHASE_MARK(2, 3);   // M1 cells
-    // ---- (f) M2 instance masks, CHUNK detections at a time, work flattened over the CTA
-    const int nlist = s_nlist;
-    for (int ch0 = 0; ch0 < nlist; ch0 += CHUNK) {
-        const int nch = min(CHUNK, nlist - ch0);
-        __syncthreads();   // previous chunk fully consumed (tables, scratch, counters)
-        // piece tables + coefficient staging
-        if (wid == 0) {
-            int npx = 0, ncell = 0;
-            if (lane < nch) {
-                const short4 rg = s_reg[s_list[ch0 + lane]];
-                const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w;
-                const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
-                const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
-                const int ja = c_lo - 1;
-                const int pa = max(ja, 0), pb = min(c_hi + 1, PW - 1);
-                // scratch rows are stored in aligned groups of 4 prototype columns
-                const int ga = pa >> 2, ngrp = (pb >> 2) - ga + 1;
-                const int npr = pr_b - pr_a + 1;
-                const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
-                s_rlo[lane] = r_lo; s_rhi[lane] = r_hi; s_clo[lane] = c_lo; s_chi[lane] = c_hi;
-                s_pra[lane] = pr_a; s_pa[lane] = 4 * ga; s_npc[lane] = 4 * ngrp; s_cia[lane] = ci_a; s_ncc[lane] = ncc;
-                s_inpc[lane] = 1.0f / (float)ngrp; s_incc[lane] = 1.0f / (float)ncc;
-                s_area[lane] = 0; s_inter[lane] = 0;
-                npx = npr * ngrp; ncell = ncr * ncc;
-            }
-            int ipx = npx, icell = ncell;
+        // ---- (d) M1 projection: bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).  Four
+        // neighbouring pixels per thread: one 16-byte shared load per channel feeds four FMA chains.
+        for (int q = tid; q < (nrows * PW) >> 2; q += K3_THREADS) {
+            const int rr = q / (PW >> 2), cg = q - rr * (PW >> 2);
+            float4 acc = make_float4(P.bias, P.bias, P.bias, P.bias);
+            const float4 *pp = reinterpret_cast<const float4 *>(s_ring + s_rowoff[rr]) + cg;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, ipx, d), u = __shfl_up_sync(0xffffffffu, icell, d);
-                if (lane >= d) { ipx += v; icell += u; }
+            for (int k = 0; k < NM; ++k) {
+                const float4 v = pp[k * (PW >> 2)];
+                const float w = s_w[k];
+                acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+                acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
             }
-            s_pxoff[lane + 1] = ipx; s_celloff[lane + 1] = icell;
-            if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
+            reinterpret_cast<float4 *>(s_lm)[q] = acc;
         }
-        if (ch0 > 0)   // chunk 0 was staged during the set-up
+        __syncthreads();
+        BT_PHASE_MARK(2, 2);   // M1 projection
+        // ---- (e) M1 cells -> cell tile (+ optional logits)
+        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+            const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
+            const int r0 = max(ci, 0) - p_lo, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
+            const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
+            float lg[16];
+            const float v00 = s_lm[r0 * PW + c0], v01 = s_lm[r0 * PW + c1], v10 = s_lm[r1 * PW + c0], v11 = s_lm[r1 * PW + c1];
+            unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
+                                         : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
+            if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+            s_m1c[q] = bits;
+            if (P.seg_logits) {
+                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
+                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                for (int ry = 0; ry < nry; ++ry) {
+                    float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
+                    for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
+                }
+            }
+        }
+        BT_PHASE_MARK(2, 3);   // M1 cells
+        // ---- (f) M2 instance masks: listed detections, CHUNK at a time, work flattened over the CTA
+        const int nent = s_nlist;
+        const int next_base = seq_base + ((g + 1 < g1 && nb == b) ? nrows - 1 : nrows);   // rows shift (same image keeps the last row)
+        if (nent == 0) {
+            __syncthreads();   // M1 projection has read the rows
+            if (tid == 0) { seq_base = next_base; top_up(); }
+        }
+        for (int ch0 = 0; ch0 < nent; ch0 += CHUNK) {
+            const int nch = min(CHUNK, nent - ch0);
+            __syncthreads();   // previous chunk fully consumed (tables, scratch, counters)
+            // piece tables + coefficient staging
+            if (wid == 0) {
+                int npx = 0, ncell = 0;
+                if (lane < nch) {
+                    const short4 rg = s_reg[s_list[ch0 + lane]];
+                    const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w;
+                    const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
+                    const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
+                    const int ja = c_lo - 1;
+                    const int pa = max(ja, 0), pb = min(c_hi + 1, PW - 1);
+                    // scratch rows are stored in aligned groups of 4 prototype columns
+                    const int ga = pa >> 2, ngrp = (pb >> 2) - ga + 1;
+                    const int npr = pr_b - pr_a + 1;
+                    const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
+                    s_rlo[lane] = r_lo; s_rhi[lane] = r_hi; s_clo[lane] = c_lo; s_chi[lane] = c_hi;
+                    s_pra[lane] = pr_a; s_pa[lane] = 4 * ga; s_npc[lane] = 4 * ngrp; s_cia[lane] = ci_a; s_ncc[lane] = ncc;
+                    s_inpc[lane] = 1.0f / (float)ngrp; s_incc[lane] = 1.0f / (float)ncc;
+                    s_area[lane] = 0; s_inter[lane] = 0;
+                    npx = npr * ngrp; ncell = ncr * ncc;
+                }
+                int ipx = npx, icell = ncell;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, ipx, d), u = __shfl_up_sync(0xffffffffu, icell, d);
+                    if (lane >= d) { ipx += v; icell += u; }
+                }
+                s_pxoff[lane + 1] = ipx; s_celloff[lane + 1] = icell;
+                if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
+            }
             for (int q = tid; q < nch * NM; q += K3_THREADS) {
                 const int e = q >> 5, i = q & 31;
                 s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[ch0 + e]) * NM + i);
             }
-        __syncthreads();
-        BT_PHASE_MARK(2, 8);   // M2: tables + coefficient staging
-        const int nbatch = (s_pxoff[nch] + SCR_GRP - 1) / SCR_GRP;   // offsets count 4-pixel groups
-        for (int bi = 0; bi < nbatch; ++bi) {
-            // entries whose first scratch pixel falls into [bi*CAP, (bi+1)*CAP) form the batch
-            if (wid == 0) {
-                const bool in = lane < nch && (s_pxoff[lane] / SCR_GRP) == bi;
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                if (lane == 0) { s_e0 = m ? (__ffs(m) - 1) : 0; s_e1 = m ? (32 - __clz(m)) : 0; }
-            }
             __syncthreads();
-            const int e0 = s_e0, e1 = s_e1;
-            if (e1 > e0) {
-                const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
-                // cropped logits of every (detection, row, 4-pixel group) item of the batch
-                for (int q = tid; q < npx; q += K3_THREADS) {
-                    int lo = e0, hi = e1;   // last entry with pxoff <= px0 + q
-                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= q) lo = mid; else hi = mid; }
-                    const int e = lo, loc = q - (s_pxoff[e] - px0);
-                    const int ngrp = s_npc[e] >> 2;
-                    const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), gg = loc - rr * ngrp;
-                    const int r = s_pra[e] + rr, c = s_pa[e] + 4 * gg;
-                    const int c_lo = s_clo[e], c_hi = s_chi[e];
-                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (r >= s_rlo[e] && r <= s_rhi[e] && c + 3 >= c_lo && c <= c_hi) {
-                        const float4 *pp = reinterpret_cast<const float4 *>(s_pro + (r - p_lo) * PW + c);
-                        const float *cf = s_cf + e * CF_PITCH;
-#pragma unroll
-                        for (int i = 0; i < NM; ++i) {
-                            const float4 v = pp[i * (CS >> 2)];
-                            const float w = cf[i];
-                            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-                            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-                        }
-                        if (c < c_lo || c > c_hi) acc.x = 0.0f;
-                        if (c + 1 < c_lo || c + 1 > c_hi) acc.y = 0.0f;
-                        if (c + 2 < c_lo || c + 2 > c_hi) acc.z = 0.0f;
-                        if (c + 3 < c_lo || c + 3 > c_hi) acc.w = 0.0f;
-                    }
-                    reinterpret_cast<float4 *>(s_scr)[q] = acc;
+            BT_PHASE_MARK(2, 8);   // tables + coefficient staging
+            const int nbatch = s_pxoff[nch - 1] / SCR_GRP + 1;   // offsets count 4-pixel groups; the last entry's batch is the last
+            for (int bi = 0; bi < nbatch; ++bi) {
+                // entries whose first scratch group falls into [bi*GRP, (bi+1)*GRP) form the batch
+                if (wid == 0) {
+                    const bool in = lane < nch && (s_pxoff[lane] / SCR_GRP) == bi;
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (lane == 0) { s_e0 = m ? (__ffs(m) - 1) : 0; s_e1 = m ? (32 - __clz(m)) : 0; }
                 }
                 __syncthreads();
-                BT_PHASE_MARK(2, 9);   // M2: logits
-                const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
-                for (int q = tid; q < ncell; q += K3_THREADS) {
-                    int lo = e0, hi = e1;
-                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
-                    const int e = lo, loc = q - (s_celloff[e] - cl0);
-                    const int ncc = s_ncc[e], npc = s_npc[e];
-                    const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
-                    const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
-                    const int pr_a = s_pra[e], pa = s_pa[e];
-                    const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
-                    const int r0 = max(ci, 0) - pr_a, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
-                    const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
-                    float unused[16];
-                    unsigned bits = cell_bits<false>(scr[r0 * npc + c0], scr[r0 * npc + c1], scr[r1 * npc + c0],
-                                                     scr[r1 * npc + c1], ci < 0, cj < 0, unused);
-                    if (bits == 0) continue;
-                    if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-                    if (bits == 0) continue;
-                    const int cell = (ci - ci_lo) * ncc_all + cj + 1;
-                    atomicOr(&s_unc[cell], bits);
-                    atomicAdd(&s_area[e], __popc(bits));
-                    const int it = __popc(bits & s_gtc[cell]);
-                    if (it) atomicAdd(&s_inter[e], it);
+                const int e0 = s_e0, e1 = s_e1;
+                if (e1 > e0) {
+                    const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
+                    // logits of every (entry, row, 4-pixel group) item of the batch, zero outside the crop box
+                    for (int q = tid; q < npx; q += K3_THREADS) {
+                        int lo = e0, hi = e1;   // last entry with pxoff <= px0 + q
+                        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= q) lo = mid; else hi = mid; }
+                        const int e = lo, loc = q - (s_pxoff[e] - px0);
+                        const int ngrp = s_npc[e] >> 2;
+                        const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), gg = loc - rr * ngrp;
+                        const int r = s_pra[e] + rr, c = s_pa[e] + 4 * gg;
+                        const int c_lo = s_clo[e], c_hi = s_chi[e];
+                        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (r >= s_rlo[e] && r <= s_rhi[e] && c + 3 >= c_lo && c <= c_hi) {
+                            const float4 *pp = reinterpret_cast<const float4 *>(s_ring + s_rowoff[r - p_lo] + c);
+                            const float *cf = s_cf + e * CF_PITCH;
+#pragma unroll(K3_THREADS <= 256 ? 32 : 8)
+                            for (int i = 0; i < NM; ++i) {
+                                const float4 v = pp[i * (PW >> 2)];
+                                const float w = cf[i];
+                                acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+                                acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+                            }
+                            if (c < c_lo || c > c_hi) acc.x = 0.0f;
+                            if (c + 1 < c_lo || c + 1 > c_hi) acc.y = 0.0f;
+                            if (c + 2 < c_lo || c + 2 > c_hi) acc.z = 0.0f;
+                            if (c + 3 < c_lo || c + 3 > c_hi) acc.w = 0.0f;
+                        }
+                        reinterpret_cast<float4 *>(s_scr)[q] = acc;
+                    }
+                    __syncthreads();
+                    BT_PHASE_MARK(2, 9);   // logits
+                    if (ch0 + CHUNK >= nent && bi + 1 == nbatch && tid == 0) {
+                        // last contraction of the strip: its rows are released (the cells only read the
+                        // scratch), the ring is topped up while the strip finishes
+                        seq_base = next_base;
+                        top_up();
+                    }
+                    const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
+                    for (int q = tid; q < ncell; q += K3_THREADS) {
+                        int lo = e0, hi = e1;
+                        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
+                        const int e = lo, loc = q - (s_celloff[e] - cl0);
+                        const int ncc = s_ncc[e], npc = s_npc[e];
+                        const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
+                        const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
+                        const int pr_a = s_pra[e], pa = s_pa[e];
+                        const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
+                        const int r0 = max(ci, 0) - pr_a, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
+                        const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
+                        const float v00 = scr[r0 * npc + c0], v01 = scr[r0 * npc + c1], v10 = scr[r1 * npc + c0],
+                                    v11 = scr[r1 * npc + c1];
+                        const int cell = (ci - ci_lo) * ncc_all + cj + 1;
+                        const bool edge = ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1;
+                        float lg[16];
+                        unsigned bits = cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
+                        if (bits == 0) continue;
+                        if (edge) bits &= cell_valid(ci, cj, S_h, S_w);
+                        if (bits == 0) continue;
+                        atomicOr(&s_unc[cell], bits);
+                        atomicAdd(&s_area[e], __popc(bits));
+                        const int it = __popc(bits & s_gtc[cell]);
+                        if (it) atomicAdd(&s_inter[e], it);
+                    }
+                }
+                __syncthreads();
+                BT_PHASE_MARK(2, 10);  // cells
+            }
+            if (tid < nch) {
+                const int k = s_list[ch0 + tid];
+                if (s_area[tid] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[tid]);
+                if (s_inter[tid] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[tid]);
+            }
+        }
+        __syncthreads();
+
+        // ---- (e) integer counters of the strip (kept in registers) + optional dense mask output
+        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+            const uint32_t gb = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
+            c5[0] += __popc(m1 & gb); c5[1] += __popc(m1); c5[2] += __popc(gb);
+            c5[3] += __popc(un & gb); c5[4] += __popc(un);
+        }
+        if (P.seg_mask || P.uni_mask) {
+            // cell tiles -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
+            for (int q = tid; q < nyrows * ncc_all; q += K3_THREADS) {
+                const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
+                const int y = y_lo + yr;
+                const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+                const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                const int cell = (ci - ci_lo) * ncc_all + cj + 1;
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    uint8_t *dst = which ? P.uni_mask : P.seg_mask;
+                    if (!dst) continue;
+                    const unsigned nib = ((which ? s_unc : s_m1c)[cell] >> (4 * ry)) & 0xfu;
+                    uint8_t *o = dst + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
+                    *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
+                    if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
                 }
             }
-            __syncthreads();
-            BT_PHASE_MARK(2, 10);  // M2: cells
         }
-        if (tid < nch) {
-            const int k = s_list[ch0 + tid];
-            if (s_area[tid] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[tid]);
-            if (s_inter[tid] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[tid]);
-        }
+        __syncthreads();   // the strip's rows and tiles are released
+        BT_PHASE_MARK(2, 5);   // counters + dense outputs
+        seq_base = next_base;
+        b = nb; s = ns;
     }
-    __syncthreads();
-
-    BT_PHASE_MARK(2, 4);   // M2
-    // ---- (g) integer counters of the strip + optional dense mask output
-    int c5[5] = {0, 0, 0, 0, 0};  // seg inter, seg P, G, uni inter, uni P
-    for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-        const uint32_t g = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
-        c5[0] += __popc(m1 & g); c5[1] += __popc(m1); c5[2] += __popc(g);
-        c5[3] += __popc(un & g); c5[4] += __popc(un);
-    }
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        int v = c5[i];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-        if (lane == 0) s_red[wid][i] = v;
-    }
-    if (P.seg_mask || P.uni_mask) {
-        // cell tiles -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
-        for (int q = tid; q < nyrows * ncc_all; q += K3_THREADS) {
-            const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
-            const int y = y_lo + yr;
-            const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
-            const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-            const int cell = (ci - ci_lo) * ncc_all + cj + 1;
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                uint8_t *dst = which ? P.uni_mask : P.seg_mask;
-                if (!dst) continue;
-                const unsigned nib = ((which ? s_unc : s_m1c)[cell] >> (4 * ry)) & 0xfu;
-                uint8_t *o = dst + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
-                *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
-                if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < 5) {
-        int v = 0;
-#pragma unroll
-        for (int w = 0; w < K3_WARPS; ++w) v += s_red[w][tid];
-        if (v) atomicAdd(&P.acc[b * 8 + tid], v);
-    }
-    BT_PHASE_MARK(2, 5);   // counters + flush
-    // ---- (h) the last strip of the image finalises Dice / IoU (test_model.py:15-23)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&P.strip_done[b], 1) == P.nstrips - 1);
-    __syncthreads();
-    if (s_last && tid < 2) {
-        __threadfence();
-        long long inter = atomicAdd(&P.acc[b * 8 + 3 * tid], 0), pp = atomicAdd(&P.acc[b * 8 + 3 * tid + 1], 0);
-        long long gg = atomicAdd(&P.acc[b * 8 + 2], 0);   // |G| is shared by both masks
-        long long total = (long long)S_h * S_w;
-        long long *img3 = tid ? P.uni_img3 : P.seg_img3;
-        long long *cnt4 = tid ? P.uni_cnt4 : P.seg_cnt4;
-        float *dice = tid ? P.uni_dice : P.seg_dice, *iou = tid ? P.uni_iou : P.seg_iou;
-        if (img3) { img3[b * 3 + 0] = inter; img3[b * 3 + 1] = pp; img3[b * 3 + 2] = gg; }
-        if (cnt4) {
-            atomicAdd((unsigned long long *)&cnt4[0], (unsigned long long)inter);
-            atomicAdd((unsigned long long *)&cnt4[1], (unsigned long long)(pp - inter));
-            atomicAdd((unsigned long long *)&cnt4[2], (unsigned long long)(gg - inter));
-            atomicAdd((unsigned long long *)&cnt4[3], (unsigned long long)(total - pp - gg + inter));
-        }
-        const float fi = (float)inter, fu = (float)(pp + gg - inter);
-        if (iou) iou[b] = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
-        if (dice) dice[b] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gg), 1e-7f));
-    }
+    flush_image(cur_b, strips_of_b);
 }
 
-static size_t k3_layout(K3Params &P, int R) {
-    const int rowsmax = R + 1;
-    size_t off = (size_t)NM * rowsmax * P.PW * sizeof(float);
+static size_t k3_layout(K3Params &P) {
+    const int rowsmax = P.R + 1;
+    size_t off = (size_t)P.NS * NM * P.PW * sizeof(float);
     P.wpr = P.S_w / 32;
     const size_t celltile = align_up((size_t)rowsmax * (P.PW + 1) * sizeof(uint32_t), 16);
     P.off_lm = (int)off; off += (size_t)rowsmax * P.PW * sizeof(float);
-    P.off_scr = (int)off; off += (size_t)(SCR_CAP + rowsmax * P.PW) * sizeof(float);
-    P.off_gtrow = (int)off; off += align_up((size_t)(4 * R + 2) * (P.wpr + 1) * sizeof(uint32_t), 16);
+    P.off_scr = (int)off; off += (size_t)(P.scr_cap + rowsmax * P.PW) * sizeof(float);
+    P.off_gtrow = (int)off; off += align_up((size_t)(4 * P.R + 2) * (P.wpr + 1) * sizeof(uint32_t), 16);
     P.off_gtc = (int)off; off += celltile;
     P.off_m1c = (int)off; off += celltile;
     P.off_unc = (int)off; off += celltile;
@@ -545,11 +603,35 @@ static size_t k3_layout(K3Params &P, int R) {
     return off;
 }
 
-template <int TPW, int TR>
-static int launch_k3(const K3Params &P, dim3 grid, size_t smem, cudaStream_t s) {
-    if (cudaFuncSetAttribute(masks_kernel<TPW, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+// 3-D tensor map of the prototypes: dims (fastest first) {PW, PH, B*NM}, box {PW, 1, NM}.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, int PW) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) != cudaSuccess || !sym ||
+            qr != cudaDriverEntryPointSuccess)
+            return BT_ERR_CUDA;
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)B * NM};
+    const cuuint64_t gstride[2] = {(cuuint64_t)PW * sizeof(float), (cuuint64_t)PW * PH * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)PW, 1u, (cuuint32_t)NM};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(protos), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
+}
+
+template <int TPW, int NT>
+static int launch_k3(const K3Params &P, const CUtensorMap &tm, int grid, size_t smem, cudaStream_t s) {
+    if (cudaFuncSetAttribute(masks_kernel<TPW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return BT_ERR_CUDA;
-    masks_kernel<TPW, TR><<<grid, K3_THREADS, smem, s>>>(P);
+    masks_kernel<TPW, NT><<<grid, NT, smem, s>>>(P, tm);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
@@ -557,32 +639,59 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     K3Params P{};
     P.B = p.batch; P.S_h = p.img_h; P.S_w = p.img_w; P.PH = p.proto_h; P.PW = p.proto_w;
     P.K = p.max_det; P.crop = p.crop; P.gt_f32 = p.gt_mask_dtype == BT_MASK_F32;
-    P.rx = (float)((double)p.proto_w / (double)p.img_w);
-    P.ry = (float)((double)p.proto_h / (double)p.img_h);
     P.bias = p.proj_bias;
-    P.protos = io.protos; P.proj_weight = io.proj_weight; P.dets = io.dets; P.det_coeff = io.det_coeff;
+    P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
     P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region;
     P.strip_done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
     P.seg_mask = io.seg_mask; P.uni_mask = io.uni_mask; P.seg_logits = io.seg_logits;
-    // largest strip height that still lets two CTAs share an SM (227 KB, 1 KB reserved per CTA)
-    int R = 1;
-    for (int r = 8; r >= 1; --r) {
-        K3Params tmp = P;
-        if (k3_layout(tmp, r) <= 114000) { R = r; break; }
+    if (p.proto_w % 4 != 0 || p.proto_w > 256) return BT_ERR_UNSUPPORTED;   // TMA box width <= 256
+    // Two persistent 256-thread CTAs per SM (their phases overlap: the contraction is bound by shared-
+    // memory bandwidth, the upsample/threshold by the ALUs) when a ring of R + 1 rows with R >= 2 fits
+    // half an SM's shared memory -- a strip releases its rows after its last contraction, so the next
+    // strip's rows land during its second half; otherwise one 1024-thread CTA with the deepest ring.
+    int nt = 0;
+    static const bool force_fat = getenv("BTPOST_K3_FAT") != nullptr;   // developer switch (scripts/): compare the two configurations
+    for (int R = 3; R >= 2 && !nt && !force_fat; --R) {
+        K3Params tmp = P; tmp.R = R; tmp.NS = R + 1; tmp.scr_cap = 1024;
+        if ((R + 1) * P.PW <= tmp.scr_cap && k3_layout(tmp) + 128 <= 111 * 1024) { P.R = R; P.NS = R + 1; P.scr_cap = 1024; nt = 256; }
     }
-    P.R = R;
-    size_t smem = k3_layout(P, R);
-    if (smem > 220 * 1024) return BT_ERR_UNSUPPORTED;
-    P.nstrips = (p.proto_h + R - 1) / R;
-    dim3 grid(P.nstrips, p.batch);
-    if (P.PW == 160 && R == 2) return launch_k3<160, 2>(P, grid, smem, s);
-    if (P.PW == 160 && R == 3) return launch_k3<160, 3>(P, grid, smem, s);
-    if (P.PW == 256 && R == 1) return launch_k3<256, 1>(P, grid, smem, s);
-    if (P.PW == 256 && R == 2) return launch_k3<256, 2>(P, grid, smem, s);
-    return launch_k3<0, 0>(P, grid, smem, s);
+    for (int R = 4; R >= 1 && !nt; --R)
+        for (int NS = 2 * R + 1; NS >= R + 1 && !nt; --NS) {
+            if (NS > NS_MAX) continue;
+            K3Params tmp = P; tmp.R = R; tmp.NS = NS; tmp.scr_cap = 4096;
+            if (k3_layout(tmp) + 128 <= 222 * 1024) { P.R = R; P.NS = NS; P.scr_cap = 4096; nt = 1024; }
+        }
+    if (!nt) return BT_ERR_UNSUPPORTED;
+    const size_t smem = k3_layout(P) + 128;
+    P.nstrips = (p.proto_h + P.R - 1) / P.R;
+    P.total_strips = P.nstrips * p.batch;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+            return BT_ERR_CUDA;
+    }
+    const int ctas = sm_count * (nt == 256 ? 2 : 1);
+    const int grid = P.total_strips < ctas ? P.total_strips : ctas;
+    CUtensorMap tm;
+    if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
+    static const char *nt_env = getenv("BTPOST_K3_NT");   // developer switch: threads per CTA of the 2-CTA configuration
+    if (nt == 256 && nt_env && P.PW == 160) {
+        if (atoi(nt_env) == 384) return launch_k3<160, 384>(P, tm, grid, smem, s);
+        if (atoi(nt_env) == 512) return launch_k3<160, 512>(P, tm, grid, smem, s);
+    }
+    if (nt == 256) {
+        if (P.PW == 160) return launch_k3<160, 256>(P, tm, grid, smem, s);
+        if (P.PW == 256) return launch_k3<256, 256>(P, tm, grid, smem, s);
+        return launch_k3<0, 256>(P, tm, grid, smem, s);
+    }
+    if (P.PW == 160) return launch_k3<160, 1024>(P, tm, grid, smem, s);
+    if (P.PW == 256) return launch_k3<256, 1024>(P, tm, grid, smem, s);
+    return launch_k3<0, 1024>(P, tm, grid, smem, s);
 }
 
 }  // namespace bt
