@@ -35,7 +35,7 @@
 namespace bt {
 
 constexpr int NM = 32;
-constexpr int CHUNK = 32;        // entries per chunk
+constexpr int ECAP = 48;         // listed detections per round
 constexpr int CF_PITCH = NM + 1; // coefficient row pitch in shared memory (bank-conflict free)
 constexpr int NS_MAX = 12;       // ring slots
 
@@ -52,7 +52,7 @@ struct K3Params {
     uint8_t *seg_mask, *uni_mask;
     float *seg_logits;
     // shared-memory offsets (bytes)
-    int off_lm, off_scr, off_gtrow, off_gtc, off_m1c, off_unc, off_list, off_cf, off_reg, wpr;
+    int off_lm, off_scr, off_gtrow, off_gtc, off_m1c, off_unc, off_list, off_cf, wpr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,11 +167,33 @@ __device__ __forceinline__ StripGeo strip_geo(int s, int R, int PH, int S_h) {
     return g;
 }
 
+// One (detection, row, 4-pixel group) item of the K=32 contraction: logits of 4 prototype pixels,
+// zero outside the crop box.
+template <int PW4>
+__device__ __forceinline__ float4 contract4(const float4 *pp, const float *cf, int pw4_rt) {
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int st = PW4 > 0 ? PW4 : pw4_rt;
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+        const float4 v = pp[i * st];
+        const float w = cf[i];
+        acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+        acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // TPW > 0: compile-time prototype width (shared-memory strides become immediates); 0: run-time.
-template <int TPW, int K3_THREADS>
-__global__ void __launch_bounds__(K3_THREADS, K3_THREADS <= 512 ? 2 : 1)
+template <int TPW, int K3_THREADS, int MINB>
+__global__ void __launch_bounds__(K3_THREADS, MINB)
 masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
     constexpr int K3_WARPS = K3_THREADS / 32;
+    constexpr int RPL = 10;   // crop regions cached per lane of warp 0 (detections lane, lane + 32, ...)
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     // TMA destinations must be 128-byte aligned: align the dynamic region by hand (128 spare bytes are allocated)
     unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -181,13 +203,14 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     __shared__ int s_red[K3_WARPS][5];
     __shared__ int s_last;
     __shared__ int s_rowoff[16];   // float offset of the strip's prototype rows inside the ring
-    // per-chunk piece tables
-    __shared__ int s_pxoff[CHUNK + 1], s_celloff[CHUNK + 1];
-    __shared__ short s_rlo[CHUNK], s_rhi[CHUNK], s_clo[CHUNK], s_chi[CHUNK];
-    __shared__ short s_pra[CHUNK], s_pa[CHUNK], s_npc[CHUNK], s_cia[CHUNK], s_ncc[CHUNK];
-    __shared__ float s_inpc[CHUNK], s_incc[CHUNK];
-    __shared__ int s_area[CHUNK], s_inter[CHUNK];
-    __shared__ int s_e0, s_e1;
+    // per-round piece tables (a round = up to ECAP listed detections)
+    __shared__ short4 s_ereg[ECAP];
+    __shared__ int s_pxoff[ECAP + 1], s_celloff[ECAP + 1];
+    __shared__ short s_rlo[ECAP], s_rhi[ECAP], s_clo[ECAP], s_chi[ECAP];
+    __shared__ short s_pra[ECAP], s_pa[ECAP], s_npc[ECAP], s_cia[ECAP], s_ncc[ECAP];
+    __shared__ float s_inpc[ECAP], s_incc[ECAP];
+    __shared__ int s_area[ECAP], s_inter[ECAP];
+    __shared__ int s_nb, s_be[ECAP + 1];   // batches of a round: entries [s_be[i], s_be[i+1])
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int PW = TPW > 0 ? TPW : P.PW, R = P.R, NS = P.NS;
@@ -195,18 +218,17 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     const int rowsmax = R + 1;
     const int ncc_all = PW + 1;    // cells per cell row (incl. the border column -1)
     const int SLOT = NM * PW;      // floats per ring slot
+    const int SCR_GRP = P.scr_cap >> 2;
 
     float *s_ring = reinterpret_cast<float *>(smem);                           // [NS][NM][PW]
     float *s_lm = reinterpret_cast<float *>(smem + P.off_lm);                  // [R+1][PW] projector logits
     float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);                // [scr_cap + (R+1)*PW]
-    const int SCR_GRP = P.scr_cap >> 2;
     uint32_t *s_gtrow = reinterpret_cast<uint32_t *>(smem + P.off_gtrow);      // [4R+2][wpr+1] row bits (bit x)
     uint32_t *s_gtc = reinterpret_cast<uint32_t *>(smem + P.off_gtc);          // [R+1][PW+1] cell bits
     uint32_t *s_m1c = reinterpret_cast<uint32_t *>(smem + P.off_m1c);          // [R+1][PW+1]
     uint32_t *s_unc = reinterpret_cast<uint32_t *>(smem + P.off_unc);          // [R+1][PW+1]
     unsigned short *s_list = reinterpret_cast<unsigned short *>(smem + P.off_list);  // [K]
-    float *s_cf = reinterpret_cast<float *>(smem + P.off_cf);                  // [CHUNK][CF_PITCH]
-    short4 *s_reg = reinterpret_cast<short4 *>(smem + P.off_reg);              // [K] crop regions (from the NMS kernel)
+    float *s_cf = reinterpret_cast<float *>(smem + P.off_cf);                  // [ECAP][CF_PITCH]
     const int wpr = P.wpr, tp = wpr + 1;
 
     // ---- this CTA's contiguous range of strips
@@ -221,13 +243,13 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     }
     __syncthreads();
 
-    // ---- producer state (warp 0; every lane tracks the same values, lane = channel)
-    // Rows are loaded in the order the strips consume them; the row shared by two consecutive strips
-    // of an image is loaded once.  Row number q of this sequence lives in slot q % NS.
+    // ---- producer state (thread 0).  Rows are loaded in the order the strips consume them; the row
+    // shared by two consecutive strips of an image is loaded once.  Row q of this sequence lives in
+    // slot q % NS.
     int pg = g0, pb = g0 / P.nstrips, ps = g0 - (g0 / P.nstrips) * P.nstrips, prow = ps * R, pseq = 0;
     int seq_base = 0;   // sequence number of the current strip's first row
     auto top_up = [&]() {
-        // lane 0 of warp 0: fill every free slot (rows before seq_base are released), one TMA per row
+        // fill every free slot (rows before seq_base are released), one TMA per row
         while (pseq < seq_base + NS && pg < g1) {
             const int p_hi = min(min(ps * R + R - 1, PH - 1) + 1, PH - 1);
             const int slot = pseq % NS;
@@ -269,6 +291,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
 
     int c5[5] = {0, 0, 0, 0, 0};   // seg inter, seg P, G, uni inter, uni P of the current image (this thread's share)
     int cur_b = -1, strips_of_b = 0;
+    short4 myreg[RPL];             // warp 0: crop regions of detections lane + 32 i of the current image
 
     // counters of image `b` -> global accumulators; the CTA that completes the image finalises it
     auto flush_image = [&](int b, int nstrips_done) {
@@ -319,16 +342,22 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
         const int nb = (s + 1 == P.nstrips) ? b + 1 : b, ns = (s + 1 == P.nstrips) ? 0 : s + 1;   // next strip
         const int ci_lo = G.ci_lo, ci_hi = G.ci_hi, ncr_all = G.ncr_all, p_lo = G.p_lo, nrows = G.nrows;
         const int y_lo = G.y_lo, nyrows = G.nyrows;
+        const int next_base = seq_base + ((g + 1 < g1 && nb == b) ? nrows - 1 : nrows);   // rows shift (same image keeps the last row)
 
-        // ---- (a) new image: flush the previous one, fetch this image's crop regions
+        // ---- (1) new image: flush the previous one, warp 0 fetches this image's crop regions
         if (b != cur_b) {
             if (cur_b >= 0) flush_image(cur_b, strips_of_b);
             cur_b = b; strips_of_b = 0;
-            for (int k = tid; k < K; k += K3_THREADS) s_reg[k] = __ldg(P.det_region + (size_t)b * K + k);
+            if (wid == 0) {
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) {
+                    const int k = i * 32 + lane;
+                    myreg[i] = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
+                }
+            }
         }
         ++strips_of_b;
-        // ---- (b) set-up: GT words (prefetched) -> row bits, tiles cleared, detection list of the strip
-        if (tid == 0) s_nlist = 0;
+        // GT words (prefetched) -> row bits, union tile cleared
         if (tid < rowsmax) s_rowoff[tid] = ((seq_base + tid) % NS) * SLOT;
         for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) s_unc[i] = 0;
         for (int q = tid; q < nyrows; q += K3_THREADS) s_gtrow[q * tp + wpr] = 0;   // pad word
@@ -360,200 +389,248 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
         }
         gt_load(g + 1, nb, ns);   // next strip's GT words: in flight during this strip's arithmetic
         __syncthreads();
-        // detection list of the strip (order is irrelevant: OR and integer adds commute)
-        for (int k = tid; k < K; k += K3_THREADS) {
-            const short4 rg = s_reg[k];
-            const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
-            if (ok) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)k;
-        }
-        // GT cells from the row bits (bit x of output row y  ->  bit ry*4+rx of cell (ci, cj))
-        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-            const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
-            const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-            const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-            unsigned bits = 0;
-            for (int ry = 0; ry < nry; ++ry) {
-                const uint32_t *row = s_gtrow + (ybase + ry - y_lo) * tp + (xbase >> 5);
-                unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
-                bits |= gb << (4 * ry);
-            }
-            s_gtc[q] = bits;
-        }
-        __syncthreads();
-        BT_PHASE_MARK(2, 0);   // set-up
-        // ---- (c) the strip's prototype rows (normally long since landed)
-        for (int i = 0; i < nrows; ++i) mbar_wait(&s_bar[(seq_base + i) % NS], (uint32_t)(((seq_base + i) / NS) & 1));
-        BT_PHASE_MARK(2, 1);   // wait for TMA
+        BT_PHASE_MARK(2, 0);   // GT words, tiles
 
-        // ---- (d) M1 projection: bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).  Four
-        // neighbouring pixels per thread: one 16-byte shared load per channel feeds four FMA chains.
-        for (int q = tid; q < (nrows * PW) >> 2; q += K3_THREADS) {
-            const int rr = q / (PW >> 2), cg = q - rr * (PW >> 2);
-            float4 acc = make_float4(P.bias, P.bias, P.bias, P.bias);
-            const float4 *pp = reinterpret_cast<const float4 *>(s_ring + s_rowoff[rr]) + cg;
+        // piece tables of the entries [r0, r0 + nch) of the strip's list (warp 0)
+        auto build_tables = [&](int r0, int nch, bool from_list) {
+            int npx[2] = {0, 0}, ncell[2] = {0, 0};
 #pragma unroll
-            for (int k = 0; k < NM; ++k) {
-                const float4 v = pp[k * (PW >> 2)];
-                const float w = s_w[k];
-                acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-                acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-            }
-            reinterpret_cast<float4 *>(s_lm)[q] = acc;
-        }
-        __syncthreads();
-        BT_PHASE_MARK(2, 2);   // M1 projection
-        // ---- (e) M1 cells -> cell tile (+ optional logits)
-        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-            const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
-            const int r0 = max(ci, 0) - p_lo, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
-            const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
-            float lg[16];
-            const float v00 = s_lm[r0 * PW + c0], v01 = s_lm[r0 * PW + c1], v10 = s_lm[r1 * PW + c0], v11 = s_lm[r1 * PW + c1];
-            unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
-                                         : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
-            if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-            s_m1c[q] = bits;
-            if (P.seg_logits) {
-                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                for (int ry = 0; ry < nry; ++ry) {
-                    float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
-                    for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
-                }
-            }
-        }
-        BT_PHASE_MARK(2, 3);   // M1 cells
-        // ---- (f) M2 instance masks: listed detections, CHUNK at a time, work flattened over the CTA
-        const int nent = s_nlist;
-        const int next_base = seq_base + ((g + 1 < g1 && nb == b) ? nrows - 1 : nrows);   // rows shift (same image keeps the last row)
-        if (nent == 0) {
-            __syncthreads();   // M1 projection has read the rows
-            if (tid == 0) { seq_base = next_base; top_up(); }
-        }
-        for (int ch0 = 0; ch0 < nent; ch0 += CHUNK) {
-            const int nch = min(CHUNK, nent - ch0);
-            __syncthreads();   // previous chunk fully consumed (tables, scratch, counters)
-            // piece tables + coefficient staging
-            if (wid == 0) {
-                int npx = 0, ncell = 0;
-                if (lane < nch) {
-                    const short4 rg = s_reg[s_list[ch0 + lane]];
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                if (e < nch) {
+                    short4 rg;
+                    if (from_list) { rg = __ldg(P.det_region + (size_t)b * K + s_list[r0 + e]); s_ereg[e] = rg; }
+                    else rg = s_ereg[e];
                     const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w;
                     const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
                     const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
                     const int ja = c_lo - 1;
-                    const int pa = max(ja, 0), pb = min(c_hi + 1, PW - 1);
+                    const int pa = max(ja, 0), pb2 = min(c_hi + 1, PW - 1);
                     // scratch rows are stored in aligned groups of 4 prototype columns
-                    const int ga = pa >> 2, ngrp = (pb >> 2) - ga + 1;
+                    const int ga = pa >> 2, ngrp = (pb2 >> 2) - ga + 1;
                     const int npr = pr_b - pr_a + 1;
                     const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
-                    s_rlo[lane] = r_lo; s_rhi[lane] = r_hi; s_clo[lane] = c_lo; s_chi[lane] = c_hi;
-                    s_pra[lane] = pr_a; s_pa[lane] = 4 * ga; s_npc[lane] = 4 * ngrp; s_cia[lane] = ci_a; s_ncc[lane] = ncc;
-                    s_inpc[lane] = 1.0f / (float)ngrp; s_incc[lane] = 1.0f / (float)ncc;
-                    s_area[lane] = 0; s_inter[lane] = 0;
-                    npx = npr * ngrp; ncell = ncr * ncc;
+                    s_rlo[e] = r_lo; s_rhi[e] = r_hi; s_clo[e] = c_lo; s_chi[e] = c_hi;
+                    s_pra[e] = pr_a; s_pa[e] = 4 * ga; s_npc[e] = 4 * ngrp; s_cia[e] = ci_a; s_ncc[e] = ncc;
+                    s_inpc[e] = 1.0f / (float)ngrp; s_incc[e] = 1.0f / (float)ncc;
+                    s_area[e] = 0; s_inter[e] = 0;
+                    npx[h] = npr * ngrp; ncell[h] = ncr * ncc;
                 }
-                int ipx = npx, icell = ncell;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int v = __shfl_up_sync(0xffffffffu, ipx, d), u = __shfl_up_sync(0xffffffffu, icell, d);
-                    if (lane >= d) { ipx += v; icell += u; }
-                }
-                s_pxoff[lane + 1] = ipx; s_celloff[lane + 1] = icell;
-                if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
             }
+            // inclusive scans over the (up to) 64 entries: lanes, then the second half on top of the first
+            int ipx[2] = {npx[0], npx[1]}, icl[2] = {ncell[0], ncell[1]};
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int v = __shfl_up_sync(0xffffffffu, ipx[h], d), u = __shfl_up_sync(0xffffffffu, icl[h], d);
+                    if (lane >= d) { ipx[h] += v; icl[h] += u; }
+                }
+            }
+            const int tpx = __shfl_sync(0xffffffffu, ipx[0], 31), tcl = __shfl_sync(0xffffffffu, icl[0], 31);
+            ipx[1] += tpx; icl[1] += tcl;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                if (e < ECAP) { s_pxoff[e + 1] = ipx[h]; s_celloff[e + 1] = icl[h]; }
+            }
+            if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
+            // batches: consecutive entries whose first scratch group falls into the same SCR_GRP window
+            unsigned first[2];
+            {
+                const int bid0 = (ipx[0] - npx[0]) / SCR_GRP, bid1 = (ipx[1] - npx[1]) / SCR_GRP;
+                const int pb0 = __shfl_up_sync(0xffffffffu, bid0, 1), last0 = __shfl_sync(0xffffffffu, bid0, 31);
+                int pb1 = __shfl_up_sync(0xffffffffu, bid1, 1);
+                if (lane == 0) pb1 = last0;
+                first[0] = __ballot_sync(0xffffffffu, lane < nch && (lane == 0 || bid0 != pb0));
+                first[1] = __ballot_sync(0xffffffffu, lane + 32 < nch && bid1 != pb1);
+            }
+            if (lane == 0) {
+                unsigned long long m = ((unsigned long long)first[1] << 32) | first[0];
+                int nbt = 0;
+                while (m) { s_be[nbt++] = __ffsll((long long)m) - 1; m &= m - 1ull; }
+                s_be[nbt] = nch;
+                s_nb = nbt;
+            }
+        };
+
+        // ---- (2) warp 0: detection list of the strip (ordered ballot compaction of the cached regions) and
+        // the first round's piece tables; the other warps: GT cells from the row bits
+        if (wid == 0) {
+            int n = 0;
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+                const short4 rg = myreg[i];
+                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const int pos = n + __popc(m & ((1u << lane) - 1u));
+                    s_list[pos] = (unsigned short)(i * 32 + lane);
+                    if (pos < ECAP) s_ereg[pos] = rg;
+                }
+                n += __popc(m);
+            }
+            for (int k0 = RPL * 32; k0 < K; k0 += 32) {   // more detections than the register cache holds
+                const int k = k0 + lane;
+                const short4 rg = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
+                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const int pos = n + __popc(m & ((1u << lane) - 1u));
+                    s_list[pos] = (unsigned short)k;
+                    if (pos < ECAP) s_ereg[pos] = rg;
+                }
+                n += __popc(m);
+            }
+            if (lane == 0) s_nlist = n;
+            __syncwarp();
+            build_tables(0, min(n, ECAP), false);
+        } else {
+            // bit x of output row y  ->  bit ry*4+rx of cell (ci, cj)
+            for (int q = tid - 32; q < ncr_all * ncc_all; q += K3_THREADS - 32) {
+                const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
+                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
+                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                unsigned bits = 0;
+                for (int ry = 0; ry < nry; ++ry) {
+                    const uint32_t *row = s_gtrow + (ybase + ry - y_lo) * tp + (xbase >> 5);
+                    unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
+                    bits |= gb << (4 * ry);
+                }
+                s_gtc[q] = bits;
+            }
+        }
+        __syncthreads();
+        BT_PHASE_MARK(2, 1);   // list + tables | GT cells
+        const int nent = s_nlist;
+        const int nM1 = ncr_all * ncc_all;
+
+        for (int r0 = 0; r0 == 0 || r0 < nent; r0 += ECAP) {
+            const int nch = min(ECAP, nent - r0);
+            if (r0 > 0) {
+                __syncthreads();   // the previous round's tables are still being read
+                if (wid == 0) build_tables(r0, nch, true);
+                __syncthreads();
+            }
+            // coefficients of the round: asynchronous 4-byte copies into the pitched table
             for (int q = tid; q < nch * NM; q += K3_THREADS) {
                 const int e = q >> 5, i = q & 31;
-                s_cf[e * CF_PITCH + i] = __ldg(P.det_coeff + ((size_t)b * K + s_list[ch0 + e]) * NM + i);
+                cp_async4(s_cf + e * CF_PITCH + i, P.det_coeff + ((size_t)b * K + s_list[r0 + e]) * NM + i);
             }
+            if (r0 == 0) {
+                // ---- (3) the strip's prototype rows (normally long since landed), then the M1 projection:
+                // bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).  Four neighbouring
+                // pixels per thread: one 16-byte shared load per channel feeds four FMA chains.
+                for (int i = 0; i < nrows; ++i) mbar_wait(&s_bar[(seq_base + i) % NS], (uint32_t)(((seq_base + i) / NS) & 1));
+                for (int q = tid; q < (nrows * PW) >> 2; q += K3_THREADS) {
+                    const int rr = q / (PW >> 2), cg = q - rr * (PW >> 2);
+                    float4 acc = make_float4(P.bias, P.bias, P.bias, P.bias);
+                    const float4 *pp = reinterpret_cast<const float4 *>(s_ring + s_rowoff[rr]) + cg;
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) {
+                        const float4 v = pp[k * (PW >> 2)];
+                        const float w = s_w[k];
+                        acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+                        acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+                    }
+                    reinterpret_cast<float4 *>(s_lm)[q] = acc;
+                }
+            }
+            cp_async_wait_all();
             __syncthreads();
-            BT_PHASE_MARK(2, 8);   // tables + coefficient staging
-            const int nbatch = s_pxoff[nch - 1] / SCR_GRP + 1;   // offsets count 4-pixel groups; the last entry's batch is the last
-            for (int bi = 0; bi < nbatch; ++bi) {
-                // entries whose first scratch group falls into [bi*GRP, (bi+1)*GRP) form the batch
-                if (wid == 0) {
-                    const bool in = lane < nch && (s_pxoff[lane] / SCR_GRP) == bi;
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (lane == 0) { s_e0 = m ? (__ffs(m) - 1) : 0; s_e1 = m ? (32 - __clz(m)) : 0; }
+            BT_PHASE_MARK(2, 2);   // coefficients + M1 projection
+            const int nbatch = (nch > 0) ? s_nb : 0;
+            for (int bi = 0; bi == 0 || bi < nbatch; ++bi) {
+                const int e0 = (nch > 0) ? s_be[bi] : 0, e1 = (nch > 0) ? s_be[bi + 1] : 0;
+                const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
+                // ---- (4) one phase: M1 cells (first pass only) and the contraction items of the batch
+                const int nm1 = (r0 == 0 && bi == 0) ? nM1 : 0;
+                for (int q = tid; q < nm1 + npx; q += K3_THREADS) {
+                    if (q < nm1) {
+                        const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
+                        const int rr0 = max(ci, 0) - p_lo, rr1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
+                        const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
+                        float lg[16];
+                        const float v00 = s_lm[rr0 * PW + c0], v01 = s_lm[rr0 * PW + c1], v10 = s_lm[rr1 * PW + c0],
+                                    v11 = s_lm[rr1 * PW + c1];
+                        unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
+                                                     : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
+                        if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+                        s_m1c[q] = bits;
+                        if (P.seg_logits) {
+                            const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
+                            const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                            for (int ry = 0; ry < nry; ++ry) {
+                                float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
+                                for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
+                            }
+                        }
+                        continue;
+                    }
+                    const int qq = q - nm1;
+                    int lo = e0, hi = e1;   // last entry with pxoff <= px0 + qq
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= qq) lo = mid; else hi = mid; }
+                    const int e = lo, loc = qq - (s_pxoff[e] - px0);
+                    const int ngrp = s_npc[e] >> 2;
+                    const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), gg = loc - rr * ngrp;
+                    const int r = s_pra[e] + rr, c = s_pa[e] + 4 * gg;
+                    const int c_lo = s_clo[e], c_hi = s_chi[e];
+                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (r >= s_rlo[e] && r <= s_rhi[e] && c + 3 >= c_lo && c <= c_hi) {
+                        acc = contract4<(TPW >> 2)>(reinterpret_cast<const float4 *>(s_ring + s_rowoff[r - p_lo] + c),
+                                                    s_cf + e * CF_PITCH, PW >> 2);
+                        if (c < c_lo || c > c_hi) acc.x = 0.0f;
+                        if (c + 1 < c_lo || c + 1 > c_hi) acc.y = 0.0f;
+                        if (c + 2 < c_lo || c + 2 > c_hi) acc.z = 0.0f;
+                        if (c + 3 < c_lo || c + 3 > c_hi) acc.w = 0.0f;
+                    }
+                    reinterpret_cast<float4 *>(s_scr)[qq] = acc;
                 }
                 __syncthreads();
-                const int e0 = s_e0, e1 = s_e1;
-                if (e1 > e0) {
-                    const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
-                    // logits of every (entry, row, 4-pixel group) item of the batch, zero outside the crop box
-                    for (int q = tid; q < npx; q += K3_THREADS) {
-                        int lo = e0, hi = e1;   // last entry with pxoff <= px0 + q
-                        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= q) lo = mid; else hi = mid; }
-                        const int e = lo, loc = q - (s_pxoff[e] - px0);
-                        const int ngrp = s_npc[e] >> 2;
-                        const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), gg = loc - rr * ngrp;
-                        const int r = s_pra[e] + rr, c = s_pa[e] + 4 * gg;
-                        const int c_lo = s_clo[e], c_hi = s_chi[e];
-                        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        if (r >= s_rlo[e] && r <= s_rhi[e] && c + 3 >= c_lo && c <= c_hi) {
-                            const float4 *pp = reinterpret_cast<const float4 *>(s_ring + s_rowoff[r - p_lo] + c);
-                            const float *cf = s_cf + e * CF_PITCH;
-#pragma unroll(K3_THREADS <= 256 ? 32 : 8)
-                            for (int i = 0; i < NM; ++i) {
-                                const float4 v = pp[i * (PW >> 2)];
-                                const float w = cf[i];
-                                acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-                                acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-                            }
-                            if (c < c_lo || c > c_hi) acc.x = 0.0f;
-                            if (c + 1 < c_lo || c + 1 > c_hi) acc.y = 0.0f;
-                            if (c + 2 < c_lo || c + 2 > c_hi) acc.z = 0.0f;
-                            if (c + 3 < c_lo || c + 3 > c_hi) acc.w = 0.0f;
-                        }
-                        reinterpret_cast<float4 *>(s_scr)[q] = acc;
-                    }
-                    __syncthreads();
-                    BT_PHASE_MARK(2, 9);   // logits
-                    if (ch0 + CHUNK >= nent && bi + 1 == nbatch && tid == 0) {
-                        // last contraction of the strip: its rows are released (the cells only read the
-                        // scratch), the ring is topped up while the strip finishes
-                        seq_base = next_base;
-                        top_up();
-                    }
-                    const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
-                    for (int q = tid; q < ncell; q += K3_THREADS) {
-                        int lo = e0, hi = e1;
-                        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
-                        const int e = lo, loc = q - (s_celloff[e] - cl0);
-                        const int ncc = s_ncc[e], npc = s_npc[e];
-                        const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
-                        const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
-                        const int pr_a = s_pra[e], pa = s_pa[e];
-                        const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
-                        const int r0 = max(ci, 0) - pr_a, r1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
-                        const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
-                        const float v00 = scr[r0 * npc + c0], v01 = scr[r0 * npc + c1], v10 = scr[r1 * npc + c0],
-                                    v11 = scr[r1 * npc + c1];
-                        const int cell = (ci - ci_lo) * ncc_all + cj + 1;
-                        const bool edge = ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1;
-                        float lg[16];
-                        unsigned bits = cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
-                        if (bits == 0) continue;
-                        if (edge) bits &= cell_valid(ci, cj, S_h, S_w);
-                        if (bits == 0) continue;
-                        atomicOr(&s_unc[cell], bits);
-                        atomicAdd(&s_area[e], __popc(bits));
-                        const int it = __popc(bits & s_gtc[cell]);
-                        if (it) atomicAdd(&s_inter[e], it);
-                    }
+                BT_PHASE_MARK(2, 9);   // M1 cells + contraction
+                if (r0 + ECAP >= nent && bi + 1 >= nbatch && tid == 0) {
+                    // last contraction of the strip: its rows are released (the cells only read the scratch),
+                    // the ring is topped up while the strip finishes
+                    seq_base = next_base;
+                    top_up();
+                }
+                // ---- (5) upsample + threshold of every (detection, cell) item of the batch
+                const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
+                for (int q = tid; q < ncell; q += K3_THREADS) {
+                    int lo = e0, hi = e1;
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
+                    const int e = lo, loc = q - (s_celloff[e] - cl0);
+                    const int ncc = s_ncc[e], npc = s_npc[e];
+                    const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
+                    const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
+                    const int pr_a = s_pra[e], pa = s_pa[e];
+                    const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
+                    const int rr0 = max(ci, 0) - pr_a, rr1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
+                    const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
+                    const float v00 = scr[rr0 * npc + c0], v01 = scr[rr0 * npc + c1], v10 = scr[rr1 * npc + c0],
+                                v11 = scr[rr1 * npc + c1];
+                    float lg[16];
+                    unsigned bits = cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
+                    if (bits == 0) continue;
+                    if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+                    if (bits == 0) continue;
+                    const int cell = (ci - ci_lo) * ncc_all + cj + 1;
+                    atomicOr(&s_unc[cell], bits);
+                    atomicAdd(&s_area[e], __popc(bits));
+                    const int it = __popc(bits & s_gtc[cell]);
+                    if (it) atomicAdd(&s_inter[e], it);
                 }
                 __syncthreads();
                 BT_PHASE_MARK(2, 10);  // cells
             }
             if (tid < nch) {
-                const int k = s_list[ch0 + tid];
+                const int k = s_list[r0 + tid];
                 if (s_area[tid] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[tid]);
                 if (s_inter[tid] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[tid]);
             }
         }
-        __syncthreads();
 
-        // ---- (e) integer counters of the strip (kept in registers) + optional dense mask output
+        // ---- (6) integer counters of the strip (kept in registers) + optional dense mask output
         for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
             const uint32_t gb = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
             c5[0] += __popc(m1 & gb); c5[1] += __popc(m1); c5[2] += __popc(gb);
@@ -578,7 +655,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                 }
             }
         }
-        __syncthreads();   // the strip's rows and tiles are released
+        __syncthreads();   // tiles and tables are released
         BT_PHASE_MARK(2, 5);   // counters + dense outputs
         seq_base = next_base;
         b = nb; s = ns;
@@ -598,8 +675,7 @@ static size_t k3_layout(K3Params &P) {
     P.off_m1c = (int)off; off += celltile;
     P.off_unc = (int)off; off += celltile;
     P.off_list = (int)off; off += align_up((size_t)P.K * sizeof(unsigned short), 16);
-    P.off_cf = (int)off; off += align_up((size_t)CHUNK * CF_PITCH * sizeof(float), 16);
-    P.off_reg = (int)off; off += align_up((size_t)P.K * sizeof(short4), 16);
+    P.off_cf = (int)off; off += align_up((size_t)ECAP * CF_PITCH * sizeof(float), 16);
     return off;
 }
 
@@ -627,11 +703,11 @@ static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, 
     return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
 }
 
-template <int TPW, int NT>
+template <int TPW, int NT, int MINB>
 static int launch_k3(const K3Params &P, const CUtensorMap &tm, int grid, size_t smem, cudaStream_t s) {
-    if (cudaFuncSetAttribute(masks_kernel<TPW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(masks_kernel<TPW, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return BT_ERR_CUDA;
-    masks_kernel<TPW, NT><<<grid, NT, smem, s>>>(P, tm);
+    masks_kernel<TPW, NT, MINB><<<grid, NT, smem, s>>>(P, tm);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
@@ -651,18 +727,18 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     // Two persistent 256-thread CTAs per SM (their phases overlap: the contraction is bound by shared-
     // memory bandwidth, the upsample/threshold by the ALUs) when a ring of R + 1 rows with R >= 2 fits
     // half an SM's shared memory -- a strip releases its rows after its last contraction, so the next
-    // strip's rows land during its second half; otherwise one 1024-thread CTA with the deepest ring.
+    // strip's rows land during its second half; otherwise one 512-thread CTA with the deepest ring.
     int nt = 0;
     static const bool force_fat = getenv("BTPOST_K3_FAT") != nullptr;   // developer switch (scripts/): compare the two configurations
     for (int R = 3; R >= 2 && !nt && !force_fat; --R) {
-        K3Params tmp = P; tmp.R = R; tmp.NS = R + 1; tmp.scr_cap = 1024;
-        if ((R + 1) * P.PW <= tmp.scr_cap && k3_layout(tmp) + 128 <= 111 * 1024) { P.R = R; P.NS = R + 1; P.scr_cap = 1024; nt = 256; }
+        K3Params tmp = P; tmp.R = R; tmp.NS = R + 1; tmp.scr_cap = 1792;
+        if ((R + 1) * P.PW <= tmp.scr_cap && k3_layout(tmp) + 128 <= 111 * 1024) { P.R = R; P.NS = R + 1; P.scr_cap = 1792; nt = 256; }
     }
     for (int R = 4; R >= 1 && !nt; --R)
         for (int NS = 2 * R + 1; NS >= R + 1 && !nt; --NS) {
             if (NS > NS_MAX) continue;
             K3Params tmp = P; tmp.R = R; tmp.NS = NS; tmp.scr_cap = 4096;
-            if (k3_layout(tmp) + 128 <= 222 * 1024) { P.R = R; P.NS = NS; P.scr_cap = 4096; nt = 1024; }
+            if (k3_layout(tmp) + 128 <= 222 * 1024) { P.R = R; P.NS = NS; P.scr_cap = 4096; nt = 512; }
         }
     if (!nt) return BT_ERR_UNSUPPORTED;
     const size_t smem = k3_layout(P) + 128;
@@ -681,17 +757,17 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
     static const char *nt_env = getenv("BTPOST_K3_NT");   // developer switch: threads per CTA of the 2-CTA configuration
     if (nt == 256 && nt_env && P.PW == 160) {
-        if (atoi(nt_env) == 384) return launch_k3<160, 384>(P, tm, grid, smem, s);
-        if (atoi(nt_env) == 512) return launch_k3<160, 512>(P, tm, grid, smem, s);
+        if (atoi(nt_env) == 384) return launch_k3<160, 384, 2>(P, tm, grid, smem, s);
+        if (atoi(nt_env) == 512) return launch_k3<160, 512, 2>(P, tm, grid, smem, s);
     }
     if (nt == 256) {
-        if (P.PW == 160) return launch_k3<160, 256>(P, tm, grid, smem, s);
-        if (P.PW == 256) return launch_k3<256, 256>(P, tm, grid, smem, s);
-        return launch_k3<0, 256>(P, tm, grid, smem, s);
+        if (P.PW == 160) return launch_k3<160, 256, 2>(P, tm, grid, smem, s);
+        if (P.PW == 256) return launch_k3<256, 256, 2>(P, tm, grid, smem, s);
+        return launch_k3<0, 256, 2>(P, tm, grid, smem, s);
     }
-    if (P.PW == 160) return launch_k3<160, 1024>(P, tm, grid, smem, s);
-    if (P.PW == 256) return launch_k3<256, 1024>(P, tm, grid, smem, s);
-    return launch_k3<0, 1024>(P, tm, grid, smem, s);
+    if (P.PW == 160) return launch_k3<160, 512, 1>(P, tm, grid, smem, s);
+    if (P.PW == 256) return launch_k3<256, 512, 1>(P, tm, grid, smem, s);
+    return launch_k3<0, 512, 1>(P, tm, grid, smem, s);
 }
 
 }  // namespace bt

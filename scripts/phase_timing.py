@@ -22,7 +22,7 @@ n = 10
 for _ in range(n): pp.run(*args)
 torch.cuda.synchronize(); L.btpost_debug_phase_cycles(buf, 1)
 names = {1: {0: "sort", 1: "stage window", 3: "chunks (tail mark)", 8: "chunk A", 11: "chunk B", 9: "chunk C", 10: "chunk insert", 6: "package", 7: "COCO match (other kernel)"},
-         2: {0: "setup", 1: "wait TMA", 8: "tables+coef", 9: "logits", 10: "cells", 5: "counters+dense out"}}
+         2: {0: "GT words+tiles", 1: "list+tables | GT cells", 2: "coef + M1 proj", 9: "M1 cells + contraction", 10: "cells", 5: "counters+dense out"}}
 for k, nb in ((1, B), (2, None)):
     tot = sum(buf[k * 16 + i] for i in range(16))
     print(f"kernel {k}: total cycles/launch {tot / n:.0f}")
