@@ -142,7 +142,8 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rc = launch_decode_filter(*p, *io, w, s);
     if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s);
-    if (rc == BT_OK) rc = launch_masks(*p, *io, w, s);
+    // the mask kernel overlaps the COCO matching kernel (launched last by the NMS stage) when there is one
+    if (rc == BT_OK) rc = launch_masks(*p, *io, w, s, io->dt_match != nullptr);
     return rc;
 }
 

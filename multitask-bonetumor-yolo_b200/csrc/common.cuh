@@ -102,6 +102,8 @@ static inline Workspace carve(const BtParams *p, void *base) {
 int check_params(const BtParams *p, const BtIO *io);
 int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s);
 int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s);
-int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s);
+// pdl: launch as a programmatic dependent of the preceding kernel in the stream (match_kernel, which the
+// mask kernel neither reads from nor writes to)
+int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, bool pdl = false);
 
 }  // namespace bt

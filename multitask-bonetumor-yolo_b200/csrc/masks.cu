@@ -661,6 +661,9 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
         b = nb; s = ns;
     }
     flush_image(cur_b, strips_of_b);
+    // When launched as a programmatic dependent (of the COCO matching kernel, whose data this kernel never
+    // touches) the completion of this grid must still imply the completion of that one; it finished long ago.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 static size_t k3_layout(K3Params &P) {
@@ -703,15 +706,23 @@ static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, 
     return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
 }
 
+static bool g_pdl = false;   // set by launch_masks for the launch below (host-side, per call)
 template <int TPW, int NT, int MINB>
 static int launch_k3(const K3Params &P, const CUtensorMap &tm, int grid, size_t smem, cudaStream_t s) {
     if (cudaFuncSetAttribute(masks_kernel<TPW, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return BT_ERR_CUDA;
-    masks_kernel<TPW, NT, MINB><<<grid, NT, smem, s>>>(P, tm);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, masks_kernel<TPW, NT, MINB>, P, tm) != cudaSuccess) return BT_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
-int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
+int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, bool pdl) {
+    g_pdl = pdl;
     K3Params P{};
     P.B = p.batch; P.S_h = p.img_h; P.S_w = p.img_w; P.PH = p.proto_h; P.PW = p.proto_w;
     P.K = p.max_det; P.crop = p.crop; P.gt_f32 = p.gt_mask_dtype == BT_MASK_F32;

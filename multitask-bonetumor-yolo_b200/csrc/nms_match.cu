@@ -28,9 +28,11 @@
 //              culled, spent 365 k cycles per image there).
 //   3. package boxes / scores / labels / keep indices / crop regions of the kept detections.
 // The exact IoU decision uses a guarded approximate division (see suppresses()).
-// gather_match_kernel then spreads the mask-coefficient gather (K x 32 scattered 4-byte reads per
-// image: latency-bound on one SM, r01e 16 us) over the whole GPU and runs COCOeval's per-image
-// matching in one extra CTA per image beside it.
+// coeff_gather_kernel spreads the mask-coefficient gather (K x 32 scattered 4-byte reads per image:
+// latency-bound on one SM, r01e 16 us; gathering for every CANDIDATE in the decode kernel instead
+// tripled the scattered DRAM sectors and cost 19 us, r01u) over the whole GPU.  match_kernel runs
+// COCOeval's per-image matching, one CTA per image; the mask kernel is launched as its programmatic
+// dependent and overlaps it.
 #include "common.cuh"
 
 namespace bt {
@@ -38,7 +40,7 @@ namespace bt {
 constexpr int K2_THREADS = 1024;
 constexpr int NMS_CHUNK = 64;
 constexpr int SORT_REG_MAX = 16384;  // keys sorted in registers (16 per thread) up to this many
-constexpr int GM_THREADS = 256;      // gather_match_kernel block: 8 detections x 32 coefficients
+constexpr int GM_THREADS = 256;      // match_kernel block
 constexpr int MAX_CELLS = 256;
 
 __device__ __forceinline__ uint32_t desc_key(float s) {
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
             P.det_anchor[(size_t)b * K + k] = -1;
         }
     }
-    // clear the matching table (filled by gather_match_kernel)
+    // clear the matching table (filled by match_kernel)
     if (P.dt_match) {
         const size_t per_img = (size_t)BT_NUM_AREA * P.T * K;
         int32_t *dm = P.dt_match + (size_t)b * per_img;
@@ -498,27 +500,33 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
 }
 
 // =================================================================================================
-// mask-coefficient gather (grid-wide) + COCOeval.evaluateImg (one CTA per image)
+// mask-coefficient gather, spread over the whole GPU: 8 detections x 32 coefficients per CTA
 // =================================================================================================
-__global__ void __launch_bounds__(GM_THREADS) gather_match_kernel(const __grid_constant__ K2Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+__global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_constant__ K2Params P) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int K = P.max_det;
-    const int ngather = (K + 7) / 8;
-    if ((int)blockIdx.x < ngather) {
-        // 8 detections x 32 coefficients per CTA: K x 32 independent scattered reads per image
-        const int k = blockIdx.x * 8 + wid, m = lane;
-        if (k >= K) return;
-        const int a = P.det_anchor[(size_t)b * K + k];
-        float v = 0.0f;
-        if (a >= 0) {
-            const float *src = (P.layout == BT_LAYOUT_L2) ? P.head + ((size_t)b * P.C + 4 + P.nc) * P.N
-                                                          : P.coeffs + (size_t)b * P.nm * P.N;
-            v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
-        }
-        P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
-        return;
+    const int k = blockIdx.x * 8 + wid, m = lane;
+    if (k >= K) return;
+    const int a = P.det_anchor[(size_t)b * K + k];
+    float v = 0.0f;
+    if (a >= 0) {
+        const float *src = (P.layout == BT_LAYOUT_L2) ? P.head + ((size_t)b * P.C + 4 + P.nc) * P.N
+                                                      : P.coeffs + (size_t)b * P.nm * P.N;
+        v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
     }
+    P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
+}
+
+// =================================================================================================
+// COCOeval.evaluateImg (one CTA per image)
+// =================================================================================================
+__global__ void __launch_bounds__(GM_THREADS) match_kernel(const __grid_constant__ K2Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K = P.max_det;
+    // the mask kernel does not read anything this kernel writes: let it start right away
+    // (programmatic dependent launch; it never waits on this grid)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (P.dt_match == nullptr) return;
     BT_PHASE_INIT();
     // ---- COCOeval.evaluateImg for every (class, area range, IoU threshold)
@@ -693,7 +701,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     size_t smem_a = region0 + (size_t)K2_TAIL_WIN * 48 + (size_t)p.max_det * 48 + 64;
     if (smem_a < (size_t)sort_slots * 8) smem_a = (size_t)sort_slots * 8;
     if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
-    // gather_match_kernel: COCO tables
+    // match_kernel: COCO tables
     const int coco_doubles = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;   // boxes + room for a [K x 4] IoU block
     P.coco_smem_doubles = coco_doubles;
     const size_t smem_b = (size_t)coco_doubles * 8 + (size_t)p.max_det * 12;
@@ -701,12 +709,13 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(gather_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+            cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
         attr_set = true;
     }
     nms_kernel<<<p.batch, K2_THREADS, smem_a, s>>>(P);
-    gather_match_kernel<<<dim3((p.max_det + 7) / 8 + 1, p.batch), GM_THREADS, smem_b, s>>>(P);
+    coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);
+    if (io.dt_match) match_kernel<<<p.batch, GM_THREADS, smem_b, s>>>(P);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
