@@ -19,6 +19,8 @@ pytestmark = pytest.mark.gpu
     dict(conf_thres=0.999),                         # nothing passes the filter
     dict(conf_thres=0.5, iou_thres=0.3),
     dict(max_cand=500),
+    dict(crop=0, max_det=100),                      # every detection on every strip: several rounds / scratch batches
+    dict(max_det=400),                              # more detections than the mask kernel's register cache of regions
 ])
 def test_pipeline_matches_oracle_640(kw):
     batch = helpers.make(batch=2, img_size=640)
