@@ -291,6 +291,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
 
     int c5[5] = {0, 0, 0, 0, 0};   // seg inter, seg P, G, uni inter, uni P of the current image (this thread's share)
     int cur_b = -1, strips_of_b = 0;
+    bool prebuilt = false;         // the current strip's list + tables were built during the previous strip
     short4 myreg[RPL];             // warp 0: crop regions of detections lane + 32 i of the current image
 
     // counters of image `b` -> global accumulators; the CTA that completes the image finalises it
@@ -392,7 +393,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
         BT_PHASE_MARK(2, 0);   // GT words, tiles
 
         // piece tables of the entries [r0, r0 + nch) of the strip's list (warp 0)
-        auto build_tables = [&](int r0, int nch, bool from_list) {
+        auto build_tables = [&](int r0, int nch, bool from_list, int ci_lo, int ci_hi) {
             int npx[2] = {0, 0}, ncell[2] = {0, 0};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -454,14 +455,14 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             }
         };
 
-        // ---- (2) warp 0: detection list of the strip (ordered ballot compaction of the cached regions) and
-        // the first round's piece tables; the other warps: GT cells from the row bits
-        if (wid == 0) {
+        // detection list of a strip of this image (ordered ballot compaction of the cached regions) and the
+        // first round's piece tables (warp 0)
+        auto list_and_tables = [&](int lo, int hi) {
             int n = 0;
 #pragma unroll
             for (int i = 0; i < RPL; ++i) {
                 const short4 rg = myreg[i];
-                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
+                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, lo) <= min((int)rg.y, hi);
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (ok) {
                     const int pos = n + __popc(m & ((1u << lane) - 1u));
@@ -473,7 +474,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             for (int k0 = RPL * 32; k0 < K; k0 += 32) {   // more detections than the register cache holds
                 const int k = k0 + lane;
                 const short4 rg = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
-                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, ci_lo) <= min((int)rg.y, ci_hi);
+                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, lo) <= min((int)rg.y, hi);
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (ok) {
                     const int pos = n + __popc(m & ((1u << lane) - 1u));
@@ -484,10 +485,15 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             }
             if (lane == 0) s_nlist = n;
             __syncwarp();
-            build_tables(0, min(n, ECAP), false);
-        } else {
+            build_tables(0, min(n, ECAP), false, lo, hi);
+        };
+        // ---- (2) GT cells from the row bits; warp 0 builds the strip's list + tables first unless the
+        // previous strip already did (during its counters phase)
+        if (wid == 0 && !prebuilt) list_and_tables(ci_lo, ci_hi);
+        {
             // bit x of output row y  ->  bit ry*4+rx of cell (ci, cj)
-            for (int q = tid - 32; q < ncr_all * ncc_all; q += K3_THREADS - 32) {
+            const int q0 = prebuilt ? tid : tid - 32, qs = prebuilt ? K3_THREADS : K3_THREADS - 32;
+            for (int q = q0; q < ncr_all * ncc_all && q >= 0; q += qs) {
                 const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
                 const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
                 const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
@@ -509,7 +515,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             const int nch = min(ECAP, nent - r0);
             if (r0 > 0) {
                 __syncthreads();   // the previous round's tables are still being read
-                if (wid == 0) build_tables(r0, nch, true);
+                if (wid == 0) build_tables(r0, nch, true, ci_lo, ci_hi);
                 __syncthreads();
             }
             // coefficients of the round: asynchronous 4-byte copies into the pitched table
@@ -623,41 +629,56 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                 __syncthreads();
                 BT_PHASE_MARK(2, 10);  // cells
             }
-            if (tid < nch) {
-                const int k = s_list[r0 + tid];
-                if (s_area[tid] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[tid]);
-                if (s_inter[tid] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[tid]);
+            if (wid == 0) {   // warp 0 alone reads the round's tables here: it rebuilds them below
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = lane + 32 * h;
+                    if (e < nch) {
+                        const int k = s_list[r0 + e];
+                        if (s_area[e] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[e]);
+                        if (s_inter[e] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[e]);
+                    }
+                }
             }
         }
 
-        // ---- (6) integer counters of the strip (kept in registers) + optional dense mask output
-        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-            const uint32_t gb = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
-            c5[0] += __popc(m1 & gb); c5[1] += __popc(m1); c5[2] += __popc(gb);
-            c5[3] += __popc(un & gb); c5[4] += __popc(un);
-        }
-        if (P.seg_mask || P.uni_mask) {
-            // cell tiles -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
-            for (int q = tid; q < nyrows * ncc_all; q += K3_THREADS) {
-                const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
-                const int y = y_lo + yr;
-                const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
-                const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                const int cell = (ci - ci_lo) * ncc_all + cj + 1;
+        // ---- (6) integer counters of the strip (kept in registers) + optional dense mask output; warp 0
+        // builds the next strip's detection list + tables meanwhile when it belongs to the same image
+        const bool prebuild_next = (g + 1 < g1) && nb == b;
+        if (prebuild_next && wid == 0) {
+            const StripGeo GN = strip_geo(ns, R, PH, S_h);
+            list_and_tables(GN.ci_lo, GN.ci_hi);
+        } else {
+            const int q0 = prebuild_next ? tid - 32 : tid, qs = prebuild_next ? K3_THREADS - 32 : K3_THREADS;
+            for (int q = q0; q < ncr_all * ncc_all; q += qs) {
+                const uint32_t gb = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
+                c5[0] += __popc(m1 & gb); c5[1] += __popc(m1); c5[2] += __popc(gb);
+                c5[3] += __popc(un & gb); c5[4] += __popc(un);
+            }
+            if (P.seg_mask || P.uni_mask) {
+                // cell tiles -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
+                for (int q = q0; q < nyrows * ncc_all; q += qs) {
+                    const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
+                    const int y = y_lo + yr;
+                    const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+                    const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                    const int cell = (ci - ci_lo) * ncc_all + cj + 1;
 #pragma unroll
-                for (int which = 0; which < 2; ++which) {
-                    uint8_t *dst = which ? P.uni_mask : P.seg_mask;
-                    if (!dst) continue;
-                    const unsigned nib = ((which ? s_unc : s_m1c)[cell] >> (4 * ry)) & 0xfu;
-                    uint8_t *o = dst + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
-                    *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
-                    if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
+                    for (int which = 0; which < 2; ++which) {
+                        uint8_t *dst = which ? P.uni_mask : P.seg_mask;
+                        if (!dst) continue;
+                        const unsigned nib = ((which ? s_unc : s_m1c)[cell] >> (4 * ry)) & 0xfu;
+                        uint8_t *o = dst + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
+                        *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
+                        if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
+                    }
                 }
             }
         }
         __syncthreads();   // tiles and tables are released
         BT_PHASE_MARK(2, 5);   // counters + dense outputs
         seq_base = next_base;
+        prebuilt = prebuild_next;
         b = nb; s = ns;
     }
     flush_image(cur_b, strips_of_b);

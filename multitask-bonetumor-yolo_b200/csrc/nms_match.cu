@@ -239,8 +239,10 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
     int *s_knext = s_korig + K;                                                              // [K] next kept box of the same cell
     int *s_scell = s_knext + K;                                                              // [WIN] packed cell range under the box
     __shared__ unsigned int s_row32[NMS_CHUNK * 2];
-    __shared__ int s_cellhead[MAX_CELLS];
+    __shared__ int s_cellhead[MAX_CELLS], s_celltail[MAX_CELLS];
     __shared__ unsigned int s_supA[2];
+    __shared__ int s_anyrow;
+    __shared__ unsigned short s_pair[NMS_CHUNK * (NMS_CHUNK - 1) / 2];   // (i << 8) | j for every pair i < j of a chunk
     __shared__ unsigned long long s_keepm;
 
     BT_PHASE_INIT();
@@ -251,7 +253,9 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
         if (P.inst_inter) P.inst_inter[(size_t)b * K + i] = 0;
     }
-    if (tid < MAX_CELLS) s_cellhead[tid] = -1;
+    if (tid < MAX_CELLS) { s_cellhead[tid] = -1; s_celltail[tid] = -1; }
+    if (tid >= 1 && tid < NMS_CHUNK)
+        for (int i = 0; i < tid; ++i) s_pair[tid * (tid - 1) / 2 + i] = (unsigned short)((i << 8) | tid);
     const int M = P.n_cand[b];
     const float4 *cbox = P.cand_box + (size_t)b * P.cap;
     const float *cscore = P.cand_score + (size_t)b * P.cap;
@@ -326,121 +330,136 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
         // (c) the chunks, in order
         for (int c0 = 0; c0 < wn && nkept < K; c0 += NMS_CHUNK) {
             const int n_in = min(NMS_CHUNK, wn - c0);
+            if (tid < 2 * NMS_CHUNK) s_row32[tid] = 0;
             if (tid < 2) s_supA[tid] = 0;
+            if (tid == 2) s_anyrow = 0;
             __syncthreads();
-            // (A) chunk vs kept boxes, 16 threads per candidate.  Centre-cull mode: only kept boxes
-            // whose centre lies in a cell under the candidate's box can suppress it (one cell per
-            // thread for boxes of up to 4 x 4 cells); otherwise the threads stride over all kept boxes.
-            {
+            // (A) chunk vs kept boxes.  Centre-cull mode: only kept boxes whose centre lies in a cell under
+            // the candidate's box can suppress it; 4 threads per candidate walk those cells (8 warps: the
+            // phase is issue-bound, r01k).  Otherwise 16 threads per candidate stride over all kept boxes.
+#ifdef BT_PHASE_TIMING
+            const long long _a0 = clock64();
+#endif
+            if (P.centre_cull) {
+                if (tid < 4 * NMS_CHUNK) {
+                    const int ci = tid >> 2, sub = tid & 3;
+                    bool f = false;
+                    if (ci < n_in) {
+                        const float4 bj = s_sbox[c0 + ci];
+                        const float2 cj = s_sctr[c0 + ci];
+                        const float aj = s_sarea[c0 + ci];
+                        const int lj = s_slabel[c0 + ci];
+                        const int pc = s_scell[c0 + ci];
+                        const int gx0 = pc & 15, gy0 = (pc >> 4) & 15, ncx = (pc >> 8) & 31, ncy = (pc >> 13) & 31;
+                        int qx = sub, qy = 0;   // cells sub, sub + 4, ... in row-major order (ncx >= 1)
+                        while (qx >= ncx) { qx -= ncx; ++qy; }
+                        while (qy < ncy && !f) {
+                            // lists are in keep order: the strongest box of a cluster comes first and usually settles it
+                            for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0 && !f; k = s_knext[k]) {
+                                const float2 ck = s_kctr[k];
+                                if (!(ck.x >= bj.x && ck.x <= bj.z && ck.y >= bj.y && ck.y <= bj.w)) continue;
+                                f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                               P.class_mode, 1, cj.x, cj.y, P.fast);
+                            }
+                            qx += 4;
+                            while (qx >= ncx) { qx -= ncx; ++qy; }
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, f);
+                    if ((lane & 3) == 0 && ((m >> lane) & 0xfu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
+                }
+            } else {
                 const int ci = tid >> 4, sub = tid & 15;
                 bool f = false;
                 if (ci < n_in) {
                     const float4 bj = s_sbox[c0 + ci];
-                    const float2 cj = s_sctr[c0 + ci];
                     const float aj = s_sarea[c0 + ci];
                     const int lj = s_slabel[c0 + ci];
-                    if (P.centre_cull) {
-                        const int pc = s_scell[c0 + ci];
-                        const int gx0 = pc & 15, gy0 = (pc >> 4) & 15, ncx = (pc >> 8) & 31, ncy = (pc >> 13) & 31;
-                        int qx = sub % ncx, qy = sub / ncx;   // cells q = sub, sub + 16, ... in row-major order (ncx >= 1)
-                        for (int q = sub; q < ncx * ncy; q += 16) {
-                            for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0; k = s_knext[k]) {
-                                const float2 ck = s_kctr[k];
-                                if (!(ck.x >= bj.x && ck.x <= bj.z && ck.y >= bj.y && ck.y <= bj.w)) continue;
-                                f |= suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
-                                                P.class_mode, 1, cj.x, cj.y, P.fast);
-                            }
-                            qx += 16;
-                            while (qx >= ncx) { qx -= ncx; ++qy; }
-                        }
-                    } else {
-                        for (int k = sub; k < nkept; k += 16)
-                            f |= suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
-                                            P.class_mode, 0, 0.0f, 0.0f, P.fast);
-                    }
+                    for (int k = sub; k < nkept && !f; k += 16)
+                        f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                       P.class_mode, 0, 0.0f, 0.0f, P.fast);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, f);
                 if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
             }
+#ifdef BT_PHASE_TIMING
+            {
+                const unsigned dt = (unsigned)(clock64() - _a0);
+                const unsigned mx = __reduce_max_sync(0xffffffffu, dt);
+                if (lane == 0 && wid < 8) { atomicAdd(&g_phase_cycles[1][12], (unsigned long long)mx); atomicAdd(&g_phase_cycles[1][13], 1ull); }
+                if (lane == 0 && wid >= 8) { atomicAdd(&g_phase_cycles[1][14], (unsigned long long)mx); }
+            }
+#endif
             __syncthreads();
             BT_PHASE_MARK(1, 8);   // chunk: A
             // (B) "who suppresses me" rows of the candidates A left undecided, against the undecided
-            // earlier candidates of the chunk only (a cluster of hundreds of candidates on one object
-            // is settled by A as soon as its leader is kept).  Warp task = (row j, half of the chunk);
-            // lanes = earlier candidates i; the exact IoU runs only when some lane passes the cheap test.
+            // earlier candidates of the chunk only (a cluster of hundreds of candidates on one object is
+            // settled by A as soon as its leader is kept).  One thread per pair (i < j) of the chunk, from a
+            // table of the 2016 pairs; the exact IoU runs only for pairs that pass the cheap necessary test.
             const unsigned long long valid = (n_in == 64) ? ~0ull : ((1ull << n_in) - 1ull);
             const unsigned long long und0 = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int task = wid * 4 + r, jo = task >> 1, half = task & 1;
-                const unsigned hm = (unsigned)(und0 >> (32 * half)) & ((jo >= 32 * half + 32) ? 0xffffffffu
-                                                : (jo > 32 * half ? ((1u << (jo - 32 * half)) - 1u) : 0u));
-                unsigned m = 0u;
-                if (((und0 >> jo) & 1ull) && hm) {
-                    const int j = c0 + jo, i = c0 + 32 * half + lane;
-                    const float4 bj = s_sbox[j];
-                    const float2 cj = s_sctr[j];
-                    bool pass = false;
-                    float4 bi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if ((hm >> lane) & 1u) {
-                        bi = s_sbox[i];
-                        if (P.centre_cull) {
-                            const float2 ci = s_sctr[i];
-                            pass = ci.x >= bj.x && ci.x <= bj.z && ci.y >= bj.y && ci.y <= bj.w &&
-                                   cj.x >= bi.x && cj.x <= bi.z && cj.y >= bi.y && cj.y <= bi.w;
-                        } else if (P.early_out) {
-                            pass = fminf(bi.z, bj.z) > fmaxf(bi.x, bj.x) && fminf(bi.w, bj.w) > fmaxf(bi.y, bj.y);
-                        } else {
-                            pass = true;
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, pass)) {
-                        bool f = false;
-                        if (pass)
-                            f = suppresses(bi, s_sarea[i], s_slabel[i], bj, s_sarea[j], s_slabel[j], P.thr_up, P.early_out,
-                                           P.class_mode, P.centre_cull, cj.x, cj.y, P.fast);
-                        m = __ballot_sync(0xffffffffu, f);
-                    }
+            for (int pq = tid; pq < NMS_CHUNK * (NMS_CHUNK - 1) / 2; pq += K2_THREADS) {
+                const int pr = s_pair[pq], io = pr >> 8, jo = pr & 255;
+                if (!((und0 >> io) & (und0 >> jo) & 1ull)) continue;
+                const int i = c0 + io, j = c0 + jo;
+                const float4 bi = s_sbox[i], bj = s_sbox[j];
+                const float2 cj = s_sctr[j];
+                if (P.centre_cull) {
+                    const float2 ci = s_sctr[i];
+                    if (!(ci.x >= bj.x && ci.x <= bj.z && ci.y >= bj.y && ci.y <= bj.w && cj.x >= bi.x && cj.x <= bi.z &&
+                          cj.y >= bi.y && cj.y <= bi.w))
+                        continue;
+                } else if (P.early_out) {
+                    if (!(fminf(bi.z, bj.z) > fmaxf(bi.x, bj.x) && fminf(bi.w, bj.w) > fmaxf(bi.y, bj.y))) continue;
                 }
-                if (lane == 0) s_row32[jo * 2 + half] = m;
+                if (suppresses(bi, s_sarea[i], s_slabel[i], bj, s_sarea[j], s_slabel[j], P.thr_up, P.early_out, P.class_mode,
+                               P.centre_cull, cj.x, cj.y, P.fast)) {
+                    atomicOr(&s_row32[jo * 2 + (io >> 5)], 1u << (io & 31));
+                    s_anyrow = 1;
+                }
             }
             __syncthreads();
             BT_PHASE_MARK(1, 11);  // chunk: B
-            // (C) one warp resolves the chunk as a fixpoint over the rows (lane: rows lane, lane + 32)
-            if (wid == 0) {
-                const unsigned long long row_a = ((unsigned long long)s_row32[lane * 2 + 1] << 32) | s_row32[lane * 2];
-                const unsigned long long row_b = ((unsigned long long)s_row32[(lane + 32) * 2 + 1] << 32) | s_row32[(lane + 32) * 2];
-                unsigned long long und = und0, keepm = 0ull;
-                if (__any_sync(0xffffffffu, (row_a | row_b) != 0ull)) {
+            unsigned long long keepm;
+            if (s_anyrow) {
+                // (C) one warp resolves the chunk as a fixpoint over the rows (lane: rows lane, lane + 32)
+                if (wid == 0) {
+                    const unsigned long long row_a = ((unsigned long long)s_row32[lane * 2 + 1] << 32) | s_row32[lane * 2];
+                    const unsigned long long row_b = ((unsigned long long)s_row32[(lane + 32) * 2 + 1] << 32) | s_row32[(lane + 32) * 2];
+                    unsigned long long und = und0, km = 0ull;
                     while (und) {
                         // kept: no undecided and no kept suppressor left; removed: a kept suppressor exists
                         const bool ua = (und >> lane) & 1ull, ub = (und >> (lane + 32)) & 1ull;
-                        const unsigned long long live = und | keepm;
+                        const unsigned long long live = und | km;
                         const unsigned long long newk =
                             ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & live) == 0ull) << 32) |
                             __ballot_sync(0xffffffffu, ua && (row_a & live) == 0ull);
-                        keepm |= newk;
+                        km |= newk;
                         und &= ~newk;
                         const unsigned long long rem =
-                            ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & keepm) != 0ull) << 32) |
-                            __ballot_sync(0xffffffffu, ua && (row_a & keepm) != 0ull);
+                            ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & km) != 0ull) << 32) |
+                            __ballot_sync(0xffffffffu, ua && (row_a & km) != 0ull);
                         und &= ~rem;
                     }
-                } else {
-                    keepm = und;
+                    if (lane == 0) s_keepm = km;
                 }
+                __syncthreads();
+                keepm = s_keepm;
+            } else {
+                keepm = und0;   // nobody in the chunk suppresses anybody: every undecided candidate is kept
+            }
+            {
                 // [:TOP_K]: only the first `room` keeps survive (later ones cannot affect earlier ones)
                 const int room = K - nkept;
-                if (__popcll(keepm) > room) {
-                    unsigned long long t = keepm, kept = 0ull;
-                    for (int i = 0; i < room; ++i) { unsigned long long low = t & (~t + 1ull); kept |= low; t ^= low; }
-                    keepm = kept;
+                if (__popcll(keepm) > room) {   // room < 64 here: cut after the room-th set bit
+                    const unsigned lo = (unsigned)keepm, hi = (unsigned)(keepm >> 32);
+                    const int nlo = __popc(lo);
+                    if (room == 0) keepm = 0ull;
+                    else if (room <= nlo) keepm &= (2ull << __fns(lo, 0, room)) - 1ull;
+                    else keepm &= (2ull << (32 + __fns(hi, 0, room - nlo))) - 1ull;
                 }
-                if (lane == 0) s_keepm = keepm;
             }
-            __syncthreads();
             BT_PHASE_MARK(1, 9);   // chunk: C
-            const unsigned long long keepm = s_keepm;
             if (tid < NMS_CHUNK && ((keepm >> tid) & 1ull)) {
                 const int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
                 const float2 ctr = s_sctr[c0 + tid];
@@ -451,7 +470,13 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
                 s_kscore[slot] = s_sscore[c0 + tid];
                 s_kanchor[slot] = s_sanchor[c0 + tid];
                 s_korig[slot] = s_sorig[c0 + tid];
-                if (P.centre_cull) s_knext[slot] = atomicExch(&s_cellhead[cell_y(ctr.y) * P.gx + cell_x(ctr.x)], slot);
+                if (P.centre_cull) {
+                    // append to the cell's list (keep order: earlier, stronger boxes first)
+                    const int cell = cell_y(ctr.y) * P.gx + cell_x(ctr.x);
+                    s_knext[slot] = -1;
+                    const int prev = atomicExch(&s_celltail[cell], slot);
+                    if (prev < 0) s_cellhead[cell] = slot; else s_knext[prev] = slot;
+                }
             }
             nkept += __popcll(keepm);
             BT_PHASE_MARK(1, 10);  // chunk: insert
