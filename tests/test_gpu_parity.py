@@ -68,3 +68,24 @@ def test_metrics_accumulate_and_reset():
     np.testing.assert_array_equal(out["inst_area"].cpu().numpy(), ref["inst_area"])
     pp.reset_metrics()
     assert int(out["cm"].sum()) == 0
+
+
+def test_large_batch_and_determinism():
+    """16 images (persistent mask CTAs cross image boundaries, the NMS kernel runs on 16 SMs at once) against
+    the oracle, then the same step 10 more times: every output must be bit-identical each time (a race between
+    warps or CTAs would show up as run-to-run differences)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    import torch
+    batch = helpers.make(batch=16, img_size=640, seed=20269)
+    with ThreadPoolExecutor(os.cpu_count() or 4) as pool:
+        ref = oracle.run_pipeline(batch, pool=pool)
+    got, pp = helpers.run_cuda(batch)
+    helpers.assert_same(got, ref, 16, 300)
+    d = helpers.to_dev(batch, "cuda:0")
+    keys = [k for k in got if k not in ("cm", "seg_cnt4", "uni_cnt4")]          # accumulated across calls
+    for _ in range(10):
+        out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+        torch.cuda.synchronize()
+        for k in keys:
+            assert out[k].cpu().numpy().tobytes() == got[k].tobytes(), k
