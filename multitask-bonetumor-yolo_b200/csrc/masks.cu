@@ -52,7 +52,7 @@ struct K3Params {
     uint8_t *seg_mask, *uni_mask;
     float *seg_logits;
     // shared-memory offsets (bytes)
-    int off_lm, off_scr, off_gtrow, off_gtc, off_m1c, off_unc, off_list, off_cf, wpr;
+    int off_lm, off_scr, off_gtrow, off_gtc, off_unc, off_list, off_cf, wpr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -188,6 +188,38 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Piece tables of a round (= up to ECAP listed detections of a strip).
+struct Tab {
+    short4 ereg[ECAP];
+    int pxoff[ECAP + 1], celloff[ECAP + 1];
+    short rlo[ECAP], rhi[ECAP], clo[ECAP], chi[ECAP];
+    short pra[ECAP], pa[ECAP], npc[ECAP], cia[ECAP], ncc[ECAP];
+    float inpc[ECAP], incc[ECAP];
+    int area[ECAP], inter[ECAP];
+    int nb, be[ECAP + 1];   // batches of a round: entries [be[i], be[i+1])
+    int nlist;
+};
+// inside the kernel `T` is the table set in use (a reference, or a lambda parameter of that name)
+#define s_ereg T.ereg
+#define s_pxoff T.pxoff
+#define s_celloff T.celloff
+#define s_rlo T.rlo
+#define s_rhi T.rhi
+#define s_clo T.clo
+#define s_chi T.chi
+#define s_pra T.pra
+#define s_pa T.pa
+#define s_npc T.npc
+#define s_cia T.cia
+#define s_ncc T.ncc
+#define s_inpc T.inpc
+#define s_incc T.incc
+#define s_area T.area
+#define s_inter T.inter
+#define s_nb T.nb
+#define s_be T.be
+#define s_nlist T.nlist
+
 // TPW > 0: compile-time prototype width (shared-memory strides become immediates); 0: run-time.
 template <int TPW, int K3_THREADS, int MINB>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
@@ -198,19 +230,12 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     // TMA destinations must be 128-byte aligned: align the dynamic region by hand (128 spare bytes are allocated)
     unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     __shared__ __align__(8) uint64_t s_bar[NS_MAX];
-    __shared__ int s_nlist;
     __shared__ float s_w[NM];
     __shared__ int s_red[K3_WARPS][5];
     __shared__ int s_last;
     __shared__ int s_rowoff[16];   // float offset of the strip's prototype rows inside the ring
-    // per-round piece tables (a round = up to ECAP listed detections)
-    __shared__ short4 s_ereg[ECAP];
-    __shared__ int s_pxoff[ECAP + 1], s_celloff[ECAP + 1];
-    __shared__ short s_rlo[ECAP], s_rhi[ECAP], s_clo[ECAP], s_chi[ECAP];
-    __shared__ short s_pra[ECAP], s_pa[ECAP], s_npc[ECAP], s_cia[ECAP], s_ncc[ECAP];
-    __shared__ float s_inpc[ECAP], s_incc[ECAP];
-    __shared__ int s_area[ECAP], s_inter[ECAP];
-    __shared__ int s_nb, s_be[ECAP + 1];   // batches of a round: entries [s_be[i], s_be[i+1])
+    // per-round piece tables, double buffered: warp 0 builds the next strip's set during this strip's contraction
+    __shared__ Tab s_tab[2];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int PW = TPW > 0 ? TPW : P.PW, R = P.R, NS = P.NS;
@@ -225,9 +250,9 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);                // [scr_cap + (R+1)*PW]
     uint32_t *s_gtrow = reinterpret_cast<uint32_t *>(smem + P.off_gtrow);      // [4R+2][wpr+1] row bits (bit x)
     uint32_t *s_gtc = reinterpret_cast<uint32_t *>(smem + P.off_gtc);          // [R+1][PW+1] cell bits
-    uint32_t *s_m1c = reinterpret_cast<uint32_t *>(smem + P.off_m1c);          // [R+1][PW+1]
     uint32_t *s_unc = reinterpret_cast<uint32_t *>(smem + P.off_unc);          // [R+1][PW+1]
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(smem + P.off_list);  // [K]
+    unsigned short *s_list2 = reinterpret_cast<unsigned short *>(smem + P.off_list);  // [2][KP] detections listed on a strip
+    const int KP = (K + 7) & ~7;
     float *s_cf = reinterpret_cast<float *>(smem + P.off_cf);                  // [ECAP][CF_PITCH]
     const int wpr = P.wpr, tp = wpr + 1;
 
@@ -339,11 +364,15 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     };
 
     for (int g = g0; g < g1; ++g) {
+        Tab &T = s_tab[g & 1], &TN = s_tab[(g + 1) & 1];
+        unsigned short *s_list = s_list2 + (g & 1) * KP, *s_list_n = s_list2 + ((g + 1) & 1) * KP;
         const StripGeo G = strip_geo(s, R, PH, S_h);
         const int nb = (s + 1 == P.nstrips) ? b + 1 : b, ns = (s + 1 == P.nstrips) ? 0 : s + 1;   // next strip
         const int ci_lo = G.ci_lo, ci_hi = G.ci_hi, ncr_all = G.ncr_all, p_lo = G.p_lo, nrows = G.nrows;
         const int y_lo = G.y_lo, nyrows = G.nyrows;
         const int next_base = seq_base + ((g + 1 < g1 && nb == b) ? nrows - 1 : nrows);   // rows shift (same image keeps the last row)
+        const bool prebuild_next = (g + 1 < g1) && nb == b;
+        const StripGeo GN = strip_geo(ns, R, PH, S_h);
 
         // ---- (1) new image: flush the previous one, warp 0 fetches this image's crop regions
         if (b != cur_b) {
@@ -393,7 +422,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
         BT_PHASE_MARK(2, 0);   // GT words, tiles
 
         // piece tables of the entries [r0, r0 + nch) of the strip's list (warp 0)
-        auto build_tables = [&](int r0, int nch, bool from_list, int ci_lo, int ci_hi) {
+        auto build_tables = [&](Tab &T, const unsigned short *s_list, int r0, int nch, bool from_list, int ci_lo, int ci_hi) {
             int npx[2] = {0, 0}, ncell[2] = {0, 0};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -413,9 +442,10 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                     const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
                     s_rlo[e] = r_lo; s_rhi[e] = r_hi; s_clo[e] = c_lo; s_chi[e] = c_hi;
                     s_pra[e] = pr_a; s_pa[e] = 4 * ga; s_npc[e] = 4 * ngrp; s_cia[e] = ci_a; s_ncc[e] = ncc;
-                    s_inpc[e] = 1.0f / (float)ngrp; s_incc[e] = 1.0f / (float)ncc;
+                    const int nst = (ncc + 3) >> 2;   // cell items are runs of 4 cells of a cell row
+                    s_inpc[e] = 1.0f / (float)ngrp; s_incc[e] = 1.0f / (float)nst;
                     s_area[e] = 0; s_inter[e] = 0;
-                    npx[h] = npr * ngrp; ncell[h] = ncr * ncc;
+                    npx[h] = npr * ngrp; ncell[h] = ncr * nst;
                 }
             }
             // inclusive scans over the (up to) 64 entries: lanes, then the second half on top of the first
@@ -457,7 +487,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
 
         // detection list of a strip of this image (ordered ballot compaction of the cached regions) and the
         // first round's piece tables (warp 0)
-        auto list_and_tables = [&](int lo, int hi) {
+        auto list_and_tables = [&](Tab &T, unsigned short *s_list, int lo, int hi) {
             int n = 0;
 #pragma unroll
             for (int i = 0; i < RPL; ++i) {
@@ -485,15 +515,11 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             }
             if (lane == 0) s_nlist = n;
             __syncwarp();
-            build_tables(0, min(n, ECAP), false, lo, hi);
+            build_tables(T, s_list, 0, min(n, ECAP), false, lo, hi);
         };
-        // ---- (2) GT cells from the row bits; warp 0 builds the strip's list + tables first unless the
-        // previous strip already did (during its counters phase)
-        if (wid == 0 && !prebuilt) list_and_tables(ci_lo, ci_hi);
-        {
-            // bit x of output row y  ->  bit ry*4+rx of cell (ci, cj)
-            const int q0 = prebuilt ? tid : tid - 32, qs = prebuilt ? K3_THREADS : K3_THREADS - 32;
-            for (int q = q0; q < ncr_all * ncc_all && q >= 0; q += qs) {
+        // GT cells from the row bits: bit x of output row y -> bit ry*4+rx of cell (ci, cj)
+        auto gt_cells = [&]() {
+            for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
                 const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
                 const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
                 const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
@@ -505,17 +531,23 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                 }
                 s_gtc[q] = bits;
             }
+        };
+        // ---- (2) only at the first strip of an image in this CTA: warp 0 builds the strip's list + tables
+        // (every other strip's were built by warp 0 during the previous strip's contraction phase)
+        if (!prebuilt) {
+            if (wid == 0) list_and_tables(T, s_list, ci_lo, ci_hi);
+            __syncthreads();
         }
-        __syncthreads();
-        BT_PHASE_MARK(2, 1);   // list + tables | GT cells
+        BT_PHASE_MARK(2, 1);   // list + tables (first strip of an image)
         const int nent = s_nlist;
-        const int nM1 = ncr_all * ncc_all;
+        const int nst_all = (ncc_all + 3) >> 2;     // runs of 4 cells per cell row of the projector mask
+        const int nM1 = ncr_all * nst_all;
 
         for (int r0 = 0; r0 == 0 || r0 < nent; r0 += ECAP) {
             const int nch = min(ECAP, nent - r0);
             if (r0 > 0) {
                 __syncthreads();   // the previous round's tables are still being read
-                if (wid == 0) build_tables(r0, nch, true, ci_lo, ci_hi);
+                if (wid == 0) build_tables(T, s_list, r0, nch, true, ci_lo, ci_hi);
                 __syncthreads();
             }
             // coefficients of the round: asynchronous 4-byte copies into the pitched table
@@ -524,6 +556,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                 cp_async4(s_cf + e * CF_PITCH + i, P.det_coeff + ((size_t)b * K + s_list[r0 + e]) * NM + i);
             }
             if (r0 == 0) {
+                gt_cells();
                 // ---- (3) the strip's prototype rows (normally long since landed), then the M1 projection:
                 // bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).  Four neighbouring
                 // pixels per thread: one 16-byte shared load per channel feeds four FMA chains.
@@ -551,24 +584,47 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                 const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
                 // ---- (4) one phase: M1 cells (first pass only) and the contraction items of the batch
                 const int nm1 = (r0 == 0 && bi == 0) ? nM1 : 0;
-                for (int q = tid; q < nm1 + npx; q += K3_THREADS) {
+                // warp 0 spends the strip's first contraction phase on the next strip's detection list + tables
+                const bool w0_builds = prebuild_next && r0 == 0 && bi == 0;
+                if (w0_builds && wid == 0) list_and_tables(TN, s_list_n, GN.ci_lo, GN.ci_hi);
+                for (int q = w0_builds ? tid - 32 : tid; q < nm1 + npx; q += w0_builds ? K3_THREADS - 32 : K3_THREADS) {
+                    if (q < 0) break;   // warp 0 (building the tables)
                     if (q < nm1) {
-                        const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
+                        // projector mask: run of 4 cells of a cell row (exclusive owner of its cell tile, + optional logits)
+                        const int cr = q / nst_all, cj0 = 4 * (q - cr * nst_all) - 1, ci = ci_lo + cr;
+                        const int nk = min(4, PW - cj0);
                         const int rr0 = max(ci, 0) - p_lo, rr1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
-                        const int c0 = max(cj, 0), c1 = (cj < 0) ? 1 : min(cj + 1, PW - 1);
-                        float lg[16];
-                        const float v00 = s_lm[rr0 * PW + c0], v01 = s_lm[rr0 * PW + c1], v10 = s_lm[rr1 * PW + c0],
-                                    v11 = s_lm[rr1 * PW + c1];
-                        unsigned bits = P.seg_logits ? cell_bits<true>(v00, v01, v10, v11, ci < 0, cj < 0, lg)
-                                                     : cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
-                        if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-                        s_m1c[q] = bits;
-                        if (P.seg_logits) {
-                            const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-                            const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                            for (int ry = 0; ry < nry; ++ry) {
-                                float *o = P.seg_logits + ((size_t)b * S_h + ybase + ry) * S_w + xbase;
-                                for (int rx = 0; rx < nrx; ++rx) o[rx] = lg[ry * 4 + rx];
+                        const int cb = max(cj0, 0), sh = (cj0 < 0) ? 1 : 0;
+                        float v0[5], v1[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const int c = min(cb + i, PW - 1);
+                            v0[i] = s_lm[rr0 * PW + c]; v1[i] = s_lm[rr1 * PW + c];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k >= nk) break;
+                            const int cj = cj0 + k;
+                            const float a0 = sh ? v0[k ? k - 1 : 0] : v0[k], a1 = sh ? v1[k ? k - 1 : 0] : v1[k];
+                            float b0 = sh ? v0[k ? k : 1] : v0[k + 1], b1 = sh ? v1[k ? k : 1] : v1[k + 1];
+                            if (cj >= PW - 1) { b0 = a0; b1 = a1; }
+                            float lg[16];
+                            unsigned bits = P.seg_logits ? cell_bits<true>(a0, b0, a1, b1, ci < 0, cj < 0, lg)
+                                                         : cell_bits<false>(a0, b0, a1, b1, ci < 0, cj < 0, lg);
+                            if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+                            // the projector mask needs no tile: its counters are taken here (GT cells are complete)
+                            c5[0] += __popc(bits & s_gtc[cr * ncc_all + cj + 1]);
+                            c5[1] += __popc(bits);
+                            if (P.seg_logits || P.seg_mask) {
+                                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
+                                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                                for (int ry = 0; ry < nry; ++ry) {
+                                    const size_t o = ((size_t)b * S_h + ybase + ry) * S_w + xbase;
+                                    for (int rx = 0; rx < nrx; ++rx) {
+                                        if (P.seg_logits) P.seg_logits[o + rx] = lg[ry * 4 + rx];
+                                        if (P.seg_mask) P.seg_mask[o + rx] = (bits >> (ry * 4 + rx)) & 1u;
+                                    }
+                                }
                             }
                         }
                         continue;
@@ -600,36 +656,54 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                     seq_base = next_base;
                     top_up();
                 }
-                // ---- (5) upsample + threshold of every (detection, cell) item of the batch
+                // ---- (5) upsample + threshold: items = (detection, cell row, run of 4 cells); the search, the
+                // table reads and the two rows of corner logits are shared by the four cells
                 const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
                 for (int q = tid; q < ncell; q += K3_THREADS) {
                     int lo = e0, hi = e1;
                     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
                     const int e = lo, loc = q - (s_celloff[e] - cl0);
-                    const int ncc = s_ncc[e], npc = s_npc[e];
+                    const int ncc = s_ncc[e], npc = s_npc[e], nst = (ncc + 3) >> 2;
                     const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
-                    const int ci = s_cia[e] + cr, cj = s_clo[e] - 1 + (loc - cr * ncc);
+                    const int ci = s_cia[e] + cr, cj0 = s_clo[e] - 1 + 4 * (loc - cr * nst);
+                    const int nk = min(4, s_clo[e] - 1 + ncc - cj0);
                     const int pr_a = s_pra[e], pa = s_pa[e];
                     const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
                     const int rr0 = max(ci, 0) - pr_a, rr1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
-                    const int c0 = max(cj, 0) - pa, c1 = ((cj < 0) ? 1 : min(cj + 1, PW - 1)) - pa;
-                    const float v00 = scr[rr0 * npc + c0], v01 = scr[rr0 * npc + c1], v10 = scr[rr1 * npc + c0],
-                                v11 = scr[rr1 * npc + c1];
-                    float lg[16];
-                    unsigned bits = cell_bits<false>(v00, v01, v10, v11, ci < 0, cj < 0, lg);
-                    if (bits == 0) continue;
-                    if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-                    if (bits == 0) continue;
-                    const int cell = (ci - ci_lo) * ncc_all + cj + 1;
-                    atomicOr(&s_unc[cell], bits);
-                    atomicAdd(&s_area[e], __popc(bits));
-                    const int it = __popc(bits & s_gtc[cell]);
-                    if (it) atomicAdd(&s_inter[e], it);
+                    const int cb = max(cj0, 0) - pa, sh = (cj0 < 0) ? 1 : 0;
+                    float v0[5], v1[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int c = min(cb + i, npc - 1);
+                        v0[i] = scr[rr0 * npc + c]; v1[i] = scr[rr1 * npc + c];
+                    }
+                    int area = 0, inter = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k >= nk) break;
+                        const int cj = cj0 + k;
+                        // corner columns of cell k: (k, k+1) from the strip's base; the border cell (cj = -1) reads the
+                        // same columns (0, 1) as cell 0; in the last column the right corner is the left one
+                        const float a0 = sh ? v0[k ? k - 1 : 0] : v0[k], a1 = sh ? v1[k ? k - 1 : 0] : v1[k];
+                        float b0 = sh ? v0[k ? k : 1] : v0[k + 1], b1 = sh ? v1[k ? k : 1] : v1[k + 1];
+                        if (cj >= PW - 1) { b0 = a0; b1 = a1; }
+                        float lg[16];
+                        unsigned bits = cell_bits<false>(a0, b0, a1, b1, ci < 0, cj < 0, lg);
+                        if (bits == 0) continue;
+                        if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
+                        if (bits == 0) continue;
+                        const int cell = (ci - ci_lo) * ncc_all + cj + 1;
+                        atomicOr(&s_unc[cell], bits);
+                        area += __popc(bits);
+                        inter += __popc(bits & s_gtc[cell]);
+                    }
+                    if (area) atomicAdd(&s_area[e], area);
+                    if (inter) atomicAdd(&s_inter[e], inter);
                 }
                 __syncthreads();
                 BT_PHASE_MARK(2, 10);  // cells
             }
-            if (wid == 0) {   // warp 0 alone reads the round's tables here: it rebuilds them below
+            if (wid == 0) {   // warp 0 alone reads the round's tables here
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int e = lane + 32 * h;
@@ -642,37 +716,23 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             }
         }
 
-        // ---- (6) integer counters of the strip (kept in registers) + optional dense mask output; warp 0
-        // builds the next strip's detection list + tables meanwhile when it belongs to the same image
-        const bool prebuild_next = (g + 1 < g1) && nb == b;
-        if (prebuild_next && wid == 0) {
-            const StripGeo GN = strip_geo(ns, R, PH, S_h);
-            list_and_tables(GN.ci_lo, GN.ci_hi);
-        } else {
-            const int q0 = prebuild_next ? tid - 32 : tid, qs = prebuild_next ? K3_THREADS - 32 : K3_THREADS;
-            for (int q = q0; q < ncr_all * ncc_all; q += qs) {
-                const uint32_t gb = s_gtc[q], m1 = s_m1c[q], un = s_unc[q];
-                c5[0] += __popc(m1 & gb); c5[1] += __popc(m1); c5[2] += __popc(gb);
-                c5[3] += __popc(un & gb); c5[4] += __popc(un);
-            }
-            if (P.seg_mask || P.uni_mask) {
-                // cell tiles -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
-                for (int q = q0; q < nyrows * ncc_all; q += qs) {
-                    const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
-                    const int y = y_lo + yr;
-                    const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
-                    const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                    const int cell = (ci - ci_lo) * ncc_all + cj + 1;
-#pragma unroll
-                    for (int which = 0; which < 2; ++which) {
-                        uint8_t *dst = which ? P.uni_mask : P.seg_mask;
-                        if (!dst) continue;
-                        const unsigned nib = ((which ? s_unc : s_m1c)[cell] >> (4 * ry)) & 0xfu;
-                        uint8_t *o = dst + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
-                        *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
-                        if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
-                    }
-                }
+        // ---- (6) integer counters of the strip (kept in registers) + optional dense mask output
+        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
+            const uint32_t gb = s_gtc[q], un = s_unc[q];
+            c5[2] += __popc(gb);
+            c5[3] += __popc(un & gb); c5[4] += __popc(un);
+        }
+        if (P.uni_mask) {
+            // union tile -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
+            for (int q = tid; q < nyrows * ncc_all; q += K3_THREADS) {
+                const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
+                const int y = y_lo + yr;
+                const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+                const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                const unsigned nib = (s_unc[(ci - ci_lo) * ncc_all + cj + 1] >> (4 * ry)) & 0xfu;
+                uint8_t *o = P.uni_mask + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
+                *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
+                if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
             }
         }
         __syncthreads();   // tiles and tables are released
@@ -696,9 +756,8 @@ static size_t k3_layout(K3Params &P) {
     P.off_scr = (int)off; off += (size_t)(P.scr_cap + rowsmax * P.PW) * sizeof(float);
     P.off_gtrow = (int)off; off += align_up((size_t)(4 * P.R + 2) * (P.wpr + 1) * sizeof(uint32_t), 16);
     P.off_gtc = (int)off; off += celltile;
-    P.off_m1c = (int)off; off += celltile;
     P.off_unc = (int)off; off += celltile;
-    P.off_list = (int)off; off += align_up((size_t)P.K * sizeof(unsigned short), 16);
+    P.off_list = (int)off; off += 2 * align_up((size_t)P.K * sizeof(unsigned short), 16);
     P.off_cf = (int)off; off += align_up((size_t)ECAP * CF_PITCH * sizeof(float), 16);
     return off;
 }
@@ -764,7 +823,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     static const bool force_fat = getenv("BTPOST_K3_FAT") != nullptr;   // developer switch (scripts/): compare the two configurations
     for (int R = 3; R >= 2 && !nt && !force_fat; --R) {
         K3Params tmp = P; tmp.R = R; tmp.NS = R + 1; tmp.scr_cap = 1792;
-        if ((R + 1) * P.PW <= tmp.scr_cap && k3_layout(tmp) + 128 <= 111 * 1024) { P.R = R; P.NS = R + 1; P.scr_cap = 1792; nt = 256; }
+        if ((R + 1) * P.PW <= tmp.scr_cap && k3_layout(tmp) + 128 + 6144 <= 113 * 1024) { P.R = R; P.NS = R + 1; P.scr_cap = 1792; nt = 256; }
     }
     for (int R = 4; R >= 1 && !nt; --R)
         for (int NS = 2 * R + 1; NS >= R + 1 && !nt; --NS) {
