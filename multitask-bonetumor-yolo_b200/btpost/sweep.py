@@ -70,7 +70,8 @@ class SweepState:
         inrange = gvalid & (gl >= 0) & (gl < self.nc)
         keep = inrange[:, None, :] & ~(out["gt_ignore"] > 0)                                         # [B,A,G]
         goh = torch.nn.functional.one_hot(gl.clamp(0, self.nc - 1), self.nc)                        # [B,G,nc]
-        self.npig += torch.einsum("bag,bgc->ac", keep.long(), goh.long())
+        # integer contraction written as a masked sum (CUDA has no int64 matmul)
+        self.npig += (keep[:, :, :, None] & (goh[:, None, :, :] > 0)).sum(dim=(0, 2))
         self.n_images += B
         self.fsum += torch.stack([out["seg_dice"].double().sum(), out["seg_iou"].double().sum(),
                                   out["uni_dice"].double().sum(), out["uni_iou"].double().sum()])

@@ -298,21 +298,26 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     if (tid == 0) top_up();
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
 
-    // ---- GT words of a strip: one 32-pixel word (two 16-byte loads) per thread, prefetched
-    uint4 gtv0 = make_uint4(0, 0, 0, 0), gtv1 = make_uint4(0, 0, 0, 0);
-    auto gt_load = [&](int g, int b, int s) {
-        gtv0 = gtv1 = make_uint4(0, 0, 0, 0);
-        if (P.gt_f32 || g >= g1) return;
+    // ---- L2 prefetch of what the next strip will read: its GT words (32 pixels per thread) and its new
+    // prototype rows (their TMA is only issued half-way through this strip: a register prefetch of the GT
+    // words was spilled to local memory by ptxas and stalled on the load, r02c)
+    auto prefetch_next = [&](int g, int b, int s) {
+        if (g >= g1) return;
         const StripGeo G = strip_geo(s, R, PH, S_h);
-        if (tid < G.nyrows * wpr) {
+        if (!P.gt_f32 && tid < G.nyrows * wpr && (tid & 3) == 0) {   // one 128-byte line per 4 threads
             const int yr = tid / wpr, w = tid - yr * wpr;
-            const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
-                                                              ((size_t)b * S_h + (G.y_lo + yr)) * S_w + (size_t)w * 32);
-            gtv0 = __ldg(gp); gtv1 = __ldg(gp + 1);
+            const uint8_t *gp = static_cast<const uint8_t *>(P.masks_gt) + ((size_t)b * S_h + (G.y_lo + yr)) * S_w + (size_t)w * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
+        }
+        // rows p_lo+1 .. p_hi of the next strip (p_lo is shared with this one), NM channels, PW*4 bytes each
+        const int lines_per_row = (PW * 4 + 127) >> 7, nnew = G.p_hi - G.p_lo;
+        for (int q = tid; q < nnew * NM * lines_per_row; q += K3_THREADS) {
+            const int ln = q % lines_per_row, ch = (q / lines_per_row) % NM, rr = q / (lines_per_row * NM);
+            const float *pp = P.protos + (((size_t)b * NM + ch) * PH + G.p_lo + 1 + rr) * PW + ln * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
         }
     };
     int b = g0 / P.nstrips, s = g0 - b * P.nstrips;
-    gt_load(g0, b, s);
 
     int c5[5] = {0, 0, 0, 0, 0};   // seg inter, seg P, G, uni inter, uni P of the current image (this thread's share)
     int cur_b = -1, strips_of_b = 0;
@@ -387,16 +392,12 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             }
         }
         ++strips_of_b;
-        // GT words (prefetched) -> row bits, union tile cleared
+        // GT words (L2-resident: prefetched during the previous strip) -> row bits, union tile cleared
         if (tid < rowsmax) s_rowoff[tid] = ((seq_base + tid) % NS) * SLOT;
         for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) s_unc[i] = 0;
         for (int q = tid; q < nyrows; q += K3_THREADS) s_gtrow[q * tp + wpr] = 0;   // pad word
         if (!P.gt_f32) {
-            if (tid < nyrows * wpr) {
-                const int yr = tid / wpr, w = tid - yr * wpr;
-                s_gtrow[yr * tp + w] = pack_u8(gtv0, 0) | pack_u8(gtv1, 1);
-            }
-            for (int q = tid + K3_THREADS; q < nyrows * wpr; q += K3_THREADS) {   // very wide images
+            for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
                 const int yr = q / wpr, w = q - yr * wpr;
                 const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
                                                                   ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
@@ -417,7 +418,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                 s_gtrow[yr * tp + w] = bits;
             }
         }
-        gt_load(g + 1, nb, ns);   // next strip's GT words: in flight during this strip's arithmetic
+        prefetch_next(g + 1, nb, ns);   // next strip's GT words and prototype rows -> L2
         __syncthreads();
         BT_PHASE_MARK(2, 0);   // GT words, tiles
 
