@@ -396,8 +396,11 @@ decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
     k1_body<VEC>(P, dec, b);
 }
 
-template <int VEC>
-__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(K1_MAX_THREADS, 1)
+// MAXT = 320: four anchors per thread in blocks small enough for 4 CTAs per SM, so the whole batch is one wave
+// and the DFL arithmetic (64 exp per anchor) has ~36 warps per SM to hide behind (r02: one anchor per thread in
+// 1056-thread blocks ran at 1 CTA per SM in 3.5 waves, 180 us).
+template <int VEC, int MAXT>
+__global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(MAXT, MAXT <= 320 ? 4 : 1)
 decode_filter_l1_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
     L1Decoder<VEC> dec;
@@ -457,9 +460,10 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
             off += W * H;
         }
         P.lvl_off[3] = off;
-        if (block_for(1) <= K1_MAX_THREADS) decode_filter_l1_kernel<1><<<grid, dim3(block_for(1)), 0, s>>>(P);
-        else if (block_for(2) <= K1_MAX_THREADS) decode_filter_l1_kernel<2><<<grid, dim3(block_for(2)), 0, s>>>(P);
-        else if (block_for(4) <= K1_MAX_THREADS) decode_filter_l1_kernel<4><<<grid, dim3(block_for(4)), 0, s>>>(P);
+        if (block_for(4) <= 320) decode_filter_l1_kernel<4, 320><<<grid, dim3(block_for(4)), 0, s>>>(P);
+        else if (block_for(1) <= K1_MAX_THREADS) decode_filter_l1_kernel<1, K1_MAX_THREADS><<<grid, dim3(block_for(1)), 0, s>>>(P);
+        else if (block_for(2) <= K1_MAX_THREADS) decode_filter_l1_kernel<2, K1_MAX_THREADS><<<grid, dim3(block_for(2)), 0, s>>>(P);
+        else if (block_for(4) <= K1_MAX_THREADS) decode_filter_l1_kernel<4, K1_MAX_THREADS><<<grid, dim3(block_for(4)), 0, s>>>(P);
         else return BT_ERR_UNSUPPORTED;
     }
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
