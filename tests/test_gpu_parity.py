@@ -89,3 +89,19 @@ def test_large_batch_and_determinism():
         torch.cuda.synchronize()
         for k in keys:
             assert out[k].cpu().numpy().tobytes() == got[k].tobytes(), k
+
+
+@pytest.mark.parametrize("mode", ["no_gt_rows", "gt_in_one_image_only", "empty_gt_mask"])
+def test_ragged_and_empty_ground_truth(mode):
+    """Edge cases of the GT side (the reference's collate_fn yields [0, 6] when a batch has no boxes)."""
+    batch = helpers.make(batch=2, img_size=640, seed=33)
+    if mode == "no_gt_rows":
+        batch["det_boxes_gt"] = np.zeros((0, 6), np.float32)
+    elif mode == "gt_in_one_image_only":
+        batch["det_boxes_gt"] = batch["det_boxes_gt"][batch["det_boxes_gt"][:, 0] == 1]
+    else:
+        batch["masks_gt"] = np.zeros_like(batch["masks_gt"])
+    kw = dict(max_det=40)
+    ref = oracle.run_pipeline(batch, **kw)
+    got, _ = helpers.run_cuda(batch, **kw)
+    helpers.assert_same(got, ref, 2, 40)
