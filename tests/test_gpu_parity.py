@@ -105,3 +105,30 @@ def test_ragged_and_empty_ground_truth(mode):
     ref = oracle.run_pipeline(batch, **kw)
     got, _ = helpers.run_cuda(batch, **kw)
     helpers.assert_same(got, ref, 2, 40)
+
+
+def test_full_size_batch_is_consistent_with_small_batches():
+    """BASELINE config size (batch 64 x 640^2; the oracle would need minutes): 8 distinct images checked against the
+    oracle, then tiled 8x into a batch of 64 -- every per-image output must not depend on the batch size or on the
+    image's position in it (at 64 images the persistent mask CTAs own ~12 strips each and cross image boundaries,
+    the NMS kernel runs 64 CTAs at once), and the accumulated counters must be exactly 8x."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    small = helpers.make(batch=8, img_size=640, seed=20270)
+    with ThreadPoolExecutor(os.cpu_count() or 4) as pool:
+        ref = oracle.run_pipeline(small, pool=pool)
+    got8, _ = helpers.run_cuda(small)
+    helpers.assert_same(got8, ref, 8, 300)
+    big = dict(small)
+    rep = lambda a: np.ascontiguousarray(np.concatenate([a] * 8, 0))
+    for k in ("head", "protos", "masks_gt"):
+        big[k] = rep(small[k])
+    big["det_boxes_gt"] = np.concatenate([small["det_boxes_gt"] + np.array([8 * i, 0, 0, 0, 0, 0], np.float32) for i in range(8)], 0)
+    from btpost import synth
+    big["cfg"] = synth.SynthConfig(batch=64, img_size=640, seed=20270)
+    got64, _ = helpers.run_cuda(big)
+    for k, v in got8.items():
+        if k in ("cm", "seg_cnt4", "uni_cnt4"):
+            np.testing.assert_array_equal(got64[k], 8 * v, err_msg=k)
+        else:
+            assert got64[k].tobytes() == rep(v).tobytes(), k
