@@ -36,7 +36,7 @@ namespace bt {
 
 constexpr int NM = 32;
 constexpr int ECAP = 48;         // listed detections per round
-constexpr int CF_PITCH = NM + 1; // coefficient row pitch in shared memory (bank-conflict free)
+constexpr int CF_PITCH = NM + 4; // coefficient row pitch in shared memory: 16-byte aligned rows (read as float4), rows 4 banks apart
 constexpr int NS_MAX = 12;       // ring slots
 
 struct K3Params {
@@ -173,12 +173,18 @@ template <int PW4>
 __device__ __forceinline__ float4 contract4(const float4 *pp, const float *cf, int pw4_rt) {
     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const int st = PW4 > 0 ? PW4 : pw4_rt;
+    const float4 *cf4 = reinterpret_cast<const float4 *>(cf);
 #pragma unroll
-    for (int i = 0; i < NM; ++i) {
-        const float4 v = pp[i * st];
-        const float w = cf[i];
-        acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-        acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+    for (int i4 = 0; i4 < NM / 4; ++i4) {
+        const float4 w4 = cf4[i4];
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 v = pp[(i4 * 4 + u) * st];
+            const float w = wv[u];
+            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+        }
     }
     return acc;
 }
