@@ -190,11 +190,12 @@ struct L1DecoderBase {
 
 template <int VEC>
 struct L1Decoder : L1DecoderBase {
+    int astep;    // distance between the VEC anchors of a thread (interleaved mapping: consecutive lanes = consecutive anchors)
     __device__ __forceinline__ void scores(int n, float (&best)[VEC], int (&lab)[VEC]) const {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float b1[1] = {0.0f}; int l1[1] = {0};
-            if (n + i < N) scores1(n + i, b1, l1);
+            if (n + i * astep < N) scores1(n + i * astep, b1, l1);
             best[i] = b1[0]; lab[i] = l1[0];
         }
     }
@@ -202,14 +203,17 @@ struct L1Decoder : L1DecoderBase {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float a[1] = {0.0f}, b[1] = {0.0f}, c[1] = {0.0f}, d[1] = {0.0f};
-            if (n + i < N) boxes1(n + i, a, b, c, d);
+            if (n + i * astep < N) boxes1(n + i * astep, a, b, c, d);
             x1[i] = a[0]; y1[i] = b[0]; x2[i] = c[0]; y2[i] = d[0];
         }
     }
 };
 
-template <int VEC, class Dec>
-__device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b) {
+// INTERLEAVED: thread t of the CTA owns anchors a0 + t, a0 + cnt + t, ... (cnt = anchors per pass) instead of VEC
+// consecutive ones: for the channel-planar raw maps (L1) every load of a warp is then one contiguous line, and the
+// ordered compaction runs one block scan per pass.
+template <int VEC, bool INTERLEAVED, class Dec>
+__device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31;
@@ -240,9 +244,11 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
     int lab[VEC];
     const int g = g0 + tid;
     const bool active = g < g1;
+    const int cnt = g1 - g0;                                     // threads in use = anchors per pass
+    auto anchor_of = [&](int i) { return INTERLEAVED ? g0 * VEC + i * cnt + tid : g * VEC + i; };
     if (active) {
-        dec.scores(g * VEC, best, lab);
-        dec.boxes(g * VEC, x1, y1, x2, y2);
+        dec.scores(anchor_of(0), best, lab);
+        dec.boxes(anchor_of(0), x1, y1, x2, y2);
     }
 
     // ---- GT prep: ordered gather of this image's rows, then the reference's cat/view layout.
@@ -296,7 +302,7 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
     if (active) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            if (g * VEC + i >= P.N) continue;
+            if (anchor_of(i) >= P.N) continue;
             if (best[i] > P.conf) { flags |= 1u << i; ++c; }
             if (G > 0) {
                 // batch_bbox_iou (running_main_v2.py:68-94) against the unclamped GT copy.  With a
@@ -336,8 +342,19 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
     for (int d = 16; d > 0; d >>= 1) npos_thread += __shfl_down_sync(0xffffffffu, npos_thread, d);
     if (lane == 0 && npos_thread) atomicAdd(&s_npos, npos_thread);
     // ---- ordered offsets: block scan, then the eight CTA totals through distributed shared memory
-    int my_total;
-    const int excl = block_excl_scan(c, my_total, s_warp);
+    int my_total, excl = 0, exclv[VEC];
+    if (INTERLEAVED) {
+        int run = 0;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {   // anchor order = pass-major
+            int tot;
+            exclv[i] = run + block_excl_scan((flags >> i) & 1u, tot, s_warp);
+            run += tot;
+        }
+        my_total = run;
+    } else {
+        excl = block_excl_scan(c, my_total, s_warp);
+    }
     if (tid == 0) s_ex = my_total;
     cluster.sync();
     int base = 0, all = 0;
@@ -367,6 +384,7 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             if (!(flags & (1u << i))) continue;
+            if (INTERLEAVED) pos = base + exclv[i];
             if (pos < P.cap) {
                 float bx1 = x1[i], by1 = y1[i], bx2 = x2[i], by2 = y2[i];
                 if (P.clamp) {
@@ -377,7 +395,7 @@ __device__ __forceinline__ void k1_body(const K1Params &P, const Dec &dec, int b
                 P.cand_box[o] = make_float4(bx1, by1, bx2, by2);
                 P.cand_score[o] = best[i];
                 P.cand_label[o] = lab[i];
-                P.cand_anchor[o] = g * VEC + i;
+                P.cand_anchor[o] = anchor_of(i);
             }
             ++pos;
         }
@@ -393,7 +411,7 @@ __global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(MAXT, MAXT 
 decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
     L2Decoder<VEC> dec{P.head + (size_t)b * P.C * P.N, P.N, P.nc};
-    k1_body<VEC>(P, dec, b);
+    k1_body<VEC, false>(P, dec, b);
 }
 
 // MAXT = 320: four anchors per thread in blocks small enough for 4 CTAs per SM, so the whole batch is one wave
@@ -416,7 +434,13 @@ decode_filter_l1_kernel(const __grid_constant__ K1Params P) {
     dec.R = P.reg_max;
     dec.nc = P.nc;
     dec.N = P.N;
-    k1_body<VEC>(P, dec, b);
+    {
+        // anchors per pass of this CTA (same expression as in k1_body)
+        const int groups = (P.N + VEC - 1) / VEC, gp = (groups + K1_CLUSTER - 1) / K1_CLUSTER;
+        const int r = (int)cg::this_cluster().block_rank();
+        dec.astep = min(groups, r * gp + gp) - r * gp;
+    }
+    k1_body<VEC, true>(P, dec, b);
 }
 
 int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
