@@ -124,6 +124,9 @@ typedef struct BtIO {
     int32_t *dt_match;          /* [B, A, T, K] matched GT index + 1, 0 = unmatched            */
     uint8_t *dt_ignore;         /* [B, A, T, K]                                                */
     uint8_t *gt_ignore;         /* [B, A, G]                                                   */
+    /* ---- optional: v3 segmentation-mAP prep (a11, src/running_main_v3.py:478-498) ---- */
+    double *seg_prob_sum;       /* [B] sum of sigmoid(logit) over the projector mask's foreground pixels:
+                                   score = seg_prob_sum / (|P| + 1e-6); |P|, mask IoU from seg_img3     */
 } BtIO;
 
 /* Library / build identification. */

@@ -45,6 +45,7 @@ _IO_FIELDS = [
     "cm_pos", "seg_img3", "seg_dice", "seg_iou", "uni_img3", "uni_dice", "uni_iou", "inst_area", "inst_inter",
     "seg_mask", "seg_logits", "uni_mask", "inst_masks",
     "dt_match", "dt_ignore", "gt_ignore",
+    "seg_prob_sum",
 ]
 
 

@@ -63,6 +63,7 @@ class PostConfig:
     with_seg_logits: bool = False
     with_uni_mask: bool = False
     with_coco: bool = True
+    with_seg_map: bool = False           # v3 segmentation-mAP prep (score numerator per image)
     num_anchors: int | None = None
 
 
@@ -124,6 +125,8 @@ class PostProcessor:
             o["dt_match"] = z(B, A, T, K, dtype=torch.int32)
             o["dt_ignore"] = z(B, A, T, K, dtype=torch.uint8)
             o["gt_ignore"] = z(B, A, G, dtype=torch.uint8)
+        if cfg.with_seg_map:
+            o["seg_prob_sum"] = z(B, dtype=torch.float64)
         self.out = o
         self._empty_gt = torch.zeros(1, 6, dtype=torch.float32, device=dev)
 

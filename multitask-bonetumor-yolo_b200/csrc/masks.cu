@@ -51,6 +51,7 @@ struct K3Params {
     float *seg_dice, *seg_iou, *uni_dice, *uni_iou;
     uint8_t *seg_mask, *uni_mask;
     float *seg_logits;
+    double *seg_prob_sum;   // [B] optional: sum of sigmoid(logit) over the projector mask's foreground pixels
     // shared-memory offsets (bytes)
     int off_lm, off_scr, off_gtrow, off_gtc, off_unc, off_list, off_cf, wpr;
 };
@@ -325,6 +326,7 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
     };
     int b = g0 / P.nstrips, s = g0 - b * P.nstrips;
 
+    double psum = 0.0;             // this thread's share of seg_prob_sum of the current image
     int c5[5] = {0, 0, 0, 0, 0};   // seg inter, seg P, G, uni inter, uni P of the current image (this thread's share)
     int cur_b = -1, strips_of_b = 0;
     bool prebuilt = false;         // the current strip's list + tables were built during the previous strip
@@ -339,6 +341,13 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
             for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
             if (lane == 0) s_red[wid][i] = v;
             c5[i] = 0;
+        }
+        if (P.seg_prob_sum) {
+            double v = psum;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+            if (lane == 0 && v != 0.0) atomicAdd(&P.seg_prob_sum[b], v);
+            psum = 0.0;
         }
         __syncthreads();
         if (tid < 5) {
@@ -616,12 +625,19 @@ masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtenso
                             float b0 = sh ? v0[k ? k : 1] : v0[k + 1], b1 = sh ? v1[k ? k : 1] : v1[k + 1];
                             if (cj >= PW - 1) { b0 = a0; b1 = a1; }
                             float lg[16];
-                            unsigned bits = P.seg_logits ? cell_bits<true>(a0, b0, a1, b1, ci < 0, cj < 0, lg)
-                                                         : cell_bits<false>(a0, b0, a1, b1, ci < 0, cj < 0, lg);
+                            unsigned bits = (P.seg_logits || P.seg_prob_sum) ? cell_bits<true>(a0, b0, a1, b1, ci < 0, cj < 0, lg)
+                                                                             : cell_bits<false>(a0, b0, a1, b1, ci < 0, cj < 0, lg);
                             if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
                             // the projector mask needs no tile: its counters are taken here (GT cells are complete)
                             c5[0] += __popc(bits & s_gtc[cr * ncc_all + cj + 1]);
                             c5[1] += __popc(bits);
+                            if (P.seg_prob_sum && bits) {
+                                float ps = 0.0f;   // v3 seg-mAP score numerator: sigmoid over the foreground pixels of the cell
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    if ((bits >> k) & 1u) ps += 1.0f / (1.0f + __expf(-lg[k]));
+                                psum += (double)ps;
+                            }
                             if (P.seg_logits || P.seg_mask) {
                                 const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
                                 const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
@@ -821,6 +837,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
     P.seg_mask = io.seg_mask; P.uni_mask = io.uni_mask; P.seg_logits = io.seg_logits;
+    P.seg_prob_sum = io.seg_prob_sum;
     if (p.proto_w % 4 != 0 || p.proto_w > 256) return BT_ERR_UNSUPPORTED;   // TMA box width <= 256
     // Two persistent 256-thread CTAs per SM (their phases overlap: the contraction is bound by shared-
     // memory bandwidth, the upsample/threshold by the ALUs) when a ring of R + 1 rows with R >= 2 fits

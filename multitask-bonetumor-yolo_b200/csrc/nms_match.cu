@@ -124,6 +124,7 @@ struct K2Params {
     uint8_t *dt_ignore, *gt_ignore;
     // accumulators of the mask kernel, zeroed here
     int32_t *strip_done, *acc, *inst_area, *inst_inter;
+    double *seg_prob_sum;
     int region0_bytes;    // shared region 0: list of candidate indices in NMS order
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
     int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
     // zero the per-image accumulators the mask kernel adds into
     if (tid < 8) P.acc[b * 8 + tid] = 0;
     if (tid == 8) P.strip_done[b] = 0;
+    if (tid == 9 && P.seg_prob_sum) P.seg_prob_sum[b] = 0.0;
     for (int i = tid; i < K; i += K2_THREADS) {
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
         if (P.inst_inter) P.inst_inter[(size_t)b * K + i] = 0;
@@ -707,6 +709,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     for (int i = 0; i < p.num_iou_thrs; ++i) P.thrs[i] = p.iou_thrs[i];
     P.dt_match = io.dt_match; P.dt_ignore = io.dt_ignore; P.gt_ignore = io.gt_ignore;
     P.strip_done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.seg_prob_sum = io.seg_prob_sum;
     P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
     P.crop = p.crop; P.PW = p.proto_w; P.PH = p.proto_h;
     P.rx = (float)((double)p.proto_w / (double)p.img_w);

@@ -208,6 +208,7 @@ def run_pipeline(batch, pool=None, **kw):
         "cm": np.zeros((nc, nc), np.int64), "cm_pos": np.zeros(B, np.int32),
         "seg_cnt4": np.zeros(4, np.int64), "seg_img3": np.zeros((B, 3), np.int64),
         "seg_dice": np.zeros(B, np.float32), "seg_iou": np.zeros(B, np.float32),
+        "seg_prob_sum": np.zeros(B, np.float64), "seg_map_score": np.zeros(B, np.float32),
         "seg_mask": np.zeros((B, S, S), np.uint8) if p["with_masks_out"] else None,
         "seg_logits": np.zeros((B, S, S), np.float32) if p["with_masks_out"] else None,
         "inst_area": np.zeros((B, max_det), np.int32), "inst_inter": np.zeros((B, max_det), np.int32),
@@ -257,6 +258,7 @@ def run_pipeline(batch, pool=None, **kw):
         img3 = mask_counts(pm, gtm, out["seg_cnt4"])
         out["seg_img3"][b] = img3
         out["seg_dice"][b], out["seg_iou"][b] = dice_iou(*img3)
+        out["seg_prob_sum"][b], out["seg_map_score"][b] = seg_map_score(up, pm)
         if p["with_masks_out"]:
             out["seg_mask"][b] = pm; out["seg_logits"][b] = up
         # M2 instance masks
@@ -297,6 +299,39 @@ def run_pipeline(batch, pool=None, **kw):
 
 
 # ------------------------------------------------------------------ AP accumulation (a9)
+def seg_map_score(logits, pred_mask):
+    """v3 segmentation-mAP prep (running_main_v3.py:478-486): score = (probs * mask).sum() / (mask.sum() + 1e-6)
+    with probs = sigmoid(logits) in fp32.  Returns (sum of the foreground probabilities as float64, fp32 score)."""
+    x = logits.astype(np.float32)
+    probs = (np.float32(1.0) / (np.float32(1.0) + np.exp(-x, dtype=np.float32))).astype(np.float32)
+    m = pred_mask.astype(bool)
+    psum = float(probs[m].astype(np.float64).sum())
+    score = np.float32(np.float32(psum) / (np.float32(m.sum()) + np.float32(1e-6)))
+    return psum, score
+
+
+def seg_map_records(seg_img3, scores, thrs):
+    """What torchmetrics MeanAveragePrecision(iou_type='segm') -> COCOeval.evaluateImg does with v3's ONE predicted
+    mask and ONE target mask per image, class 0 (running_main_v3.py:478-498; SURVEY.md A.3 with mask IoU =
+    inter / union, areas = mask pixel counts).  Returns the arrays of the detection pipeline's layout with K = G = 1."""
+    seg_img3 = np.asarray(seg_img3, np.int64)
+    B, T = seg_img3.shape[0], len(thrs)
+    inter, P, G = (seg_img3[:, i].astype(np.float64) for i in range(3))
+    union = P + G - inter
+    iou = np.where(union > 0, inter / np.where(union > 0, union, 1.0), 0.0)
+    lo = np.array([0.0, 0.0, 32.0 ** 2, 96.0 ** 2]); hi = np.array([1e10, 32.0 ** 2, 96.0 ** 2, 1e10])
+    gt_ig = (G[:, None] < lo[None]) | (G[:, None] > hi[None])                       # [B, A]
+    dt_out = (P[:, None] < lo[None]) | (P[:, None] > hi[None])
+    thr = np.minimum(np.asarray(thrs, np.float64), 1 - 1e-10)
+    hit = iou[:, None] >= thr[None]                                                  # [B, T]
+    dt_match = np.broadcast_to(hit[:, None, :], (B, 4, T)).astype(np.int32)[..., None]
+    dt_ignore = np.where(hit[:, None, :], gt_ig[:, :, None], dt_out[:, :, None]).astype(np.uint8)[..., None]
+    dets = np.zeros((B, 1, 6), np.float32); dets[:, 0, 4] = scores
+    return dict(dets=dets, det_count=np.ones(B, np.int32), dt_match=np.ascontiguousarray(dt_match),
+                dt_ignore=np.ascontiguousarray(dt_ignore), gt_ignore=gt_ig.astype(np.uint8)[..., None],
+                gt_labels=np.zeros((B, 1), np.int32), gt_count=np.ones(B, np.int32))
+
+
 def accumulate_ap(records, n_gt_valid, thrs, max_dets=(1, 10, 100), nc=3):
     """COCOeval.accumulate + summarize from per-detection match records.
 
