@@ -58,6 +58,13 @@ struct Workspace {
     int32_t *strip_done;  // [B] strips finished per image (mask kernel)
     int32_t *acc;         // [B, 8] per-image int counters: seg inter,P,G ; uni inter,P,G
     short4 *det_region;   // [B, K] crop region of each kept detection at prototype resolution (r_lo, r_hi, c_lo, c_hi)
+    int32_t *scr_off;     // [B, K] offset (floats) of the detection's crop-box logits in `pool`; -1: none (invalid / pool full)
+    unsigned long long *pool_used;   // [1] floats handed out of `pool` in this call
+    int32_t *gpart;       // [B, NBY] GT pixels per row of cell blocks
+    unsigned long long *gtc, *unc;   // [B, NBY, NBX] GT / union-of-instance-masks bits per 2x2 block of cells
+    float *lm;            // [B, PH, PW] projector logits at prototype resolution
+    float *pool;          // [pool_cap] logits of the detections' crop boxes, back to back
+    long long pool_cap;
     size_t bytes;
 };
 
@@ -67,6 +74,18 @@ static inline int cand_capacity(const BtParams *p) {
     return (p->max_cand > 0 && p->max_cand < p->num_anchors) ? p->max_cand : p->num_anchors;
 }
 
+
+// 2x2 blocks of cells per dimension: cells -1 .. n-1 (a cell = the 4x4 output pixels between four prototype pixels)
+static inline int mask_blocks(int n) { return (n + 2) / 2; }
+
+// Logit pool of the mask stage: room for 16 full-image crop boxes per image (the synthetic workload uses ~2),
+// shared by the batch; detections that do not fit are contracted corner by corner in cells_kernel.
+static inline long long mask_pool_floats(const BtParams *p) {
+    long long v = (long long)p->batch * 16 * p->proto_h * p->proto_w;
+    const long long full = (long long)p->batch * p->max_det * p->proto_h * p->proto_w;
+    if (v > full) v = full;
+    return v > 0x7fffff00ll ? 0x7fffff00ll : v;
+}
 
 static inline int next_pow2(int v) {
     int r = 1;
@@ -95,6 +114,15 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.strip_done = reinterpret_cast<int32_t *>(take(B * sizeof(int32_t)));
     w.acc = reinterpret_cast<int32_t *>(take(B * 8 * sizeof(int32_t)));
     w.det_region = reinterpret_cast<short4 *>(take(B * (size_t)p->max_det * sizeof(short4)));
+    const size_t nby = (size_t)mask_blocks(p->proto_h), nbx = (size_t)mask_blocks(p->proto_w);
+    w.scr_off = reinterpret_cast<int32_t *>(take(B * (size_t)p->max_det * sizeof(int32_t)));
+    w.pool_used = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long)));
+    w.gpart = reinterpret_cast<int32_t *>(take(B * nby * sizeof(int32_t)));
+    w.gtc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
+    w.unc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
+    w.lm = reinterpret_cast<float *>(take(B * (size_t)p->proto_h * p->proto_w * sizeof(float)));
+    w.pool_cap = mask_pool_floats(p);
+    w.pool = reinterpret_cast<float *>(take((size_t)w.pool_cap * sizeof(float)));
     w.bytes = off;
     return w;
 }

@@ -1,4 +1,4 @@
-// Kernel 3: mask assembly + segmentation counters in ONE pass over the prototypes.
+// Stage 3: mask assembly + segmentation counters.
 //
 // Reference statements replaced (paths under /root/reference/src):
 //   M1 projector   running_main_v2.py:689-703 (Conv2d(32->1,k=1) -> F.interpolate bilinear x4,
@@ -8,25 +8,25 @@
 //   counters       running_main_v2.py:704-713 (tp/fp/fn/tn, DiceScore) and test_model.py:15-23
 //                  (per-image IoU / Dice with eps 1e-7)
 //
-// B200 mapping.  The prototypes are 2/3 of the path's compulsory HBM bytes and every other operand
-// is tiny, so the kernel is a PERSISTENT streamer: one 1024-thread CTA per SM owns a contiguous
-// range of strips (a strip = R "cell rows" of one image, a cell = the 4x4 output pixels between four
-// neighbouring prototype pixels) and keeps the prototype rows it needs in a shared-memory RING of
-// NS row slots (32 channels x PW floats each).  One warp feeds the ring with bulk async copies
-// (TMA, cp.async.bulk + one mbarrier per slot) as soon as a strip has released its rows, so the
-// loads always run a whole strip ahead of the arithmetic, every prototype row is read from HBM
-// once (the row shared by two consecutive strips stays in the ring; r01d: the one-strip-per-CTA
-// version sat 40 % of its time waiting for its own loads) and the GT-mask words of the next strip
-// travel in registers meanwhile.
-// Per strip the work is flattened over the CTA as two item lists found by prefix sums:
-// (entry, row, 4-pixel group) for the K=32 contraction (sequential fp32 FMA, the oracle's
-// summation order; TF32 tensor cores would break bit parity and the op is ~0.5 FLOP/B) and
-// (entry, cell) for bilinear upsample + threshold.  An entry is a detection whose crop box
-// touches the strip -- or the projector mask itself, which is just entry 0 with the projector
-// weights, the bias as initial value and the whole strip as its box, so M1 costs no extra phases.
-// Integer counters stay in registers across the strips of an image; output ownership per strip is
-// exclusive, so there are no global atomics on pixels; the last CTA to finish an image turns the
-// counters into Dice / IoU.
+// B200 mapping: three kernels, each bound by one resource.
+//   gt_pack_kernel    GT mask bytes -> bits, one 64-bit word per 2x2 block of cells (a cell = the 4x4
+//                     output pixels between four neighbouring prototype pixels).  Pure streaming.
+//   contract_kernel   THE pass over the prototypes (2/3 of the path's compulsory HBM bytes): a CTA takes a
+//                     32 x 8 pixel tile of all 32 channels with ONE 3-D tensor-map TMA (128-byte swizzle),
+//                     every thread moves its two pixels x 32 channels into registers once, and then the K=32
+//                     contraction of the projector and of every detection whose crop box touches the tile is
+//                     32 packed FFMA2 per (detection, pixel pair) with the coefficients broadcast from shared
+//                     memory: no prototype re-reads, no search, sequential fp32 order (bit parity with torch).
+//                     Logits go to an L2-resident scratch (projector: [B,PH,PW]; detections: their crop boxes
+//                     back to back in a pool).  HBM-bound.
+//   cells_kernel      bilinear x4 + threshold on 2x2 cell blocks: 9 corner logits -> 64 output pixels with
+//                     packed FMUL2/FFMA2 (two pixels per instruction), the threshold as the sign bit of a
+//                     packed subtraction gathered by one funnel shift per pixel.  One warp per detection,
+//                     the union of an image's instance masks is a 64-bit RED.OR per block; the projector mask
+//                     owns its cells.  The last CTA of an image folds the counters into Dice / IoU.
+//                     Instruction-issue bound (ALU pipe).
+// tcgen05 is deliberately not used: K = 32 at <= 0.5 FLOP/B, and TF32/BF16 accumulation would break the bit
+// parity of the thresholded masks with the fp32 reference.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -35,25 +35,28 @@
 namespace bt {
 
 constexpr int NM = 32;
-constexpr int ECAP = 48;         // listed detections per round
-constexpr int CF_PITCH = NM + 4; // coefficient row pitch in shared memory: 16-byte aligned rows (read as float4), rows 4 banks apart
-constexpr int NS_MAX = 12;       // ring slots
+constexpr int TA_W = 32, TA_H = 8;      // contract_kernel tile (prototype pixels)
+constexpr int A_THREADS = 128;          // 4 warps, each an 8 x 8 pixel block, 2 pixels per thread
+constexpr int A_LCAP = 32;              // detections staged per round
+constexpr int C_THREADS = 256;
+
+typedef unsigned long long u64;
 
 struct K3Params {
-    int B, S_h, S_w, PH, PW, R, NS, K, crop, gt_f32, nstrips, total_strips, scr_cap;
+    int B, S_h, S_w, PH, PW, K, gt_f32, NBY, NBX, ntx, nty, m1_items;
     float bias;
     const float *protos, *proj_weight, *det_coeff;
-    const int32_t *det_count;
+    const int32_t *det_count, *scr_off;
     const short4 *det_region;
     const void *masks_gt;
-    int32_t *strip_done, *acc, *inst_area, *inst_inter;
+    float *pool, *lm;
+    u64 *gtc, *unc;
+    int32_t *gpart, *work, *acc, *inst_area, *inst_inter;
     long long *seg_cnt4, *uni_cnt4, *seg_img3, *uni_img3;
     float *seg_dice, *seg_iou, *uni_dice, *uni_iou;
     uint8_t *seg_mask, *uni_mask;
     float *seg_logits;
     double *seg_prob_sum;   // [B] optional: sum of sigmoid(logit) over the projector mask's foreground pixels
-    // shared-memory offsets (bytes)
-    int off_lm, off_scr, off_gtrow, off_gtc, off_unc, off_list, off_cf, wpr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,18 +67,12 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// One prototype row of all 32 channels ([NM][PW] box of the [B*NM, PH, PW] tensor) -> one ring slot.
-__device__ __forceinline__ void tma_row_g2s(void *dst, const CUtensorMap *tm, int row, int chan0, uint64_t *bar) {
+// One [NM][TA_H][TA_W] box of the [B*NM, PH, PW] prototype tensor -> shared memory.
+__device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *tm, int col, int row, int chan0, uint64_t *bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
             smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(chan0), "r"(smem_u32(bar))
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(chan0), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -93,16 +90,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2, one issue slot for two results; every lane rounds
+// exactly like the scalar instruction)
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void unpack2u(u64 v, uint32_t &lo, uint32_t &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // torch's bilinear kernel order, pinned in the oracle: fma(h0, fma(w0,v00,w1*v01), h1*fma(w0,v10,w1*v11))
 __device__ __forceinline__ float lerp_row(float a, float b, float w0, float w1) {
     return __fmaf_rn(w0, a, __fmul_rn(w1, b));
 }
 
-// Evaluate one cell: 4 corner values -> 4x4 thresholded output pixels, bit (ry*4+rx).
-// Border cells (index -1) use interpolation weight 0 (source coordinate clamped to 0).
-template <bool LOG>
-__device__ __forceinline__ unsigned cell_bits(float v00, float v01, float v10, float v11, bool border_y, bool border_x,
-                                              float (&logits)[16]) {
+// Scalar cell evaluation with the logits kept (dense-output / score paths only): 4 corner values -> 4x4
+// thresholded output pixels, bit (ry*4+rx).  Border cells (index -1) use interpolation weight 0.
+__device__ __forceinline__ unsigned cell_bits_log(float v00, float v01, float v10, float v11, bool border_y, bool border_x,
+                                                  float (&logits)[16]) {
     float top[4], bot[4];
 #pragma unroll
     for (int rx = 0; rx < 4; ++rx) {
@@ -119,7 +135,7 @@ __device__ __forceinline__ unsigned cell_bits(float v00, float v01, float v10, f
 #pragma unroll
         for (int rx = 0; rx < 4; ++rx) {
             float v = __fmaf_rn(h0, top[rx], __fmul_rn(h1, bot[rx]));
-            if (LOG) logits[ry * 4 + rx] = v;
+            logits[ry * 4 + rx] = v;
             if (sigmoid_gt_half(v)) bits |= 1u << (ry * 4 + rx);
         }
     }
@@ -127,8 +143,9 @@ __device__ __forceinline__ unsigned cell_bits(float v00, float v01, float v10, f
 }
 
 // Valid-pixel mask of a cell: border cells (-1) own output rows/cols {0,1}; the last cell row/col
-// owns only the two pixels left before the image edge.
-__device__ __forceinline__ unsigned cell_valid(int ci, int cj, int S_h, int S_w) {
+// owns only the two pixels left before the image edge; cells past the last one do not exist.
+__device__ __forceinline__ unsigned cell_valid(int ci, int cj, int PH, int PW, int S_h, int S_w) {
+    if (ci > PH - 1 || cj > PW - 1) return 0u;
     const int nry = (ci < 0) ? 2 : min(4, S_h - (4 * ci + 2));
     const int nrx = (cj < 0) ? 2 : min(4, S_w - (4 * cj + 2));
     const unsigned rowm = (1u << nrx) - 1u;
@@ -137,6 +154,101 @@ __device__ __forceinline__ unsigned cell_valid(int ci, int cj, int S_h, int S_w)
     return m;
 }
 
+// ---- 2x2 cell blocks.  Block (by, bx) holds the cells ci in {2by-1, 2by}, cj in {2bx-1, 2bx}; its 64-bit
+// word is cell (a, c) at bits 16*(2a+c) .. +15, pixel (ry, rx) of a cell at bit 4*ry+rx.
+struct BlockGeo {
+    int r0, r1, r2, c0, c1, c2;   // prototype rows / columns of the 3x3 corner logits
+};
+__device__ __forceinline__ BlockGeo block_geo(int by, int bx, int PH, int PW) {
+    BlockGeo g;
+    // cell row A (ci = 2by-1) interpolates rows (r0, r1), cell row B (ci = 2by) rows (by ? r1 : r0, r2): the border
+    // cell -1 reads the same rows (0, 1) as cell 0 with weight 0 on the second; past the last row the lower corner is
+    // the upper one (source index clamped).  PH, PW >= 2.
+    g.r0 = max(2 * by - 1, 0);
+    g.r1 = max(min(2 * by, PH - 1), 1);
+    g.r2 = min(2 * by + 1, PH - 1);
+    g.c0 = max(2 * bx - 1, 0);
+    g.c1 = max(min(2 * bx, PW - 1), 1);
+    g.c2 = min(2 * bx + 1, PW - 1);
+    return g;
+}
+
+__device__ __forceinline__ u64 block_valid(int by, int bx, int PH, int PW, int S_h, int S_w) {
+    const int ciA = 2 * by - 1, cjA = 2 * bx - 1;
+    if (by > 0 && bx > 0 && ciA + 1 < PH - 1 && cjA + 1 < PW - 1) return ~0ull;
+    const u64 vAA = cell_valid(ciA, cjA, PH, PW, S_h, S_w), vAB = cell_valid(ciA, cjA + 1, PH, PW, S_h, S_w);
+    const u64 vBA = cell_valid(ciA + 1, cjA, PH, PW, S_h, S_w), vBB = cell_valid(ciA + 1, cjA + 1, PH, PW, S_h, S_w);
+    return vAA | (vAB << 16) | (vBA << 32) | (vBB << 48);
+}
+
+// Thresholded pixels of a 2x2 cell block from its 3x3 corner logits v[row][col] (unmasked).  BY0 / BX0: the block
+// holds the border cells of row / column -1 (compile-time: interior blocks carry no selects).
+template <bool BY0, bool BX0>
+__device__ __forceinline__ u64 block_bits_t(const float (&v)[3][3]) {
+    // horizontal interpolation of the three rows for the two cell columns, two pixels per instruction
+    const u64 W1a = pack2(0.125f, 0.375f), W1b = pack2(0.625f, 0.875f);
+    const u64 W0a = pack2(0.875f, 0.625f), W0b = pack2(0.375f, 0.125f);
+    const u64 ONE = pack2(1.0f, 1.0f), ZERO = pack2(0.0f, 0.0f);
+    const u64 wA0a = BX0 ? ONE : W0a, wA0b = BX0 ? ONE : W0b, wA1a = BX0 ? ZERO : W1a, wA1b = BX0 ? ZERO : W1b;
+    u64 hA[3][2], hB[3][2];   // [row][pixel pair] of cell column A / B
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float lA = v[i][0], rA = v[i][1];
+        const float lB = BX0 ? v[i][0] : v[i][1], rB = v[i][2];
+        const u64 lA2 = pack2(lA, lA), rA2 = pack2(rA, rA), lB2 = pack2(lB, lB), rB2 = pack2(rB, rB);
+        hA[i][0] = fma2(wA0a, lA2, mul2(wA1a, rA2));
+        hA[i][1] = fma2(wA0b, lA2, mul2(wA1b, rA2));
+        hB[i][0] = fma2(W0a, lB2, mul2(W1a, rB2));
+        hB[i][1] = fma2(W0b, lB2, mul2(W1b, rB2));
+    }
+    // sigmoid(x) > 0.5  <=>  x > T0  <=>  sign bit of (T0 - x); NaN gives the canonical positive NaN (false)
+    const u64 T0 = pack2(8.940696716308594e-08f, 8.940696716308594e-08f), NEG1 = pack2(-1.0f, -1.0f);
+    uint32_t word[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {          // cell row A / B
+        const int it = (a == 1 && !BY0) ? 1 : 0;   // top row of the cell
+        const int ib = a + 1;                      // bottom row
+        const bool border = (a == 0) && BY0;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int c = 1; c >= 0; --c) {     // cell column B first: it lands in the upper half of the word
+            u64 top[2], bot[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                top[q] = c ? hB[it][q] : hA[it][q];
+                bot[q] = c ? hB[ib][q] : hA[ib][q];
+            }
+#pragma unroll
+            for (int ry = 3; ry >= 0; --ry) {
+                const float h1f = border ? 0.0f : 0.125f + 0.25f * ry, h0f = 1.0f - h1f;
+                const u64 h1 = pack2(h1f, h1f), h0 = pack2(h0f, h0f);
+#pragma unroll
+                for (int q = 1; q >= 0; --q) {
+                    const u64 val = fma2(h0, top[q], mul2(h1, bot[q]));
+                    const u64 d = fma2(val, NEG1, T0);   // T0 - val, one rounding
+                    uint32_t dlo, dhi;
+                    unpack2u(d, dlo, dhi);
+                    acc = __funnelshift_l(dhi, acc, 1);
+                    acc = __funnelshift_l(dlo, acc, 1);
+                }
+            }
+        }
+        word[a] = acc;
+    }
+    return ((u64)word[1] << 32) | word[0];
+}
+__device__ __forceinline__ u64 block_bits(const float (&v)[3][3], bool by0, bool bx0) {
+    if (!by0 && !bx0) return block_bits_t<false, false>(v);
+    if (by0 && !bx0) return block_bits_t<true, false>(v);
+    if (!by0) return block_bits_t<false, true>(v);
+    return block_bits_t<true, true>(v);
+}
+
+// =================================================================================================
+// GT mask -> cell-block bits.  One CTA per (image, block row): the row's <= 8 output rows are packed to
+// row bits with coalesced 32-byte reads, then one thread per block assembles its word.  Also clears
+// the union words of the row, the per-image accumulators and the completion counter.
+// =================================================================================================
 __device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
     uint32_t wv[4] = {v.x, v.y, v.z, v.w}, bits = 0;
 #pragma unroll
@@ -150,642 +262,470 @@ __device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
     return bits;
 }
 
-// Strip geometry (s = strip index inside its image).
-struct StripGeo {
-    int ci_lo, ci_hi, ncr_all, p_lo, p_hi, nrows, y_lo, nyrows;
-};
-__device__ __forceinline__ StripGeo strip_geo(int s, int R, int PH, int S_h) {
-    StripGeo g;
-    g.ci_lo = (s == 0) ? -1 : s * R;
-    g.ci_hi = min(s * R + R - 1, PH - 1);
-    g.ncr_all = g.ci_hi - g.ci_lo + 1;
-    g.p_lo = s * R;
-    g.p_hi = min(g.ci_hi + 1, PH - 1);
-    g.nrows = g.p_hi - g.p_lo + 1;
-    g.y_lo = (s == 0) ? 0 : 4 * s * R + 2;
-    const int y_hi = (g.ci_hi == PH - 1) ? S_h : 4 * (g.ci_hi + 1) + 2;
-    g.nyrows = y_hi - g.y_lo;
-    return g;
-}
-
-// One (detection, row, 4-pixel group) item of the K=32 contraction: logits of 4 prototype pixels,
-// zero outside the crop box.
-template <int PW4>
-__device__ __forceinline__ float4 contract4(const float4 *pp, const float *cf, int pw4_rt) {
-    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    const int st = PW4 > 0 ? PW4 : pw4_rt;
-    const float4 *cf4 = reinterpret_cast<const float4 *>(cf);
-#pragma unroll
-    for (int i4 = 0; i4 < NM / 4; ++i4) {
-        const float4 w4 = cf4[i4];
-        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 v = pp[(i4 * 4 + u) * st];
-            const float w = wv[u];
-            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-        }
+__global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constant__ K3Params P) {
+    extern __shared__ uint32_t s_rows[];   // [8][wpr + 1]
+    __shared__ int s_cnt[C_THREADS / 32];
+    const int by = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int S_h = P.S_h, S_w = P.S_w, wpr = S_w >> 5, tp = wpr + 1;
+    const int y_lo = by ? 8 * by - 2 : 0, y_hi = min(8 * by + 6, S_h);   // output rows of the block row
+    const int nyr = y_hi - y_lo;
+    if (by == 0) {
+        if (tid < 8) P.acc[b * 8 + tid] = 0;
+        if (tid == 8 && b == 0) *P.work = 0;
     }
-    return acc;
-}
-
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Piece tables of a round (= up to ECAP listed detections of a strip).
-struct Tab {
-    short4 ereg[ECAP];
-    int pxoff[ECAP + 1], celloff[ECAP + 1];
-    short rlo[ECAP], rhi[ECAP], clo[ECAP], chi[ECAP];
-    short pra[ECAP], pa[ECAP], npc[ECAP], cia[ECAP], ncc[ECAP];
-    float inpc[ECAP], incc[ECAP];
-    int area[ECAP], inter[ECAP];
-    int nb, be[ECAP + 1];   // batches of a round: entries [be[i], be[i+1])
-    int nlist;
-};
-// inside the kernel `T` is the table set in use (a reference, or a lambda parameter of that name)
-#define s_ereg T.ereg
-#define s_pxoff T.pxoff
-#define s_celloff T.celloff
-#define s_rlo T.rlo
-#define s_rhi T.rhi
-#define s_clo T.clo
-#define s_chi T.chi
-#define s_pra T.pra
-#define s_pa T.pa
-#define s_npc T.npc
-#define s_cia T.cia
-#define s_ncc T.ncc
-#define s_inpc T.inpc
-#define s_incc T.incc
-#define s_area T.area
-#define s_inter T.inter
-#define s_nb T.nb
-#define s_be T.be
-#define s_nlist T.nlist
-
-// TPW > 0: compile-time prototype width (shared-memory strides become immediates); 0: run-time.
-template <int TPW, int K3_THREADS, int MINB>
-__global__ void __launch_bounds__(K3_THREADS, MINB)
-masks_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
-    constexpr int K3_WARPS = K3_THREADS / 32;
-    constexpr int RPL = 10;   // crop regions cached per lane of warp 0 (detections lane, lane + 32, ...)
-    extern __shared__ __align__(128) unsigned char smem_dyn[];
-    // TMA destinations must be 128-byte aligned: align the dynamic region by hand (128 spare bytes are allocated)
-    unsigned char *smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
-    __shared__ __align__(8) uint64_t s_bar[NS_MAX];
-    __shared__ float s_w[NM];
-    __shared__ int s_red[K3_WARPS][5];
-    __shared__ int s_last;
-    __shared__ int s_rowoff[16];   // float offset of the strip's prototype rows inside the ring
-    // per-round piece tables, double buffered: warp 0 builds the next strip's set during this strip's contraction
-    __shared__ Tab s_tab[2];
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int PW = TPW > 0 ? TPW : P.PW, R = P.R, NS = P.NS;
-    const int PH = P.PH, S_w = P.S_w, S_h = P.S_h, K = P.K;
-    const int rowsmax = R + 1;
-    const int ncc_all = PW + 1;    // cells per cell row (incl. the border column -1)
-    const int SLOT = NM * PW;      // floats per ring slot
-    const int SCR_GRP = P.scr_cap >> 2;
-
-    float *s_ring = reinterpret_cast<float *>(smem);                           // [NS][NM][PW]
-    float *s_lm = reinterpret_cast<float *>(smem + P.off_lm);                  // [R+1][PW] projector logits
-    float *s_scr = reinterpret_cast<float *>(smem + P.off_scr);                // [scr_cap + (R+1)*PW]
-    uint32_t *s_gtrow = reinterpret_cast<uint32_t *>(smem + P.off_gtrow);      // [4R+2][wpr+1] row bits (bit x)
-    uint32_t *s_gtc = reinterpret_cast<uint32_t *>(smem + P.off_gtc);          // [R+1][PW+1] cell bits
-    uint32_t *s_unc = reinterpret_cast<uint32_t *>(smem + P.off_unc);          // [R+1][PW+1]
-    unsigned short *s_list2 = reinterpret_cast<unsigned short *>(smem + P.off_list);  // [2][KP] detections listed on a strip
-    const int KP = (K + 7) & ~7;
-    float *s_cf = reinterpret_cast<float *>(smem + P.off_cf);                  // [ECAP][CF_PITCH]
-    const int wpr = P.wpr, tp = wpr + 1;
-
-    // ---- this CTA's contiguous range of strips
-    const int g0 = (int)(((long long)blockIdx.x * P.total_strips) / gridDim.x);
-    const int g1 = (int)(((long long)(blockIdx.x + 1) * P.total_strips) / gridDim.x);
-    if (g0 >= g1) return;
-
-    BT_PHASE_INIT();
-    if (tid == 0) {
-        for (int i = 0; i < NS; ++i) mbar_init(&s_bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // ---- producer state (thread 0).  Rows are loaded in the order the strips consume them; the row
-    // shared by two consecutive strips of an image is loaded once.  Row q of this sequence lives in
-    // slot q % NS.
-    int pg = g0, pb = g0 / P.nstrips, ps = g0 - (g0 / P.nstrips) * P.nstrips, prow = ps * R, pseq = 0;
-    int seq_base = 0;   // sequence number of the current strip's first row
-    auto top_up = [&]() {
-        // fill every free slot (rows before seq_base are released), one TMA per row
-        while (pseq < seq_base + NS && pg < g1) {
-            const int p_hi = min(min(ps * R + R - 1, PH - 1) + 1, PH - 1);
-            const int slot = pseq % NS;
-            mbar_expect_tx(&s_bar[slot], (uint32_t)(SLOT * sizeof(float)));
-            tma_row_g2s(s_ring + (size_t)slot * SLOT, &tmap, prow, pb * NM, &s_bar[slot]);
-            ++pseq;
-            if (prow < p_hi) {
-                ++prow;
-            } else {
-                // next strip that brings new rows (a last strip of one row only re-uses its predecessor's)
-                for (;;) {
-                    ++pg;
-                    if (++ps == P.nstrips) { ps = 0; ++pb; }
-                    if (pg >= g1) break;
-                    const int start = (ps == 0) ? 0 : ps * R + 1;   // same image: the strip's first row is already in the ring
-                    if (start <= min(min(ps * R + R - 1, PH - 1) + 1, PH - 1)) { prow = start; break; }
-                }
-            }
-        }
-    };
-    if (tid == 0) top_up();
-    if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
-
-    // ---- L2 prefetch of what the next strip will read: its GT words (32 pixels per thread) and its new
-    // prototype rows (their TMA is only issued half-way through this strip: a register prefetch of the GT
-    // words was spilled to local memory by ptxas and stalled on the load, r02c)
-    auto prefetch_next = [&](int g, int b, int s) {
-        if (g >= g1) return;
-        const StripGeo G = strip_geo(s, R, PH, S_h);
-        if (!P.gt_f32 && tid < G.nyrows * wpr && (tid & 3) == 0) {   // one 128-byte line per 4 threads
-            const int yr = tid / wpr, w = tid - yr * wpr;
-            const uint8_t *gp = static_cast<const uint8_t *>(P.masks_gt) + ((size_t)b * S_h + (G.y_lo + yr)) * S_w + (size_t)w * 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
-        }
-        // rows p_lo+1 .. p_hi of the next strip (p_lo is shared with this one), NM channels, PW*4 bytes each
-        const int lines_per_row = (PW * 4 + 127) >> 7, nnew = G.p_hi - G.p_lo;
-        for (int q = tid; q < nnew * NM * lines_per_row; q += K3_THREADS) {
-            const int ln = q % lines_per_row, ch = (q / lines_per_row) % NM, rr = q / (lines_per_row * NM);
-            const float *pp = P.protos + (((size_t)b * NM + ch) * PH + G.p_lo + 1 + rr) * PW + ln * 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-        }
-    };
-    int b = g0 / P.nstrips, s = g0 - b * P.nstrips;
-
-    double psum = 0.0;             // this thread's share of seg_prob_sum of the current image
-    int c5[5] = {0, 0, 0, 0, 0};   // seg inter, seg P, G, uni inter, uni P of the current image (this thread's share)
-    int cur_b = -1, strips_of_b = 0;
-    bool prebuilt = false;         // the current strip's list + tables were built during the previous strip
-    short4 myreg[RPL];             // warp 0: crop regions of detections lane + 32 i of the current image
-
-    // counters of image `b` -> global accumulators; the CTA that completes the image finalises it
-    auto flush_image = [&](int b, int nstrips_done) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            int v = c5[i];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-            if (lane == 0) s_red[wid][i] = v;
-            c5[i] = 0;
-        }
-        if (P.seg_prob_sum) {
-            double v = psum;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-            if (lane == 0 && v != 0.0) atomicAdd(&P.seg_prob_sum[b], v);
-            psum = 0.0;
-        }
-        __syncthreads();
-        if (tid < 5) {
-            int v = 0;
-#pragma unroll
-            for (int w = 0; w < K3_WARPS; ++w) v += s_red[w][tid];
-            if (v) atomicAdd(&P.acc[b * 8 + tid], v);
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(&P.strip_done[b], nstrips_done) + nstrips_done == P.nstrips);
-        __syncthreads();
-        if (s_last && tid < 2) {
-            // (test_model.py:15-23)
-            __threadfence();
-            long long inter = atomicAdd(&P.acc[b * 8 + 3 * tid], 0), pp = atomicAdd(&P.acc[b * 8 + 3 * tid + 1], 0);
-            long long gg = atomicAdd(&P.acc[b * 8 + 2], 0);   // |G| is shared by both masks
-            long long total = (long long)S_h * S_w;
-            long long *img3 = tid ? P.uni_img3 : P.seg_img3;
-            long long *cnt4 = tid ? P.uni_cnt4 : P.seg_cnt4;
-            float *dice = tid ? P.uni_dice : P.seg_dice, *iou = tid ? P.uni_iou : P.seg_iou;
-            if (img3) { img3[b * 3 + 0] = inter; img3[b * 3 + 1] = pp; img3[b * 3 + 2] = gg; }
-            if (cnt4) {
-                atomicAdd((unsigned long long *)&cnt4[0], (unsigned long long)inter);
-                atomicAdd((unsigned long long *)&cnt4[1], (unsigned long long)(pp - inter));
-                atomicAdd((unsigned long long *)&cnt4[2], (unsigned long long)(gg - inter));
-                atomicAdd((unsigned long long *)&cnt4[3], (unsigned long long)(total - pp - gg + inter));
-            }
-            const float fi = (float)inter, fu = (float)(pp + gg - inter);
-            if (iou) iou[b] = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
-            if (dice) dice[b] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gg), 1e-7f));
-        }
-        __syncthreads();
-    };
-
-    for (int g = g0; g < g1; ++g) {
-        Tab &T = s_tab[g & 1], &TN = s_tab[(g + 1) & 1];
-        unsigned short *s_list = s_list2 + (g & 1) * KP, *s_list_n = s_list2 + ((g + 1) & 1) * KP;
-        const StripGeo G = strip_geo(s, R, PH, S_h);
-        const int nb = (s + 1 == P.nstrips) ? b + 1 : b, ns = (s + 1 == P.nstrips) ? 0 : s + 1;   // next strip
-        const int ci_lo = G.ci_lo, ci_hi = G.ci_hi, ncr_all = G.ncr_all, p_lo = G.p_lo, nrows = G.nrows;
-        const int y_lo = G.y_lo, nyrows = G.nyrows;
-        const int next_base = seq_base + ((g + 1 < g1 && nb == b) ? nrows - 1 : nrows);   // rows shift (same image keeps the last row)
-        const bool prebuild_next = (g + 1 < g1) && nb == b;
-        const StripGeo GN = strip_geo(ns, R, PH, S_h);
-
-        // ---- (1) new image: flush the previous one, warp 0 fetches this image's crop regions
-        if (b != cur_b) {
-            if (cur_b >= 0) flush_image(cur_b, strips_of_b);
-            cur_b = b; strips_of_b = 0;
-            if (wid == 0) {
-#pragma unroll
-                for (int i = 0; i < RPL; ++i) {
-                    const int k = i * 32 + lane;
-                    myreg[i] = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
-                }
-            }
-        }
-        ++strips_of_b;
-        // GT words (L2-resident: prefetched during the previous strip) -> row bits, union tile cleared
-        if (tid < rowsmax) s_rowoff[tid] = ((seq_base + tid) % NS) * SLOT;
-        for (int i = tid; i < rowsmax * ncc_all; i += K3_THREADS) s_unc[i] = 0;
-        for (int q = tid; q < nyrows; q += K3_THREADS) s_gtrow[q * tp + wpr] = 0;   // pad word
-        if (!P.gt_f32) {
-            for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
-                const int yr = q / wpr, w = q - yr * wpr;
+    for (int q = tid; q < 8 * tp; q += C_THREADS) {
+        const int yr = q / tp, w = q - yr * tp;
+        uint32_t bits = 0;
+        if (yr < nyr && w < wpr) {
+            if (!P.gt_f32) {
                 const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
                                                                   ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
-                s_gtrow[yr * tp + w] = pack_u8(__ldg(gp), 0) | pack_u8(__ldg(gp + 1), 1);
-            }
-        } else {
-            for (int q = tid; q < nyrows * wpr; q += K3_THREADS) {
-                const int yr = q / wpr, w = q - yr * wpr;
+                bits = pack_u8(__ldg(gp), 0) | pack_u8(__ldg(gp + 1), 1);
+            } else {
                 const float4 *gp = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) +
                                                                     ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
-                uint32_t bits = 0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float4 v = __ldg(gp + i);
                     bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
                             ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
                 }
-                s_gtrow[yr * tp + w] = bits;
             }
         }
-        prefetch_next(g + 1, nb, ns);   // next strip's GT words and prototype rows -> L2
-        __syncthreads();
-        BT_PHASE_MARK(2, 0);   // GT words, tiles
-
-        // piece tables of the entries [r0, r0 + nch) of the strip's list (warp 0)
-        auto build_tables = [&](Tab &T, const unsigned short *s_list, int r0, int nch, bool from_list, int ci_lo, int ci_hi) {
-            int npx[2] = {0, 0}, ncell[2] = {0, 0};
+        s_rows[q] = bits;
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int bx = tid; bx < P.NBX; bx += C_THREADS) {
+        u64 word = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = lane + 32 * h;
-                if (e < nch) {
-                    short4 rg;
-                    if (from_list) { rg = __ldg(P.det_region + (size_t)b * K + s_list[r0 + e]); s_ereg[e] = rg; }
-                    else rg = s_ereg[e];
-                    const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w;
-                    const int ci_a = max(r_lo - 1, ci_lo), ci_b = min(r_hi, ci_hi);
-                    const int pr_a = max(ci_a, 0), pr_b = min(ci_b + 1, PH - 1);
-                    const int ja = c_lo - 1;
-                    const int pa = max(ja, 0), pb2 = min(c_hi + 1, PW - 1);
-                    // scratch rows are stored in aligned groups of 4 prototype columns
-                    const int ga = pa >> 2, ngrp = (pb2 >> 2) - ga + 1;
-                    const int npr = pr_b - pr_a + 1;
-                    const int ncr = ci_b - ci_a + 1, ncc = c_hi - ja + 1;
-                    s_rlo[e] = r_lo; s_rhi[e] = r_hi; s_clo[e] = c_lo; s_chi[e] = c_hi;
-                    s_pra[e] = pr_a; s_pa[e] = 4 * ga; s_npc[e] = 4 * ngrp; s_cia[e] = ci_a; s_ncc[e] = ncc;
-                    const int nst = (ncc + 3) >> 2;   // cell items are runs of 4 cells of a cell row
-                    s_inpc[e] = 1.0f / (float)ngrp; s_incc[e] = 1.0f / (float)nst;
-                    s_area[e] = 0; s_inter[e] = 0;
-                    npx[h] = npr * ngrp; ncell[h] = ncr * nst;
-                }
-            }
-            // inclusive scans over the (up to) 64 entries: lanes, then the second half on top of the first
-            int ipx[2] = {npx[0], npx[1]}, icl[2] = {ncell[0], ncell[1]};
+        for (int a = 0; a < 2; ++a) {
+            const int ci = 2 * by - 1 + a;
+            if (ci > P.PH - 1) continue;
+            const int ybase = (ci < 0) ? 0 : 4 * ci + 2, nry = (ci < 0) ? 2 : min(4, S_h - ybase);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int v = __shfl_up_sync(0xffffffffu, ipx[h], d), u = __shfl_up_sync(0xffffffffu, icl[h], d);
-                    if (lane >= d) { ipx[h] += v; icl[h] += u; }
-                }
-            }
-            const int tpx = __shfl_sync(0xffffffffu, ipx[0], 31), tcl = __shfl_sync(0xffffffffu, icl[0], 31);
-            ipx[1] += tpx; icl[1] += tcl;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = lane + 32 * h;
-                if (e < ECAP) { s_pxoff[e + 1] = ipx[h]; s_celloff[e + 1] = icl[h]; }
-            }
-            if (lane == 0) { s_pxoff[0] = 0; s_celloff[0] = 0; }
-            // batches: consecutive entries whose first scratch group falls into the same SCR_GRP window
-            unsigned first[2];
-            {
-                const int bid0 = (ipx[0] - npx[0]) / SCR_GRP, bid1 = (ipx[1] - npx[1]) / SCR_GRP;
-                const int pb0 = __shfl_up_sync(0xffffffffu, bid0, 1), last0 = __shfl_sync(0xffffffffu, bid0, 31);
-                int pb1 = __shfl_up_sync(0xffffffffu, bid1, 1);
-                if (lane == 0) pb1 = last0;
-                first[0] = __ballot_sync(0xffffffffu, lane < nch && (lane == 0 || bid0 != pb0));
-                first[1] = __ballot_sync(0xffffffffu, lane + 32 < nch && bid1 != pb1);
-            }
-            if (lane == 0) {
-                unsigned long long m = ((unsigned long long)first[1] << 32) | first[0];
-                int nbt = 0;
-                while (m) { s_be[nbt++] = __ffsll((long long)m) - 1; m &= m - 1ull; }
-                s_be[nbt] = nch;
-                s_nb = nbt;
-            }
-        };
-
-        // detection list of a strip of this image (ordered ballot compaction of the cached regions) and the
-        // first round's piece tables (warp 0)
-        auto list_and_tables = [&](Tab &T, unsigned short *s_list, int lo, int hi) {
-            int n = 0;
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) {
-                const short4 rg = myreg[i];
-                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, lo) <= min((int)rg.y, hi);
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                    const int pos = n + __popc(m & ((1u << lane) - 1u));
-                    s_list[pos] = (unsigned short)(i * 32 + lane);
-                    if (pos < ECAP) s_ereg[pos] = rg;
-                }
-                n += __popc(m);
-            }
-            for (int k0 = RPL * 32; k0 < K; k0 += 32) {   // more detections than the register cache holds
-                const int k = k0 + lane;
-                const short4 rg = (k < K) ? __ldg(P.det_region + (size_t)b * K + k) : make_short4(1, 0, 1, 0);
-                const bool ok = rg.x <= rg.y && rg.z <= rg.w && max((int)rg.x - 1, lo) <= min((int)rg.y, hi);
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                    const int pos = n + __popc(m & ((1u << lane) - 1u));
-                    s_list[pos] = (unsigned short)k;
-                    if (pos < ECAP) s_ereg[pos] = rg;
-                }
-                n += __popc(m);
-            }
-            if (lane == 0) s_nlist = n;
-            __syncwarp();
-            build_tables(T, s_list, 0, min(n, ECAP), false, lo, hi);
-        };
-        // GT cells from the row bits: bit x of output row y -> bit ry*4+rx of cell (ci, cj)
-        auto gt_cells = [&]() {
-            for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-                const int cr = q / ncc_all, cj = q - cr * ncc_all - 1, ci = ci_lo + cr;
-                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+            for (int c = 0; c < 2; ++c) {
+                const int cj = 2 * bx - 1 + c;
+                if (cj > P.PW - 1) continue;
+                const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
                 unsigned bits = 0;
                 for (int ry = 0; ry < nry; ++ry) {
-                    const uint32_t *row = s_gtrow + (ybase + ry - y_lo) * tp + (xbase >> 5);
-                    unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
+                    const uint32_t *row = s_rows + (ybase + ry - y_lo) * tp + (xbase >> 5);
+                    const unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
                     bits |= gb << (4 * ry);
                 }
-                s_gtc[q] = bits;
+                word |= (u64)bits << (16 * (2 * a + c));
             }
-        };
-        // ---- (2) only at the first strip of an image in this CTA: warp 0 builds the strip's list + tables
-        // (every other strip's were built by warp 0 during the previous strip's contraction phase)
-        if (!prebuilt) {
-            if (wid == 0) list_and_tables(T, s_list, ci_lo, ci_hi);
-            __syncthreads();
         }
-        BT_PHASE_MARK(2, 1);   // list + tables (first strip of an image)
-        const int nent = s_nlist;
-        const int nst_all = (ncc_all + 3) >> 2;     // runs of 4 cells per cell row of the projector mask
-        const int nM1 = ncr_all * nst_all;
+        const size_t o = ((size_t)b * P.NBY + by) * P.NBX + bx;
+        P.gtc[o] = word;
+        P.unc[o] = 0ull;
+        cnt += __popcll(word);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int v = 0;
+        for (int w = 0; w < C_THREADS / 32; ++w) v += s_cnt[w];
+        P.gpart[b * P.NBY + by] = v;
+    }
+}
 
-        for (int r0 = 0; r0 == 0 || r0 < nent; r0 += ECAP) {
-            const int nch = min(ECAP, nent - r0);
-            if (r0 > 0) {
-                __syncthreads();   // the previous round's tables are still being read
-                if (wid == 0) build_tables(T, s_list, r0, nch, true, ci_lo, ci_hi);
-                __syncthreads();
-            }
-            // coefficients of the round: asynchronous 4-byte copies into the pitched table
-            for (int q = tid; q < nch * NM; q += K3_THREADS) {
-                const int e = q >> 5, i = q & 31;
-                cp_async4(s_cf + e * CF_PITCH + i, P.det_coeff + ((size_t)b * K + s_list[r0 + e]) * NM + i);
-            }
-            if (r0 == 0) {
-                gt_cells();
-                // ---- (3) the strip's prototype rows (normally long since landed), then the M1 projection:
-                // bias + sum_k w_k p_k, sequential fmaf (== torch conv2d, pinned).  Four neighbouring
-                // pixels per thread: one 16-byte shared load per channel feeds four FMA chains.
-                for (int i = 0; i < nrows; ++i) mbar_wait(&s_bar[(seq_base + i) % NS], (uint32_t)(((seq_base + i) / NS) & 1));
-                for (int q = tid; q < (nrows * PW) >> 2; q += K3_THREADS) {
-                    const int rr = q / (PW >> 2), cg = q - rr * (PW >> 2);
-                    float4 acc = make_float4(P.bias, P.bias, P.bias, P.bias);
-                    const float4 *pp = reinterpret_cast<const float4 *>(s_ring + s_rowoff[rr]) + cg;
-#pragma unroll
-                    for (int k = 0; k < NM; ++k) {
-                        const float4 v = pp[k * (PW >> 2)];
-                        const float w = s_w[k];
-                        acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-                        acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-                    }
-                    reinterpret_cast<float4 *>(s_lm)[q] = acc;
+// =================================================================================================
+// contract_kernel: one pass over the prototypes
+// =================================================================================================
+__global__ void __launch_bounds__(A_THREADS, 3)
+contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // the swizzled TMA destinations must be 1024-byte aligned: align by hand (1024 spare bytes are allocated)
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    constexpr int TILE_FLOATS = NM * TA_H * TA_W;
+    float *s_tiles = reinterpret_cast<float *>(smem);                                  // [2][NM][TA_H][TA_W], 16-byte chunks XOR row
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(smem + 2 * TILE_FLOATS * 4);    // [K]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(16) float s_cf[A_LCAP][NM];
+    __shared__ short4 s_reg[A_LCAP];
+    __shared__ int s_off[A_LCAP];        // pool offset of the box origin minus (r_lo * bw + c_lo): + r * bw + c addresses a pixel
+    __shared__ __align__(16) float s_w[NM];
+    __shared__ int s_n;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tiles = P.ntx * P.nty, total = tiles * P.B;
+    const int PH = P.PH, PW = P.PW, K = P.K;
+
+    auto issue = [&](int tile, int stage) {   // thread 0
+        const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
+        mbar_expect_tx(&s_bar[stage], (uint32_t)(TILE_FLOATS * sizeof(float)));
+        tma_tile_g2s(s_tiles + stage * TILE_FLOATS, &tmap, tx * TA_W, ty * TA_H, b * NM, &s_bar[stage]);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+        s_n = 0;
+    }
+    if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
+    __syncthreads();
+
+    // this thread's two pixels: rows {0,2,4,6} in lanes 0-15 and {1,3,5,7} in lanes 16-31 keep the 8-byte shared
+    // loads of the swizzled tile free of bank conflicts
+    const int i16 = lane & 15;
+    const int row = 2 * (i16 >> 2) + (lane >> 4), colp = (wid << 3) + 2 * (i16 & 3);   // tile-local row / first column
+    const int soff = row * TA_W + (((colp >> 2) ^ row) << 2) + (colp & 3);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
+        const int R0 = ty * TA_H, C0 = tx * TA_W;
+        const int r = R0 + row, c = C0 + colp;
+
+        // ---- detections whose crop box touches the tile (any order: every (detection, pixel) logit is independent)
+        {
+            const int n = min(__ldg(P.det_count + b), K);
+            for (int k0 = 0; k0 < n; k0 += A_THREADS) {
+                const int k = k0 + tid;
+                bool ok = false;
+                if (k < n) {
+                    const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
+                    ok = rg.x <= rg.y && rg.z <= rg.w && rg.x <= R0 + TA_H - 1 && rg.y >= R0 && rg.z <= C0 + TA_W - 1 && rg.w >= C0 &&
+                         __ldg(P.scr_off + (size_t)b * K + k) >= 0;
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (ok) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
             }
-            cp_async_wait_all();
-            __syncthreads();
-            BT_PHASE_MARK(2, 2);   // coefficients + M1 projection
-            const int nbatch = (nch > 0) ? s_nb : 0;
-            for (int bi = 0; bi == 0 || bi < nbatch; ++bi) {
-                const int e0 = (nch > 0) ? s_be[bi] : 0, e1 = (nch > 0) ? s_be[bi + 1] : 0;
-                const int px0 = s_pxoff[e0], npx = s_pxoff[e1] - px0;
-                // ---- (4) one phase: M1 cells (first pass only) and the contraction items of the batch
-                const int nm1 = (r0 == 0 && bi == 0) ? nM1 : 0;
-                // warp 0 spends the strip's first contraction phase on the next strip's detection list + tables
-                const bool w0_builds = prebuild_next && r0 == 0 && bi == 0;
-                if (w0_builds && wid == 0) list_and_tables(TN, s_list_n, GN.ci_lo, GN.ci_hi);
-                for (int q = w0_builds ? tid - 32 : tid; q < nm1 + npx; q += w0_builds ? K3_THREADS - 32 : K3_THREADS) {
-                    if (q < 0) break;   // warp 0 (building the tables)
-                    if (q < nm1) {
-                        // projector mask: run of 4 cells of a cell row (exclusive owner of its cell tile, + optional logits)
-                        const int cr = q / nst_all, cj0 = 4 * (q - cr * nst_all) - 1, ci = ci_lo + cr;
-                        const int nk = min(4, PW - cj0);
-                        const int rr0 = max(ci, 0) - p_lo, rr1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - p_lo;
-                        const int cb = max(cj0, 0), sh = (cj0 < 0) ? 1 : 0;
-                        float v0[5], v1[5];
+        }
+        // ---- the tile: shared memory -> registers, then the stage is free for the tile after next
+        mbar_wait(&s_bar[stage], (uint32_t)((it >> 1) & 1));
+        u64 p[NM];
+        {
+            const float *src = s_tiles + stage * TILE_FLOATS + soff;
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const int c = min(cb + i, PW - 1);
-                            v0[i] = s_lm[rr0 * PW + c]; v1[i] = s_lm[rr1 * PW + c];
-                        }
+            for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
+        }
+        __syncthreads();
+        const int nlist = s_n;
+        if (tid == 0 && tile + 2 * (int)gridDim.x < total) issue(tile + 2 * gridDim.x, stage);
+
+        // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
+        {
+            u64 acc = pack2(P.bias, P.bias);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k >= nk) break;
-                            const int cj = cj0 + k;
-                            const float a0 = sh ? v0[k ? k - 1 : 0] : v0[k], a1 = sh ? v1[k ? k - 1 : 0] : v1[k];
-                            float b0 = sh ? v0[k ? k : 1] : v0[k + 1], b1 = sh ? v1[k ? k : 1] : v1[k + 1];
-                            if (cj >= PW - 1) { b0 = a0; b1 = a1; }
-                            float lg[16];
-                            unsigned bits = (P.seg_logits || P.seg_prob_sum) ? cell_bits<true>(a0, b0, a1, b1, ci < 0, cj < 0, lg)
-                                                                             : cell_bits<false>(a0, b0, a1, b1, ci < 0, cj < 0, lg);
-                            if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-                            // the projector mask needs no tile: its counters are taken here (GT cells are complete)
-                            c5[0] += __popc(bits & s_gtc[cr * ncc_all + cj + 1]);
-                            c5[1] += __popc(bits);
-                            if (P.seg_prob_sum && bits) {
-                                float ps = 0.0f;   // v3 seg-mAP score numerator: sigmoid over the foreground pixels of the cell
-#pragma unroll
-                                for (int k = 0; k < 16; ++k)
-                                    if ((bits >> k) & 1u) ps += 1.0f / (1.0f + __expf(-lg[k]));
-                                psum += (double)ps;
-                            }
-                            if (P.seg_logits || P.seg_mask) {
-                                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
-                                const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                                for (int ry = 0; ry < nry; ++ry) {
-                                    const size_t o = ((size_t)b * S_h + ybase + ry) * S_w + xbase;
-                                    for (int rx = 0; rx < nrx; ++rx) {
-                                        if (P.seg_logits) P.seg_logits[o + rx] = lg[ry * 4 + rx];
-                                        if (P.seg_mask) P.seg_mask[o + rx] = (bits >> (ry * 4 + rx)) & 1u;
-                                    }
-                                }
-                            }
-                        }
-                        continue;
-                    }
-                    const int qq = q - nm1;
-                    int lo = e0, hi = e1;   // last entry with pxoff <= px0 + qq
-                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pxoff[mid] - px0 <= qq) lo = mid; else hi = mid; }
-                    const int e = lo, loc = qq - (s_pxoff[e] - px0);
-                    const int ngrp = s_npc[e] >> 2;
-                    const int rr = __float2int_rz(((float)loc + 0.5f) * s_inpc[e]), gg = loc - rr * ngrp;
-                    const int r = s_pra[e] + rr, c = s_pa[e] + 4 * gg;
-                    const int c_lo = s_clo[e], c_hi = s_chi[e];
-                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (r >= s_rlo[e] && r <= s_rhi[e] && c + 3 >= c_lo && c <= c_hi) {
-                        acc = contract4<(TPW >> 2)>(reinterpret_cast<const float4 *>(s_ring + s_rowoff[r - p_lo] + c),
-                                                    s_cf + e * CF_PITCH, PW >> 2);
-                        if (c < c_lo || c > c_hi) acc.x = 0.0f;
-                        if (c + 1 < c_lo || c + 1 > c_hi) acc.y = 0.0f;
-                        if (c + 2 < c_lo || c + 2 > c_hi) acc.z = 0.0f;
-                        if (c + 3 < c_lo || c + 3 > c_hi) acc.w = 0.0f;
-                    }
-                    reinterpret_cast<float4 *>(s_scr)[qq] = acc;
-                }
-                __syncthreads();
-                BT_PHASE_MARK(2, 9);   // M1 cells + contraction
-                if (r0 + ECAP >= nent && bi + 1 >= nbatch && tid == 0) {
-                    // last contraction of the strip: its rows are released (the cells only read the scratch),
-                    // the ring is topped up while the strip finishes
-                    seq_base = next_base;
-                    top_up();
-                }
-                // ---- (5) upsample + threshold: items = (detection, cell row, run of 4 cells); the search, the
-                // table reads and the two rows of corner logits are shared by the four cells
-                const int cl0 = s_celloff[e0], ncell = s_celloff[e1] - cl0;
-                for (int q = tid; q < ncell; q += K3_THREADS) {
-                    int lo = e0, hi = e1;
-                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_celloff[mid] - cl0 <= q) lo = mid; else hi = mid; }
-                    const int e = lo, loc = q - (s_celloff[e] - cl0);
-                    const int ncc = s_ncc[e], npc = s_npc[e], nst = (ncc + 3) >> 2;
-                    const int cr = __float2int_rz(((float)loc + 0.5f) * s_incc[e]);
-                    const int ci = s_cia[e] + cr, cj0 = s_clo[e] - 1 + 4 * (loc - cr * nst);
-                    const int nk = min(4, s_clo[e] - 1 + ncc - cj0);
-                    const int pr_a = s_pra[e], pa = s_pa[e];
-                    const float *scr = s_scr + 4 * (s_pxoff[e] - px0);
-                    const int rr0 = max(ci, 0) - pr_a, rr1 = ((ci < 0) ? 1 : min(ci + 1, PH - 1)) - pr_a;
-                    const int cb = max(cj0, 0) - pa, sh = (cj0 < 0) ? 1 : 0;
-                    float v0[5], v1[5];
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const int c = min(cb + i, npc - 1);
-                        v0[i] = scr[rr0 * npc + c]; v1[i] = scr[rr1 * npc + c];
-                    }
-                    int area = 0, inter = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k >= nk) break;
-                        const int cj = cj0 + k;
-                        // corner columns of cell k: (k, k+1) from the strip's base; the border cell (cj = -1) reads the
-                        // same columns (0, 1) as cell 0; in the last column the right corner is the left one
-                        const float a0 = sh ? v0[k ? k - 1 : 0] : v0[k], a1 = sh ? v1[k ? k - 1 : 0] : v1[k];
-                        float b0 = sh ? v0[k ? k : 1] : v0[k + 1], b1 = sh ? v1[k ? k : 1] : v1[k + 1];
-                        if (cj >= PW - 1) { b0 = a0; b1 = a1; }
-                        float lg[16];
-                        unsigned bits = cell_bits<false>(a0, b0, a1, b1, ci < 0, cj < 0, lg);
-                        if (bits == 0) continue;
-                        if (ci < 0 || cj < 0 || ci == PH - 1 || cj == PW - 1) bits &= cell_valid(ci, cj, S_h, S_w);
-                        if (bits == 0) continue;
-                        const int cell = (ci - ci_lo) * ncc_all + cj + 1;
-                        atomicOr(&s_unc[cell], bits);
-                        area += __popc(bits);
-                        inter += __popc(bits & s_gtc[cell]);
-                    }
-                    if (area) atomicAdd(&s_area[e], area);
-                    if (inter) atomicAdd(&s_inter[e], inter);
-                }
-                __syncthreads();
-                BT_PHASE_MARK(2, 10);  // cells
+            for (int k4 = 0; k4 < NM / 4; ++k4) {
+                const float4 w4 = reinterpret_cast<const float4 *>(s_w)[k4];
+                acc = fma2(pack2(w4.x, w4.x), p[4 * k4 + 0], acc);
+                acc = fma2(pack2(w4.y, w4.y), p[4 * k4 + 1], acc);
+                acc = fma2(pack2(w4.z, w4.z), p[4 * k4 + 2], acc);
+                acc = fma2(pack2(w4.w, w4.w), p[4 * k4 + 3], acc);
             }
-            if (wid == 0) {   // warp 0 alone reads the round's tables here
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int e = lane + 32 * h;
-                    if (e < nch) {
-                        const int k = s_list[r0 + e];
-                        if (s_area[e] && P.inst_area) atomicAdd(&P.inst_area[(size_t)b * K + k], s_area[e]);
-                        if (s_inter[e] && P.inst_inter) atomicAdd(&P.inst_inter[(size_t)b * K + k], s_inter[e]);
-                    }
-                }
-            }
+            // PW is even: both pixels of the pair are inside the image together
+            if (r < PH && c < PW) *reinterpret_cast<u64 *>(P.lm + ((size_t)b * PH + r) * PW + c) = acc;
         }
 
-        // ---- (6) integer counters of the strip (kept in registers) + optional dense mask output
-        for (int q = tid; q < ncr_all * ncc_all; q += K3_THREADS) {
-            const uint32_t gb = s_gtc[q], un = s_unc[q];
-            c5[2] += __popc(gb);
-            c5[3] += __popc(un & gb); c5[4] += __popc(un);
+        // ---- M2: rounds of A_LCAP listed detections
+        const int wc0 = C0 + (wid << 3);   // the warp's 8 x 8 block: rows R0 .. R0+7, columns wc0 .. wc0+7
+        for (int r0 = 0; r0 < nlist; r0 += A_LCAP) {
+            const int nch = min(A_LCAP, nlist - r0);
+            if (r0 > 0) __syncthreads();
+            for (int q = tid; q < nch * (NM / 4); q += A_THREADS) {
+                const int e = q >> 3, i = q & 7;
+                reinterpret_cast<float4 *>(&s_cf[e][0])[i] =
+                    __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + s_list[r0 + e]) * NM) + i);
+            }
+            if (tid < nch) {
+                const int k = s_list[r0 + tid];
+                const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
+                s_reg[tid] = rg;
+                s_off[tid] = __ldg(P.scr_off + (size_t)b * K + k) - (rg.x * (rg.w - rg.z + 1) + rg.z);
+            }
+            __syncthreads();
+            // the round's detections that touch this warp's block: one lane tests one detection
+            short4 mine = make_short4(1, 0, 1, 0);
+            if (lane < nch) mine = s_reg[lane];
+            unsigned todo = __ballot_sync(0xffffffffu, mine.x <= R0 + TA_H - 1 && mine.y >= R0 && mine.z <= wc0 + 7 && mine.w >= wc0);
+            while (todo) {
+                const int e = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const short4 rg = s_reg[e];
+                u64 acc = pack2(0.0f, 0.0f);
+#pragma unroll
+                for (int k4 = 0; k4 < NM / 4; ++k4) {
+                    const float4 w4 = reinterpret_cast<const float4 *>(&s_cf[e][0])[k4];
+                    acc = fma2(pack2(w4.x, w4.x), p[4 * k4 + 0], acc);
+                    acc = fma2(pack2(w4.y, w4.y), p[4 * k4 + 1], acc);
+                    acc = fma2(pack2(w4.z, w4.z), p[4 * k4 + 2], acc);
+                    acc = fma2(pack2(w4.w, w4.w), p[4 * k4 + 3], acc);
+                }
+                if (r >= rg.x && r <= rg.y) {
+                    float a0, a1;
+                    unpack2(acc, a0, a1);
+                    float *dst = P.pool + (s_off[e] + r * (rg.w - rg.z + 1) + c);
+                    if (c >= rg.z && c <= rg.w) dst[0] = a0;
+                    if (c + 1 >= rg.z && c + 1 <= rg.w) dst[1] = a1;
+                }
+            }
         }
-        if (P.uni_mask) {
-            // union tile -> bytes.  Thread = (output row, cell): writes the cell's <=4 pixels of that row.
-            for (int q = tid; q < nyrows * ncc_all; q += K3_THREADS) {
-                const int yr = q / ncc_all, cj = q - yr * ncc_all - 1;
-                const int y = y_lo + yr;
-                const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+        // every warp has read s_n (after the barrier above; when the list was not empty, also past a round barrier)
+        if (tid == 0) s_n = 0;
+        __syncthreads();   // list and round tables are rebuilt for the next tile
+    }
+}
+
+// =================================================================================================
+// cells_kernel: bilinear x4 + threshold + counters.  Persistent warps pull work items off one global counter:
+// first the detections (one warp each, their sizes vary by 100x), then the projector mask in runs of 32 blocks.
+// =================================================================================================
+constexpr int C_WARPS = 4;   // warps per CTA of cells_kernel
+
+__device__ __forceinline__ void m1_item(const K3Params &P, int b, int q, int lane) {
+    const int PH = P.PH, PW = P.PW, S_h = P.S_h, S_w = P.S_w, NBX = P.NBX, NBY = P.NBY;
+    int inter = 0, area = 0;
+    double psum = 0.0;
+    if (q < NBY * NBX) {
+        const int by = q / NBX, bx = q - by * NBX;
+        const BlockGeo g = block_geo(by, bx, PH, PW);
+        const float *lm = P.lm + (size_t)b * PH * PW;
+        float v[3][3];
+        const int rr[3] = {g.r0 * PW, g.r1 * PW, g.r2 * PW}, cc[3] = {g.c0, g.c1, g.c2};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v[i][j] = __ldg(lm + rr[i] + cc[j]);
+        const u64 gtw = __ldg(P.gtc + ((size_t)b * NBY + by) * NBX + bx);
+        if (!(P.seg_logits || P.seg_mask || P.seg_prob_sum)) {
+            const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, S_h, S_w);
+            area = __popcll(bits); inter = __popcll(bits & gtw);
+        } else {
+            // dense outputs / v3 score: scalar path that keeps the logits
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int ci = 2 * by - 1 + a, cj = 2 * bx - 1 + c;
+                    if (ci > PH - 1 || cj > PW - 1) continue;
+                    const int it = (a == 0 || by == 0) ? 0 : 1, ib = (a == 0) ? 1 : 2;
+                    const int jl = (c == 0 || bx == 0) ? 0 : 1, jr = (c == 0) ? 1 : 2;
+                    float lg[16];
+                    unsigned bits = cell_bits_log(v[it][jl], v[it][jr], v[ib][jl], v[ib][jr], ci < 0, cj < 0, lg);
+                    bits &= cell_valid(ci, cj, PH, PW, S_h, S_w);
+                    area += __popc(bits);
+                    inter += __popc(bits & (unsigned)((gtw >> (16 * (2 * a + c))) & 0xffffull));
+                    if (P.seg_prob_sum && bits) {
+                        float ps = 0.0f;   // v3 seg-mAP score numerator: sigmoid over the foreground pixels of the cell
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if ((bits >> k) & 1u) ps += 1.0f / (1.0f + __expf(-lg[k]));
+                        psum += (double)ps;
+                    }
+                    if (P.seg_logits || P.seg_mask) {
+                        const int ybase = (ci < 0) ? 0 : 4 * ci + 2, xbase = (cj < 0) ? 0 : 4 * cj + 2;
+                        const int nry = (ci < 0) ? 2 : min(4, S_h - ybase), nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+#pragma unroll
+                        for (int ry = 0; ry < 4; ++ry) {
+                            if (ry >= nry) break;
+                            const size_t o = ((size_t)b * S_h + ybase + ry) * S_w + xbase;
+#pragma unroll
+                            for (int rx = 0; rx < 4; ++rx) {
+                                if (rx >= nrx) break;
+                                if (P.seg_logits) P.seg_logits[o + rx] = lg[ry * 4 + rx];
+                                if (P.seg_mask) P.seg_mask[o + rx] = (bits >> (ry * 4 + rx)) & 1u;
+                            }
+                        }
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        inter += __shfl_down_sync(0xffffffffu, inter, d);
+        area += __shfl_down_sync(0xffffffffu, area, d);
+    }
+    if (lane == 0) {
+        if (inter) atomicAdd(&P.acc[b * 8 + 0], inter);
+        if (area) atomicAdd(&P.acc[b * 8 + 1], area);
+    }
+    if (P.seg_prob_sum) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) psum += __shfl_down_sync(0xffffffffu, psum, d);
+        if (lane == 0 && psum != 0.0) atomicAdd(&P.seg_prob_sum[b], psum);
+    }
+}
+
+__device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int lane) {
+    const int PH = P.PH, PW = P.PW, K = P.K, NBX = P.NBX, NBY = P.NBY;
+    const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
+    if (!(rg.x <= rg.y && rg.z <= rg.w)) return;
+    const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w, bw = c_hi - c_lo + 1;
+    const int by0 = r_lo >> 1, bx0 = c_lo >> 1, nbx = ((c_hi + 1) >> 1) - bx0 + 1, nby = ((r_hi + 1) >> 1) - by0 + 1;
+    const int nblk = nbx * nby;
+    const int off = __ldg(P.scr_off + (size_t)b * K + k);
+    const float inv = 1.0f / (float)nbx;
+    int area = 0, inter = 0;
+    for (int i0 = 0; i0 < nblk; i0 += 32) {
+        const int i = i0 + lane;
+        const bool act = i < nblk;
+        int yy = __float2int_rz(((float)i + 0.5f) * inv);
+        int xx = i - yy * nbx;
+        if (xx < 0) { --yy; xx += nbx; } else if (xx >= nbx) { ++yy; xx -= nbx; }
+        const int by = act ? by0 + yy : by0, bx = act ? bx0 + xx : bx0;
+        const BlockGeo g = block_geo(by, bx, PH, PW);
+        const int rr[3] = {g.r0, g.r1, g.r2}, cc[3] = {g.c0, g.c1, g.c2};
+        bool rin[3], cin[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            rin[a] = act && rr[a] >= r_lo && rr[a] <= r_hi;
+            cin[a] = cc[a] >= c_lo && cc[a] <= c_hi;
+        }
+        float v[3][3];
+        if (off >= 0) {
+            // the crop box's logits; corners outside the box are zero (clamped address, value discarded)
+            const float *scr = P.pool + off;
+            int ro[3], co[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                ro[a] = (min(max(rr[a], r_lo), r_hi) - r_lo) * bw;
+                co[a] = min(max(cc[a], c_lo), c_hi) - c_lo;
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float x = __ldg(scr + ro[a] + co[c]);
+                    v[a][c] = (rin[a] && cin[c]) ? x : 0.0f;
+                }
+        } else {
+            // no room in the logit pool (huge crop boxes / crop off): contract the 9 corners here,
+            // same sequential order
+            const float *pr = P.protos + (size_t)b * NM * PH * PW;
+            const float mycf = __ldg(P.det_coeff + ((size_t)b * K + k) * NM + lane);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[a][c] = 0.0f;
+            for (int ch = 0; ch < NM; ++ch) {
+                const float w = __shfl_sync(0xffffffffu, mycf, ch);
+                const float *pc = pr + (size_t)ch * PH * PW;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(w, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
+            }
+        }
+        if (!act) continue;
+        const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, P.S_h, P.S_w);
+        if (bits) {
+            const size_t o = ((size_t)b * NBY + by) * NBX + bx;
+            atomicOr(P.unc + o, bits);
+            area += __popcll(bits);
+            inter += __popcll(bits & __ldg(P.gtc + o));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        inter += __shfl_down_sync(0xffffffffu, inter, d);
+        area += __shfl_down_sync(0xffffffffu, area, d);
+    }
+    if (lane == 0) {
+        if (P.inst_area) P.inst_area[(size_t)b * K + k] = area;
+        if (P.inst_inter) P.inst_inter[(size_t)b * K + k] = inter;
+    }
+}
+
+__global__ void __launch_bounds__(C_WARPS * 32) cells_kernel(const __grid_constant__ K3Params P) {
+    const int lane = threadIdx.x & 31;
+    const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items;
+    int item = 0;
+    if (lane == 0) item = atomicAdd(P.work, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    while (item < total) {
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(P.work, 1);   // in flight while this item is processed
+        if (item < ndet) {
+            const int b = item / P.K;
+            det_item(P, b, item - b * P.K, lane);
+        } else {
+            const int m = item - ndet, b = m / P.m1_items;
+            m1_item(P, b, (m - b * P.m1_items) * 32 + lane, lane);
+        }
+        item = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+}
+
+// per-image epilogue: union counters, |G|, Dice / IoU (test_model.py:15-23), optional dense union mask
+__global__ void __launch_bounds__(C_THREADS) finalize_kernel(const __grid_constant__ K3Params P) {
+    __shared__ int s_red[(C_THREADS / 32) * 3];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nblk = P.NBY * P.NBX;
+    int ui = 0, up = 0, gg = 0;
+    const u64 *un = P.unc + (size_t)b * nblk, *gt = P.gtc + (size_t)b * nblk;
+    for (int q = tid; q < nblk; q += C_THREADS) {
+        const u64 u = __ldg(un + q), g = __ldg(gt + q);
+        up += __popcll(u); ui += __popcll(u & g);
+    }
+    for (int q = tid; q < P.NBY; q += C_THREADS) gg += __ldg(P.gpart + b * P.NBY + q);
+    int v3[3] = {ui, up, gg};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int v = v3[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0) s_red[wid * 3 + i] = v;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        long long s3[3] = {0, 0, 0};
+        for (int w = 0; w < C_THREADS / 32; ++w)
+            for (int i = 0; i < 3; ++i) s3[i] += s_red[w * 3 + i];
+        long long inter, pp;
+        const long long gsum = s3[2];
+        if (tid == 0) { inter = P.acc[b * 8 + 0]; pp = P.acc[b * 8 + 1]; }
+        else { inter = s3[0]; pp = s3[1]; }
+        const long long total = (long long)P.S_h * P.S_w;
+        long long *img3 = tid ? P.uni_img3 : P.seg_img3;
+        long long *cnt4 = tid ? P.uni_cnt4 : P.seg_cnt4;
+        float *dice = tid ? P.uni_dice : P.seg_dice, *iou = tid ? P.uni_iou : P.seg_iou;
+        if (img3) { img3[b * 3 + 0] = inter; img3[b * 3 + 1] = pp; img3[b * 3 + 2] = gsum; }
+        if (cnt4) {
+            atomicAdd((unsigned long long *)&cnt4[0], (unsigned long long)inter);
+            atomicAdd((unsigned long long *)&cnt4[1], (unsigned long long)(pp - inter));
+            atomicAdd((unsigned long long *)&cnt4[2], (unsigned long long)(gsum - inter));
+            atomicAdd((unsigned long long *)&cnt4[3], (unsigned long long)(total - pp - gsum + inter));
+        }
+        const float fi = (float)inter, fu = (float)(pp + gsum - inter);
+        if (iou) iou[b] = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
+        if (dice) dice[b] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gsum), 1e-7f));
+    }
+    if (P.uni_mask) {
+        // union words -> bytes: thread = (output row, block), 8 pixels of that row (6 in block column 0)
+        const int S_h = P.S_h, S_w = P.S_w;
+        for (int q = tid; q < S_h * P.NBX; q += C_THREADS) {
+            const int y = q / P.NBX, bx = q - y * P.NBX;
+            const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+            const int by = (ci + 1) >> 1, a = (ci + 1) & 1;
+            const u64 w = __ldg(un + (size_t)by * P.NBX + bx);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int cj = 2 * bx - 1 + c;
+                if (cj > P.PW - 1) continue;
                 const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                const unsigned nib = (s_unc[(ci - ci_lo) * ncc_all + cj + 1] >> (4 * ry)) & 0xfu;
+                const unsigned nib = (unsigned)(w >> (16 * (2 * a + c) + 4 * ry)) & 0xfu;
                 uint8_t *o = P.uni_mask + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
                 *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
                 if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
             }
         }
-        __syncthreads();   // tiles and tables are released
-        BT_PHASE_MARK(2, 5);   // counters + dense outputs
-        seq_base = next_base;
-        prebuilt = prebuild_next;
-        b = nb; s = ns;
     }
-    flush_image(cur_b, strips_of_b);
-    // When launched as a programmatic dependent (of the COCO matching kernel, whose data this kernel never
-    // touches) the completion of this grid must still imply the completion of that one; it finished long ago.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-static size_t k3_layout(K3Params &P) {
-    const int rowsmax = P.R + 1;
-    size_t off = (size_t)P.NS * NM * P.PW * sizeof(float);
-    P.wpr = P.S_w / 32;
-    const size_t celltile = align_up((size_t)rowsmax * (P.PW + 1) * sizeof(uint32_t), 16);
-    P.off_lm = (int)off; off += (size_t)rowsmax * P.PW * sizeof(float);
-    P.off_scr = (int)off; off += (size_t)(P.scr_cap + rowsmax * P.PW) * sizeof(float);
-    P.off_gtrow = (int)off; off += align_up((size_t)(4 * P.R + 2) * (P.wpr + 1) * sizeof(uint32_t), 16);
-    P.off_gtc = (int)off; off += celltile;
-    P.off_unc = (int)off; off += celltile;
-    P.off_list = (int)off; off += 2 * align_up((size_t)P.K * sizeof(unsigned short), 16);
-    P.off_cf = (int)off; off += align_up((size_t)ECAP * CF_PITCH * sizeof(float), 16);
-    return off;
-}
-
-// 3-D tensor map of the prototypes: dims (fastest first) {PW, PH, B*NM}, box {PW, 1, NM}.
+// 3-D tensor map of the prototypes: dims (fastest first) {PW, PH, B*NM}, box {TA_W, TA_H, NM}, 128-byte swizzle.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -801,88 +741,63 @@ static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, 
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)B * NM};
     const cuuint64_t gstride[2] = {(cuuint64_t)PW * sizeof(float), (cuuint64_t)PW * PH * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)PW, 1u, (cuuint32_t)NM};
+    const cuuint32_t box[3] = {(cuuint32_t)TA_W, (cuuint32_t)TA_H, (cuuint32_t)NM};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(protos), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
 }
 
-static bool g_pdl = false;   // set by launch_masks for the launch below (host-side, per call)
-template <int TPW, int NT, int MINB>
-static int launch_k3(const K3Params &P, const CUtensorMap &tm, int grid, size_t smem, cudaStream_t s) {
-    if (cudaFuncSetAttribute(masks_kernel<TPW, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return BT_ERR_CUDA;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, masks_kernel<TPW, NT, MINB>, P, tm) != cudaSuccess) return BT_ERR_CUDA;
-    return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
-}
-
 int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, bool pdl) {
-    g_pdl = pdl;
+    (void)pdl;
     K3Params P{};
     P.B = p.batch; P.S_h = p.img_h; P.S_w = p.img_w; P.PH = p.proto_h; P.PW = p.proto_w;
-    P.K = p.max_det; P.crop = p.crop; P.gt_f32 = p.gt_mask_dtype == BT_MASK_F32;
+    P.K = p.max_det; P.gt_f32 = p.gt_mask_dtype == BT_MASK_F32;
     P.bias = p.proj_bias;
     P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
-    P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region;
-    P.strip_done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region; P.scr_off = w.scr_off;
+    P.pool = w.pool; P.lm = w.lm; P.gtc = w.gtc; P.unc = w.unc; P.gpart = w.gpart;
+    P.work = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
     P.seg_mask = io.seg_mask; P.uni_mask = io.uni_mask; P.seg_logits = io.seg_logits;
     P.seg_prob_sum = io.seg_prob_sum;
-    if (p.proto_w % 4 != 0 || p.proto_w > 256) return BT_ERR_UNSUPPORTED;   // TMA box width <= 256
-    // Two persistent 256-thread CTAs per SM (their phases overlap: the contraction is bound by shared-
-    // memory bandwidth, the upsample/threshold by the ALUs) when a ring of R + 1 rows with R >= 2 fits
-    // half an SM's shared memory -- a strip releases its rows after its last contraction, so the next
-    // strip's rows land during its second half; otherwise one 512-thread CTA with the deepest ring.
-    int nt = 0;
-    static const bool force_fat = getenv("BTPOST_K3_FAT") != nullptr;   // developer switch (scripts/): compare the two configurations
-    for (int R = 3; R >= 2 && !nt && !force_fat; --R) {
-        K3Params tmp = P; tmp.R = R; tmp.NS = R + 1; tmp.scr_cap = 1792;
-        if ((R + 1) * P.PW <= tmp.scr_cap && k3_layout(tmp) + 128 + 6144 <= 113 * 1024) { P.R = R; P.NS = R + 1; P.scr_cap = 1792; nt = 256; }
-    }
-    for (int R = 4; R >= 1 && !nt; --R)
-        for (int NS = 2 * R + 1; NS >= R + 1 && !nt; --NS) {
-            if (NS > NS_MAX) continue;
-            K3Params tmp = P; tmp.R = R; tmp.NS = NS; tmp.scr_cap = 4096;
-            if (k3_layout(tmp) + 128 <= 222 * 1024) { P.R = R; P.NS = NS; P.scr_cap = 4096; nt = 512; }
-        }
-    if (!nt) return BT_ERR_UNSUPPORTED;
-    const size_t smem = k3_layout(P) + 128;
-    P.nstrips = (p.proto_h + P.R - 1) / P.R;
-    P.total_strips = P.nstrips * p.batch;
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
-            return BT_ERR_CUDA;
-    }
-    const int ctas = sm_count * (nt == 256 ? 2 : 1);
-    const int grid = P.total_strips < ctas ? P.total_strips : ctas;
+    if (p.proto_w % 4 != 0) return BT_ERR_UNSUPPORTED;   // 16-byte global strides for the tensor map
+    P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
+    P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
+    P.m1_items = (P.NBY * P.NBX + 31) / 32;
     CUtensorMap tm;
     if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
-    static const char *nt_env = getenv("BTPOST_K3_NT");   // developer switch: threads per CTA of the 2-CTA configuration
-    if (nt == 256 && nt_env && P.PW == 160) {
-        if (atoi(nt_env) == 384) return launch_k3<160, 384, 2>(P, tm, grid, smem, s);
-        if (atoi(nt_env) == 512) return launch_k3<160, 512, 2>(P, tm, grid, smem, s);
+
+    const size_t smem_g = (size_t)8 * (p.img_w / 32 + 1) * sizeof(uint32_t);
+    gt_pack_kernel<<<dim3(P.NBY, p.batch), C_THREADS, smem_g, s>>>(P);
+
+    const size_t smem_a = (size_t)2 * NM * TA_H * TA_W * sizeof(float) + align_up((size_t)p.max_det * sizeof(unsigned short), 16) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+            return BT_ERR_CUDA;
+        attr_set = true;
     }
-    if (nt == 256) {
-        if (P.PW == 160) return launch_k3<160, 256, 2>(P, tm, grid, smem, s);
-        if (P.PW == 256) return launch_k3<256, 256, 2>(P, tm, grid, smem, s);
-        return launch_k3<0, 256, 2>(P, tm, grid, smem, s);
+    {
+        static int sm_count = 0;
+        if (!sm_count) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+                return BT_ERR_CUDA;
+        }
+        if (smem_a > 100 * 1024) return BT_ERR_UNSUPPORTED;
+        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * 3;
+        contract_kernel<<<ntiles < cta_a ? ntiles : cta_a, A_THREADS, smem_a, s>>>(P, tm);
+        const long long items = (long long)p.batch * (p.max_det + P.m1_items);
+        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
+        cells_kernel<<<(unsigned)(want < cap ? want : cap), C_WARPS * 32, 0, s>>>(P);
     }
-    if (P.PW == 160) return launch_k3<160, 512, 1>(P, tm, grid, smem, s);
-    if (P.PW == 256) return launch_k3<256, 512, 1>(P, tm, grid, smem, s);
-    return launch_k3<0, 512, 1>(P, tm, grid, smem, s);
+    finalize_kernel<<<p.batch, C_THREADS, 0, s>>>(P);
+    return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
 }  // namespace bt

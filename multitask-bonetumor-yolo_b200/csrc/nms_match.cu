@@ -127,6 +127,7 @@ struct K2Params {
     double *seg_prob_sum;
     int region0_bytes;    // shared region 0: list of candidate indices in NMS order
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
+    int32_t *scr_off; unsigned long long *pool_used; long long pool_cap;   // logit-pool plan of the mask stage
     int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
     int gx, gy; float inv_cw, inv_ch;   // centre-cell grid
     int coco_smem_doubles;
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
     // zero the per-image accumulators the mask kernel adds into
     if (tid < 8) P.acc[b * 8 + tid] = 0;
     if (tid == 8) P.strip_done[b] = 0;
+    if (tid == 10 && b == 0) *P.pool_used = 0ull;
     if (tid == 9 && P.seg_prob_sum) P.seg_prob_sum[b] = 0.0;
     for (int i = tid; i < K; i += K2_THREADS) {
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
@@ -533,15 +535,63 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
     const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int K = P.max_det;
     const int k = blockIdx.x * 8 + wid, m = lane;
-    if (k >= K) return;
-    const int a = P.det_anchor[(size_t)b * K + k];
-    float v = 0.0f;
-    if (a >= 0) {
-        const float *src = (P.layout == BT_LAYOUT_L2) ? P.head + ((size_t)b * P.C + 4 + P.nc) * P.N
-                                                      : P.coeffs + (size_t)b * P.nm * P.N;
-        v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
+    if (k < K) {
+        const int a = P.det_anchor[(size_t)b * K + k];
+        float v = 0.0f;
+        if (a >= 0) {
+            const float *src = (P.layout == BT_LAYOUT_L2) ? P.head + ((size_t)b * P.C + 4 + P.nc) * P.N
+                                                          : P.coeffs + (size_t)b * P.nm * P.N;
+            v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
+        }
+        P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
     }
-    P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
+    if (blockIdx.x != 0) return;
+    // ---- plan of the mask stage (first CTA of the image): where each detection's crop-box logits live in the
+    // pool.  Exclusive prefix sum of the box areas; the image's base comes from one bump of the pool counter.
+    __shared__ long long s_base;
+    const int tid = threadIdx.x;
+    const int per = (K + GM_THREADS - 1) / GM_THREADS;
+    const short4 *reg = P.det_region + (size_t)b * K;
+    int mine = 0;
+    for (int i = 0; i < per; ++i) {
+        const int kk = tid * per + i;
+        if (kk < K) {
+            const short4 rg = reg[kk];
+            if (rg.x <= rg.y && rg.z <= rg.w) mine += (rg.y - rg.x + 1) * (rg.w - rg.z + 1);
+        }
+    }
+    // a full-image box is < 2^16 * 2^16; the running sum is kept in 64 bits only across warps
+    long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    __shared__ long long s_wtot[GM_THREADS / 32];
+    if (lane == 31) s_wtot[wid] = incl;
+    __syncthreads();
+    long long before = 0, total = 0;
+    for (int w = 0; w < GM_THREADS / 32; ++w) { const long long v = s_wtot[w]; if (w < wid) before += v; total += v; }
+    if (tid == 0) {
+        // the counter saturates instead of wrapping: images that find the pool full use no pool at all
+        const long long want = total > P.pool_cap ? P.pool_cap : total;
+        s_base = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(P.pool_used), (unsigned long long)want);
+    }
+    __syncthreads();
+    long long off = s_base + before + incl - mine;
+    for (int i = 0; i < per; ++i) {
+        const int kk = tid * per + i;
+        if (kk < K) {
+            const short4 rg = reg[kk];
+            int o = -1;
+            if (rg.x <= rg.y && rg.z <= rg.w) {
+                const long long area = (long long)(rg.y - rg.x + 1) * (rg.w - rg.z + 1);
+                if (off + area <= P.pool_cap) o = (int)off;
+                off += area;
+            }
+            P.scr_off[(size_t)b * K + kk] = o;
+        }
+    }
 }
 
 // =================================================================================================
@@ -715,6 +765,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.rx = (float)((double)p.proto_w / (double)p.img_w);
     P.ry = (float)((double)p.proto_h / (double)p.img_h);
     P.det_region = w.det_region;
+    P.scr_off = w.scr_off; P.pool_used = w.pool_used; P.pool_cap = w.pool_cap;
     // centre-cell grid: cells of >= 64 px, at most 16 x 16
     P.gx = p.img_w / 64 < 1 ? 1 : (p.img_w / 64 > 16 ? 16 : p.img_w / 64);
     P.gy = p.img_h / 64 < 1 ? 1 : (p.img_h / 64 > 16 ? 16 : p.img_h / 64);
