@@ -225,7 +225,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- warm-up; the step is captured once into a CUDA graph (5 kernels per replay)
+    # ---------------- warm-up; the step is captured once into a CUDA graph (8 kernels per replay)
     graph = pp.capture(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], bias)
     out = pp.out
     for _ in range(args.warmup):
@@ -260,11 +260,12 @@ def main():
 
     # ---------------- per-stage device times (CUDA events on the launching stream)
     stage_ms = {}
-    for stage in ("decode_filter", "nms_match", "masks"):
+    ORDER = ("decode_filter", "nms_match", "masks_pack", "masks_contract", "masks_cells")
+    for stage in ORDER:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tot = 0.0
         for _ in range(args.steps):
-            for s2 in ("decode_filter", "nms_match", "masks"):   # keep the real order so caches look like a step
+            for s2 in ORDER:   # keep the real order so caches look like a step
                 if s2 == stage:
                     e0.record()
                 step(stage=s2)
@@ -317,13 +318,13 @@ def main():
         peaks = json.loads(pk.read_text())
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     ab = algorithmic_bytes_per_image(S)
-    mask_bytes = (ab["protos"] + ab["gt_mask"]) * B       # algorithmic bytes of one masks_kernel launch
-    achieved = mask_bytes / (stage_ms["masks"] / 1e3) / 1e9
+    mask_bytes = ab["protos"] * B       # algorithmic bytes of one contract_kernel launch: the prototypes, once
+    achieved = mask_bytes / (stage_ms["masks_contract"] / 1e3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(f"masks_kernel_B{B}_S{S}")
+            traffic = json.loads(tf.read_text()).get(f"contract_kernel_B{B}_S{S}")
         except Exception:
             traffic = None
     line = {
@@ -332,15 +333,16 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": B * world, "sharding": f"images sharded, {B}/GPU",
                    "l2": "inputs (%.0f MB/step/GPU) larger than the 126 MB L2" % (ab["total"] * B / 1e6)},
-        "roofline": {"bound": "hbm", "kernel": "masks_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "contract_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": mask_bytes},
         "pipeline": {"algorithmic_bytes_per_image": ab["total"],
                      "achieved_gbs": ab["total"] * B / (ms / args.steps / 1e3) / 1e9,
                      "frac_of_peak": ab["total"] * B / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
                      "stage_ms": stage_ms},
-        "clocks": clocks, "gpu_launches": 5 * args.steps,
-        "kernels_per_step": ["decode_filter_l2_kernel", "nms_kernel", "coeff_gather_kernel", "match_kernel", "masks_kernel"],
+        "clocks": clocks, "gpu_launches": 8 * args.steps,
+        "kernels_per_step": ["gt_pack_kernel", "decode_filter_l2_kernel", "nms_kernel", "coeff_gather_kernel", "match_kernel",
+                             "contract_kernel", "cells_kernel", "finalize_kernel"],
     }
     if e2e:
         line["e2e"] = e2e

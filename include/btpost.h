@@ -7,8 +7,8 @@
  * intended method `_prepare_det_outputs_for_metrics_and_logging` (src/evaluate_model.py:174-178).
  * Each entry point below names the reference statements it replaces.  Everything is plain C:
  * pointers, sizes, POD structs; no torch types.  All pointers are DEVICE pointers owned by the
- * caller unless stated otherwise.  The library never allocates, never synchronises, keeps no
- * mutable global state, and enqueues all work on the caller's stream (CUDA-graph capturable).
+ * caller unless stated otherwise.  The library never allocates device memory, never synchronises, and orders
+ * all work on the caller's stream (CUDA-graph capturable; btpost_run forks one helper stream, see below).
  *
  * Return value: 0 on success, a negative BT_ERR_* otherwise (btpost_error_string decodes it).
  */
@@ -154,7 +154,18 @@ BTPOST_API int btpost_nms_match(const BtParams *p, const BtIO *io, void *ws, siz
  * Replaces src/running_main_v2.py:689-713, src/test_model.py:15-23,80-89. */
 BTPOST_API int btpost_masks(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
-/* Whole hot path for one batch: the three stages above, back to back on `stream`. */
+/* The kernels of btpost_masks one by one (same arguments; `parts` is an OR of BT_MASKS_*), in the order
+ * PACK -> CONTRACT -> CELLS on one stream: GT mask bytes -> bits (independent of the detections), the one pass over
+ * the prototypes (projector + per-detection K=32 contraction, logits to the workspace), bilinear x4 + threshold +
+ * counters + per-image Dice/IoU.  Used by btpost_run to overlap PACK with the detection stages, and by bench.py to
+ * time the HBM-side kernel alone. */
+enum { BT_MASKS_PACK = 1, BT_MASKS_CONTRACT = 2, BT_MASKS_CELLS = 4 };
+BTPOST_API int btpost_masks_parts(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream, int parts);
+
+/* Whole hot path for one batch: the three stages above, ordered on `stream`.  The GT-bit packing and the COCO
+ * matching run on a helper stream of the library (one per device) that is forked from and joined back into `stream`
+ * with events, so the call is still a unit of work on `stream` and capturable into a CUDA graph; concurrent
+ * btpost_run calls on the same device from several host threads are not supported. */
 BTPOST_API int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus

@@ -75,8 +75,13 @@ def load():
             f = getattr(L, name)
             f.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p]
             f.restype = C.c_int
+    L.btpost_masks_parts.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    L.btpost_masks_parts.restype = C.c_int
     _lib = L
     return L
+
+
+MASKS_PACK, MASKS_CONTRACT, MASKS_CELLS = 1, 2, 4   # btpost_masks_parts
 
 
 def check(rc: int, what: str):

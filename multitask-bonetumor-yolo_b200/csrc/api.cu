@@ -67,6 +67,28 @@ static int check_stage3(const BtParams *p, const BtIO *io) {
     return BT_OK;
 }
 
+// One helper stream per device for btpost_run: the GT-bit packing (independent of the detections) runs beside the
+// decode / NMS kernels, which leave most SMs idle, and the COCO matching beside the mask kernels.  The helper
+// stream is forked from and joined back into the caller's stream with events, so the whole call is still ordered
+// on the caller's stream and capturable into a CUDA graph.  Calls on the same device are not re-entrant.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, pack = nullptr, nms = nullptr, join = nullptr;
+};
+static SideStream *side_stream() {
+    static SideStream tab[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream &t = tab[dev];
+    if (!t.stream) {
+        if (cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking) != cudaSuccess) { t.stream = nullptr; return nullptr; }
+        cudaEvent_t *ev[4] = {&t.fork, &t.pack, &t.nms, &t.join};
+        for (auto e : ev)
+            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &t;
+}
+
 }  // namespace bt
 
 using namespace bt;
@@ -124,11 +146,16 @@ int btpost_nms_match(const BtParams *p, const BtIO *io, void *ws, size_t ws_byte
 }
 
 int btpost_masks(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream) {
+    return btpost_masks_parts(p, io, ws, ws_bytes, stream, BT_MASKS_PACK | BT_MASKS_CONTRACT | BT_MASKS_CELLS);
+}
+
+int btpost_masks_parts(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream, int parts) {
     int rc = check_params(p, io);
     if (rc == BT_OK) rc = check_ws(p, ws, ws_bytes);
     if (rc == BT_OK) rc = check_stage3(p, io);
+    if (rc == BT_OK && (parts & ~7)) rc = BT_ERR_BAD_ARG;
     if (rc != BT_OK) return rc;
-    return launch_masks(*p, *io, carve(p, ws), static_cast<cudaStream_t>(stream));
+    return launch_masks(*p, *io, carve(p, ws), static_cast<cudaStream_t>(stream), parts);
 }
 
 int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream) {
@@ -140,10 +167,23 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     if (rc != BT_OK) return rc;
     Workspace w = carve(p, ws);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    rc = launch_decode_filter(*p, *io, w, s);
-    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s);
-    // the mask kernel overlaps the COCO matching kernel (launched last by the NMS stage) when there is one
-    if (rc == BT_OK) rc = launch_masks(*p, *io, w, s, io->dt_match != nullptr);
+    SideStream *side = side_stream();
+    if (!side) return BT_ERR_CUDA;
+    auto ok = [](cudaError_t e) { return e == cudaSuccess; };
+    // fork: GT bits on the helper stream while the caller's stream decodes, filters and runs the NMS
+    if (!ok(cudaEventRecord(side->fork, s)) || !ok(cudaStreamWaitEvent(side->stream, side->fork, 0))) return BT_ERR_CUDA;
+    rc = launch_masks(*p, *io, w, side->stream, BT_MASKS_PACK);
+    if (rc == BT_OK && !ok(cudaEventRecord(side->pack, side->stream))) rc = BT_ERR_CUDA;
+    if (rc == BT_OK) rc = launch_decode_filter(*p, *io, w, s);
+    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s, BT_NMS_SORT_SWEEP);
+    // COCO matching on the helper stream, beside the mask kernels
+    if (rc == BT_OK && (!ok(cudaEventRecord(side->nms, s)) || !ok(cudaStreamWaitEvent(side->stream, side->nms, 0)))) rc = BT_ERR_CUDA;
+    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_COCO);
+    if (rc == BT_OK && !ok(cudaEventRecord(side->join, side->stream))) rc = BT_ERR_CUDA;
+    if (rc == BT_OK && !ok(cudaStreamWaitEvent(s, side->pack, 0))) rc = BT_ERR_CUDA;
+    if (rc == BT_OK) rc = launch_masks(*p, *io, w, s, BT_MASKS_CONTRACT | BT_MASKS_CELLS);
+    // join (always, so that a capture never ends with an unjoined stream)
+    if (!ok(cudaStreamWaitEvent(s, side->join, 0)) && rc == BT_OK) rc = BT_ERR_CUDA;
     return rc;
 }
 

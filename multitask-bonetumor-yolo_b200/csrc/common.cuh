@@ -60,6 +60,7 @@ struct Workspace {
     short4 *det_region;   // [B, K] crop region of each kept detection at prototype resolution (r_lo, r_hi, c_lo, c_hi)
     int32_t *scr_off;     // [B, K] offset (floats) of the detection's crop-box logits in `pool`; -1: none (invalid / pool full)
     unsigned long long *pool_used;   // [1] floats handed out of `pool` in this call
+    int32_t *work;        // [32 * 32] work-queue counters of cells_kernel (one per 128 bytes)
     int32_t *gpart;       // [B, NBY] GT pixels per row of cell blocks
     unsigned long long *gtc, *unc;   // [B, NBY, NBX] GT / union-of-instance-masks bits per 2x2 block of cells
     float *lm;            // [B, PH, PW] projector logits at prototype resolution
@@ -117,6 +118,7 @@ static inline Workspace carve(const BtParams *p, void *base) {
     const size_t nby = (size_t)mask_blocks(p->proto_h), nbx = (size_t)mask_blocks(p->proto_w);
     w.scr_off = reinterpret_cast<int32_t *>(take(B * (size_t)p->max_det * sizeof(int32_t)));
     w.pool_used = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long)));
+    w.work = reinterpret_cast<int32_t *>(take(32 * 32 * sizeof(int32_t)));
     w.gpart = reinterpret_cast<int32_t *>(take(B * nby * sizeof(int32_t)));
     w.gtc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
     w.unc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
@@ -129,9 +131,11 @@ static inline Workspace carve(const BtParams *p, void *base) {
 
 int check_params(const BtParams *p, const BtIO *io);
 int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s);
-int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s);
-// pdl: launch as a programmatic dependent of the preceding kernel in the stream (match_kernel, which the
-// mask kernel neither reads from nor writes to)
-int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, bool pdl = false);
+// parts: BT_NMS_SORT_SWEEP (NMS + coefficient gather + mask-stage plan), BT_NMS_COCO (evaluateImg matching)
+enum { BT_NMS_SORT_SWEEP = 1, BT_NMS_COCO = 2 };
+int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts = 3);
+// parts: BT_MASKS_PACK (GT bits; independent of the detections), BT_MASKS_CONTRACT (the pass over the prototypes),
+// BT_MASKS_CELLS (upsample + threshold + counters + per-image finalize)
+int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts = 7);
 
 }  // namespace bt

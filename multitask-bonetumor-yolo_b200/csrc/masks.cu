@@ -39,6 +39,7 @@ constexpr int TA_W = 32, TA_H = 8;      // contract_kernel tile (prototype pixel
 constexpr int A_THREADS = 128;          // 4 warps, each an 8 x 8 pixel block, 2 pixels per thread
 constexpr int A_LCAP = 32;              // detections staged per round
 constexpr int C_THREADS = 256;
+constexpr int C_NQ = 32, C_QSTRIDE = 32;   // work queues of cells_kernel: counters 128 bytes apart
 
 typedef unsigned long long u64;
 
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constan
     const int nyr = y_hi - y_lo;
     if (by == 0) {
         if (tid < 8) P.acc[b * 8 + tid] = 0;
-        if (tid == 8 && b == 0) *P.work = 0;
+        if (b == 0 && tid >= 32 && tid < 32 + C_NQ) P.work[(tid - 32) * C_QSTRIDE] = 0;
     }
     for (int q = tid; q < 8 * tp; q += C_THREADS) {
         const int yr = q / tp, w = q - yr * tp;
@@ -336,15 +337,20 @@ __global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constan
 // =================================================================================================
 // contract_kernel: one pass over the prototypes
 // =================================================================================================
-__global__ void __launch_bounds__(A_THREADS, 3)
+constexpr int A_KCACHE = 1024;   // detections of an image whose crop regions / pool offsets are cached in shared memory
+
+__global__ void __launch_bounds__(A_THREADS, 4)
 contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destinations must be 1024-byte aligned: align by hand (1024 spare bytes are allocated)
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     constexpr int TILE_FLOATS = NM * TA_H * TA_W;
-    float *s_tiles = reinterpret_cast<float *>(smem);                                  // [2][NM][TA_H][TA_W], 16-byte chunks XOR row
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(smem + 2 * TILE_FLOATS * 4);    // [K]
-    __shared__ __align__(8) uint64_t s_bar[2];
+    float *s_tile = reinterpret_cast<float *>(smem);                                   // [NM][TA_H][TA_W], 16-byte chunks XOR row
+    const int KC = min(P.K, A_KCACHE);
+    short4 *s_creg = reinterpret_cast<short4 *>(smem + TILE_FLOATS * 4);           // [KC] crop regions of the current image
+    int *s_coff = reinterpret_cast<int *>(s_creg + KC);                                // [KC] pool offsets
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_coff + KC);          // [K] detections listed on the tile
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) float s_cf[A_LCAP][NM];
     __shared__ short4 s_reg[A_LCAP];
     __shared__ int s_off[A_LCAP];        // pool offset of the box origin minus (r_lo * bw + c_lo): + r * bw + c addresses a pixel
@@ -354,22 +360,24 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tiles = P.ntx * P.nty, total = tiles * P.B;
     const int PH = P.PH, PW = P.PW, K = P.K;
+    // this CTA's contiguous range of tiles (mostly one image: its regions are cached once)
+    const int t_begin = (int)(((long long)blockIdx.x * total) / gridDim.x), t_end = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+    if (t_begin >= t_end) return;
 
-    auto issue = [&](int tile, int stage) {   // thread 0
+    // The tile buffer is dead as soon as every thread holds its pixels in registers: the next tile's TMA is issued
+    // right then and lands under this tile's arithmetic (one buffer, four CTAs per SM).
+    auto issue = [&](int tile) {   // thread 0
         const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
-        mbar_expect_tx(&s_bar[stage], (uint32_t)(TILE_FLOATS * sizeof(float)));
-        tma_tile_g2s(s_tiles + stage * TILE_FLOATS, &tmap, tx * TA_W, ty * TA_H, b * NM, &s_bar[stage]);
+        mbar_expect_tx(&s_bar, (uint32_t)(TILE_FLOATS * sizeof(float)));
+        tma_tile_g2s(s_tile, &tmap, tx * TA_W, ty * TA_H, b * NM, &s_bar);
     };
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
-        if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+        issue(t_begin);
         s_n = 0;
     }
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
-    __syncthreads();
 
     // this thread's two pixels: rows {0,2,4,6} in lanes 0-15 and {1,3,5,7} in lanes 16-31 keep the 8-byte shared
     // loads of the swizzled tile free of bank conflicts
@@ -377,42 +385,70 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     const int row = 2 * (i16 >> 2) + (lane >> 4), colp = (wid << 3) + 2 * (i16 & 3);   // tile-local row / first column
     const int soff = row * TA_W + (((colp >> 2) ^ row) << 2) + (colp & 3);
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
+    int cur_b = -1, n = 0;
+    for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
         const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
         const int R0 = ty * TA_H, C0 = tx * TA_W;
         const int r = R0 + row, c = C0 + colp;
 
-        // ---- detections whose crop box touches the tile (any order: every (detection, pixel) logit is independent)
-        {
-            const int n = min(__ldg(P.det_count + b), K);
-            for (int k0 = 0; k0 < n; k0 += A_THREADS) {
-                const int k = k0 + tid;
-                bool ok = false;
-                if (k < n) {
-                    const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
-                    ok = rg.x <= rg.y && rg.z <= rg.w && rg.x <= R0 + TA_H - 1 && rg.y >= R0 && rg.z <= C0 + TA_W - 1 && rg.w >= C0 &&
-                         __ldg(P.scr_off + (size_t)b * K + k) >= 0;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                int base = 0;
-                if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (ok) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+        if (b != cur_b) {
+            // new image: its crop regions and pool offsets -> shared memory (detections without pool room are dropped here)
+            cur_b = b;
+            n = min(__ldg(P.det_count + b), K);
+            for (int k = tid; k < min(n, KC); k += A_THREADS) {
+                short4 rg = __ldg(P.det_region + (size_t)b * K + k);
+                const int off = __ldg(P.scr_off + (size_t)b * K + k);
+                if (off < 0) rg = make_short4(1, 0, 1, 0);
+                s_creg[k] = rg; s_coff[k] = off;
             }
         }
-        // ---- the tile: shared memory -> registers, then the stage is free for the tile after next
-        mbar_wait(&s_bar[stage], (uint32_t)((it >> 1) & 1));
+        __syncthreads();   // region cache (and, first tile, the barriers / projector weights)
+
+        // ---- detections whose crop box touches the tile (any order: every (detection, pixel) logit is independent)
+        for (int k0 = 0; k0 < n; k0 += A_THREADS) {
+            const int k = k0 + tid;
+            bool ok = false;
+            if (k < n) {
+                short4 rg;
+                if (k < KC) rg = s_creg[k];
+                else {
+                    rg = __ldg(P.det_region + (size_t)b * K + k);
+                    if (__ldg(P.scr_off + (size_t)b * K + k) < 0) rg = make_short4(1, 0, 1, 0);
+                }
+                ok = rg.x <= rg.y && rg.z <= rg.w && rg.x <= R0 + TA_H - 1 && rg.y >= R0 && rg.z <= C0 + TA_W - 1 && rg.w >= C0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ok) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+        }
+        __syncthreads();
+        const int nlist = s_n;
+
+        // ---- first round's coefficients: global loads in flight under the tile wait and the projection
+        const int nch0 = min(A_LCAP, nlist);
+        float4 cfr[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int q = tid + j * A_THREADS;
+            if (q < nch0 * (NM / 4))
+                cfr[j] = __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + s_list[q >> 3]) * NM) + (q & 7));
+        }
+
+        // ---- the tile: shared memory -> registers, then the buffer is free for the next tile
+        mbar_wait(&s_bar, (uint32_t)(it & 1));
         u64 p[NM];
         {
-            const float *src = s_tiles + stage * TILE_FLOATS + soff;
+            const float *src = s_tile + soff;
 #pragma unroll
             for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
         }
         __syncthreads();
-        const int nlist = s_n;
-        if (tid == 0 && tile + 2 * (int)gridDim.x < total) issue(tile + 2 * gridDim.x, stage);
+        if (tid == 0) {
+            if (tile + 1 < t_end) issue(tile + 1);
+            s_n = 0;   // every warp has read it (two barriers ago)
+        }
 
         // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
         {
@@ -433,27 +469,63 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         const int wc0 = C0 + (wid << 3);   // the warp's 8 x 8 block: rows R0 .. R0+7, columns wc0 .. wc0+7
         for (int r0 = 0; r0 < nlist; r0 += A_LCAP) {
             const int nch = min(A_LCAP, nlist - r0);
-            if (r0 > 0) __syncthreads();
-            for (int q = tid; q < nch * (NM / 4); q += A_THREADS) {
-                const int e = q >> 3, i = q & 7;
-                reinterpret_cast<float4 *>(&s_cf[e][0])[i] =
-                    __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + s_list[r0 + e]) * NM) + i);
+            if (r0 == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int q = tid + j * A_THREADS;
+                    if (q < nch * (NM / 4)) reinterpret_cast<float4 *>(&s_cf[q >> 3][0])[q & 7] = cfr[j];
+                }
+            } else {
+                __syncthreads();   // the previous round's tables are still being read
+                for (int q = tid; q < nch * (NM / 4); q += A_THREADS)
+                    reinterpret_cast<float4 *>(&s_cf[q >> 3][0])[q & 7] =
+                        __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + s_list[r0 + (q >> 3)]) * NM) + (q & 7));
             }
             if (tid < nch) {
                 const int k = s_list[r0 + tid];
-                const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
+                short4 rg; int off;
+                if (k < KC) { rg = s_creg[k]; off = s_coff[k]; }
+                else { rg = __ldg(P.det_region + (size_t)b * K + k); off = __ldg(P.scr_off + (size_t)b * K + k); }
                 s_reg[tid] = rg;
-                s_off[tid] = __ldg(P.scr_off + (size_t)b * K + k) - (rg.x * (rg.w - rg.z + 1) + rg.z);
+                s_off[tid] = off - (rg.x * (rg.w - rg.z + 1) + rg.z);
             }
             __syncthreads();
             // the round's detections that touch this warp's block: one lane tests one detection
             short4 mine = make_short4(1, 0, 1, 0);
             if (lane < nch) mine = s_reg[lane];
-            unsigned todo = __ballot_sync(0xffffffffu, mine.x <= R0 + TA_H - 1 && mine.y >= R0 && mine.z <= wc0 + 7 && mine.w >= wc0);
-            while (todo) {
-                const int e = __ffs(todo) - 1;
-                todo &= todo - 1;
+            unsigned todo = __ballot_sync(0xffffffffu, lane < nch && mine.x <= R0 + TA_H - 1 && mine.y >= R0 && mine.z <= wc0 + 7 &&
+                                                           mine.w >= wc0);
+            auto store = [&](int e, u64 acc) {
                 const short4 rg = s_reg[e];
+                if (r >= rg.x && r <= rg.y) {
+                    float a0, a1;
+                    unpack2(acc, a0, a1);
+                    float *dst = P.pool + (s_off[e] + r * (rg.w - rg.z + 1) + c);
+                    if (c >= rg.z && c <= rg.w) dst[0] = a0;
+                    if (c + 1 >= rg.z && c + 1 <= rg.w) dst[1] = a1;
+                }
+            };
+            // two detections at a time: two independent FFMA2 chains per thread
+            while (todo & (todo - 1)) {
+                const int e0 = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int e1 = __ffs(todo) - 1;
+                todo &= todo - 1;
+                u64 acc0 = pack2(0.0f, 0.0f), acc1 = acc0;
+#pragma unroll
+                for (int k4 = 0; k4 < NM / 4; ++k4) {
+                    const float4 w0 = reinterpret_cast<const float4 *>(&s_cf[e0][0])[k4];
+                    const float4 w1 = reinterpret_cast<const float4 *>(&s_cf[e1][0])[k4];
+                    acc0 = fma2(pack2(w0.x, w0.x), p[4 * k4 + 0], acc0); acc1 = fma2(pack2(w1.x, w1.x), p[4 * k4 + 0], acc1);
+                    acc0 = fma2(pack2(w0.y, w0.y), p[4 * k4 + 1], acc0); acc1 = fma2(pack2(w1.y, w1.y), p[4 * k4 + 1], acc1);
+                    acc0 = fma2(pack2(w0.z, w0.z), p[4 * k4 + 2], acc0); acc1 = fma2(pack2(w1.z, w1.z), p[4 * k4 + 2], acc1);
+                    acc0 = fma2(pack2(w0.w, w0.w), p[4 * k4 + 3], acc0); acc1 = fma2(pack2(w1.w, w1.w), p[4 * k4 + 3], acc1);
+                }
+                store(e0, acc0);
+                store(e1, acc1);
+            }
+            if (todo) {
+                const int e = __ffs(todo) - 1;
                 u64 acc = pack2(0.0f, 0.0f);
 #pragma unroll
                 for (int k4 = 0; k4 < NM / 4; ++k4) {
@@ -463,18 +535,10 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                     acc = fma2(pack2(w4.z, w4.z), p[4 * k4 + 2], acc);
                     acc = fma2(pack2(w4.w, w4.w), p[4 * k4 + 3], acc);
                 }
-                if (r >= rg.x && r <= rg.y) {
-                    float a0, a1;
-                    unpack2(acc, a0, a1);
-                    float *dst = P.pool + (s_off[e] + r * (rg.w - rg.z + 1) + c);
-                    if (c >= rg.z && c <= rg.w) dst[0] = a0;
-                    if (c + 1 >= rg.z && c + 1 <= rg.w) dst[1] = a1;
-                }
+                store(e, acc);
             }
         }
-        // every warp has read s_n (after the barrier above; when the list was not empty, also past a round barrier)
-        if (tid == 0) s_n = 0;
-        __syncthreads();   // list and round tables are rebuilt for the next tile
+        __syncthreads();   // list, round tables and region cache may be rebuilt for the next tile
     }
 }
 
@@ -619,13 +683,14 @@ __device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int la
                         if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(w, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
             }
         }
+        const size_t o = ((size_t)b * NBY + by) * NBX + bx;
+        const u64 gtw = __ldg(P.gtc + o);   // with the corner loads, not behind the arithmetic
         if (!act) continue;
         const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, P.S_h, P.S_w);
         if (bits) {
-            const size_t o = ((size_t)b * NBY + by) * NBX + bx;
             atomicOr(P.unc + o, bits);
             area += __popcll(bits);
-            inter += __popcll(bits & __ldg(P.gtc + o));
+            inter += __popcll(bits & gtw);
         }
     }
 #pragma unroll
@@ -639,33 +704,56 @@ __device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int la
     }
 }
 
+// Work queues of cells_kernel: item i lives in queue i % C_NQ; one counter per queue, 128 bytes apart (atomics on
+// one address serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).
+__device__ __forceinline__ int atom_inc(int *p) {
+    int v;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(C_WARPS * 32) cells_kernel(const __grid_constant__ K3Params P) {
     const int lane = threadIdx.x & 31;
     const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items;
-    int item = 0;
-    if (lane == 0) item = atomicAdd(P.work, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    while (item < total) {
-        int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(P.work, 1);   // in flight while this item is processed
+    int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) % C_NQ, left = C_NQ;   // lane 0: current queue, queues not yet seen empty
+    int j = 0;
+    if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);
+    for (;;) {
+        int item = -1;
+        if (lane == 0) {
+            item = q + C_NQ * j;
+            while (item >= total && --left > 0) {   // this queue is drained: try the next ones
+                q = (q + 1) % C_NQ;
+                item = total;
+                if (*reinterpret_cast<volatile int *>(P.work + q * C_QSTRIDE) * C_NQ + q < total)
+                    item = q + C_NQ * atom_inc(P.work + q * C_QSTRIDE);
+            }
+            if (item >= total) item = -1;
+        }
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item < 0) break;
+        if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);   // next item of this queue: in flight while this one is processed
         if (item < ndet) {
-            const int b = item / P.K;
-            det_item(P, b, item - b * P.K, lane);
+            // detections in rank-major order: the high-score (large) boxes of every image first
+            const int k = item / P.B;
+            det_item(P, item - k * P.B, k, lane);
         } else {
             const int m = item - ndet, b = m / P.m1_items;
             m1_item(P, b, (m - b * P.m1_items) * 32 + lane, lane);
         }
-        item = __shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
 // per-image epilogue: union counters, |G|, Dice / IoU (test_model.py:15-23), optional dense union mask
-__global__ void __launch_bounds__(C_THREADS) finalize_kernel(const __grid_constant__ K3Params P) {
+constexpr int F_THREADS = 1024;
+__global__ void __launch_bounds__(F_THREADS) finalize_kernel(const __grid_constant__ K3Params P) {
+    constexpr int C_THREADS = F_THREADS;   // (this kernel only)
     __shared__ int s_red[(C_THREADS / 32) * 3];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nblk = P.NBY * P.NBX;
     int ui = 0, up = 0, gg = 0;
     const u64 *un = P.unc + (size_t)b * nblk, *gt = P.gtc + (size_t)b * nblk;
+#pragma unroll 4
     for (int q = tid; q < nblk; q += C_THREADS) {
         const u64 u = __ldg(un + q), g = __ldg(gt + q);
         up += __popcll(u); ui += __popcll(u & g);
@@ -749,8 +837,7 @@ static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, 
     return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
 }
 
-int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, bool pdl) {
-    (void)pdl;
+int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts) {
     K3Params P{};
     P.B = p.batch; P.S_h = p.img_h; P.S_w = p.img_w; P.PH = p.proto_h; P.PW = p.proto_w;
     P.K = p.max_det; P.gt_f32 = p.gt_mask_dtype == BT_MASK_F32;
@@ -758,7 +845,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
     P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region; P.scr_off = w.scr_off;
     P.pool = w.pool; P.lm = w.lm; P.gtc = w.gtc; P.unc = w.unc; P.gpart = w.gpart;
-    P.work = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.work = w.work; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
@@ -771,10 +858,13 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     CUtensorMap tm;
     if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 
-    const size_t smem_g = (size_t)8 * (p.img_w / 32 + 1) * sizeof(uint32_t);
-    gt_pack_kernel<<<dim3(P.NBY, p.batch), C_THREADS, smem_g, s>>>(P);
+    if (parts & BT_MASKS_PACK) {
+        const size_t smem_g = (size_t)8 * (p.img_w / 32 + 1) * sizeof(uint32_t);
+        gt_pack_kernel<<<dim3(P.NBY, p.batch), C_THREADS, smem_g, s>>>(P);
+    }
 
-    const size_t smem_a = (size_t)2 * NM * TA_H * TA_W * sizeof(float) + align_up((size_t)p.max_det * sizeof(unsigned short), 16) + 1024;
+    const size_t kc = p.max_det < A_KCACHE ? p.max_det : A_KCACHE;
+    const size_t smem_a = (size_t)NM * TA_H * TA_W * sizeof(float) + kc * 12 + align_up((size_t)p.max_det * sizeof(unsigned short), 16) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
@@ -790,13 +880,15 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
                 return BT_ERR_CUDA;
         }
         if (smem_a > 100 * 1024) return BT_ERR_UNSUPPORTED;
-        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * 3;
-        contract_kernel<<<ntiles < cta_a ? ntiles : cta_a, A_THREADS, smem_a, s>>>(P, tm);
+        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * 4;
+        if (parts & BT_MASKS_CONTRACT) contract_kernel<<<ntiles < cta_a ? ntiles : cta_a, A_THREADS, smem_a, s>>>(P, tm);
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);
         const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
-        cells_kernel<<<(unsigned)(want < cap ? want : cap), C_WARPS * 32, 0, s>>>(P);
+        if (parts & BT_MASKS_CELLS) {
+            cells_kernel<<<(unsigned)(want < cap ? want : cap), C_WARPS * 32, 0, s>>>(P);
+            finalize_kernel<<<p.batch, F_THREADS, 0, s>>>(P);
+        }
     }
-    finalize_kernel<<<p.batch, C_THREADS, 0, s>>>(P);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 

@@ -601,9 +601,6 @@ __global__ void __launch_bounds__(GM_THREADS) match_kernel(const __grid_constant
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = P.max_det;
-    // the mask kernel does not read anything this kernel writes: let it start right away
-    // (programmatic dependent launch; it never waits on this grid)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (P.dt_match == nullptr) return;
     BT_PHASE_INIT();
     // ---- COCOeval.evaluateImg for every (class, area range, IoU threshold)
@@ -736,7 +733,7 @@ __global__ void __launch_bounds__(GM_THREADS) match_kernel(const __grid_constant
     BT_PHASE_MARK(1, 7);   // COCO matching
 }
 
-int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s) {
+int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts) {
     K2Params P{};
     P.N = p.num_anchors; P.nc = p.nc; P.nm = p.nm; P.C = 4 + p.nc + p.nm;
     P.cap = cand_capacity(&p); P.cap_pow2 = next_pow2(P.cap);
@@ -792,9 +789,11 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
             return BT_ERR_CUDA;
         attr_set = true;
     }
-    nms_kernel<<<p.batch, K2_THREADS, smem_a, s>>>(P);
-    coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);
-    if (io.dt_match) match_kernel<<<p.batch, GM_THREADS, smem_b, s>>>(P);
+    if (parts & BT_NMS_SORT_SWEEP) {
+        nms_kernel<<<p.batch, K2_THREADS, smem_a, s>>>(P);
+        coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);
+    }
+    if ((parts & BT_NMS_COCO) && io.dt_match) match_kernel<<<p.batch, GM_THREADS, smem_b, s>>>(P);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
 
