@@ -235,6 +235,49 @@ class PostProcessor:
         return map_preds, map_targets, log_preds, log_gts
 
 
+class Pipeline:
+    """``depth`` independent PostProcessors (own workspace and outputs each) whose captured steps are replayed
+    round-robin on ``depth`` streams: consecutive batches overlap on the GPU, so the NMS of batch i+1 (one CTA per
+    image, most SMs idle) runs under the mask kernels of batch i.  Every step still does all of its work; per-step
+    outputs are read from ``procs[i % depth].out`` after ``join()``; the accumulated counters (cm, seg_cnt4,
+    uni_cnt4) are the sums over the processors (``counters()``)."""
+
+    def __init__(self, cfg: PostConfig, device="cuda:0", depth: int = 2):
+        self.procs = [PostProcessor(cfg, device) for _ in range(depth)]
+        self.device = self.procs[0].device
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self.graphs = []
+        self._i = 0
+
+    def capture(self, *args, **kw):
+        self.graphs = [p.capture(*args, **kw) for p in self.procs]
+        return self
+
+    def fork(self):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+
+    def replay(self):
+        i = self._i % len(self.procs)
+        self._i += 1
+        with torch.cuda.stream(self.streams[i]):
+            self.graphs[i].replay()
+        return self.procs[i]
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def reset_metrics(self):
+        for p in self.procs:
+            p.reset_metrics()
+
+    def counters(self, key):
+        return sum(p.out[key] for p in self.procs)
+
+
 _cached: dict = {}
 
 

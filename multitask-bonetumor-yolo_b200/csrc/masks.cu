@@ -45,14 +45,14 @@ typedef unsigned long long u64;
 
 struct K3Params {
     int B, S_h, S_w, PH, PW, K, gt_f32, NBY, NBX, ntx, nty, m1_items;
-    float bias;
+    float bias, inv_B, inv_m1;
     const float *protos, *proj_weight, *det_coeff;
     const int32_t *det_count, *scr_off;
     const short4 *det_region;
     const void *masks_gt;
     float *pool, *lm;
     u64 *gtc, *unc;
-    int32_t *gpart, *work, *acc, *inst_area, *inst_inter;
+    int32_t *gpart, *work, *done, *acc, *inst_area, *inst_inter;
     long long *seg_cnt4, *uni_cnt4, *seg_img3, *uni_img3;
     float *seg_dice, *seg_iou, *uni_dice, *uni_iou;
     uint8_t *seg_mask, *uni_mask;
@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constan
     const int nyr = y_hi - y_lo;
     if (by == 0) {
         if (tid < 8) P.acc[b * 8 + tid] = 0;
+        if (tid == 8) P.done[b] = 0;
         if (b == 0 && tid >= 32 && tid < 32 + C_NQ) P.work[(tid - 32) * C_QSTRIDE] = 0;
     }
     for (int q = tid; q < 8 * tp; q += C_THREADS) {
@@ -631,7 +632,7 @@ __device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int la
     const int nblk = nbx * nby;
     const int off = __ldg(P.scr_off + (size_t)b * K + k);
     const float inv = 1.0f / (float)nbx;
-    int area = 0, inter = 0;
+    int area = 0, inter = 0, uarea = 0, uinter = 0;   // uarea / uinter: pixels this detection ADDS to the image's union
     for (int i0 = 0; i0 < nblk; i0 += 32) {
         const int i = i0 + lane;
         const bool act = i < nblk;
@@ -688,98 +689,43 @@ __device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int la
         if (!act) continue;
         const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, P.S_h, P.S_w);
         if (bits) {
-            atomicOr(P.unc + o, bits);
+            // the OR is serialised per word in the L2: the bits that were not set before are counted exactly once
+            // over all detections, so the union's counters need no pass over the union afterwards
+            const u64 fresh = bits & ~atomicOr(P.unc + o, bits);
             area += __popcll(bits);
             inter += __popcll(bits & gtw);
+            uarea += __popcll(fresh);
+            uinter += __popcll(fresh & gtw);
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         inter += __shfl_down_sync(0xffffffffu, inter, d);
         area += __shfl_down_sync(0xffffffffu, area, d);
+        uinter += __shfl_down_sync(0xffffffffu, uinter, d);
+        uarea += __shfl_down_sync(0xffffffffu, uarea, d);
     }
     if (lane == 0) {
         if (P.inst_area) P.inst_area[(size_t)b * K + k] = area;
         if (P.inst_inter) P.inst_inter[(size_t)b * K + k] = inter;
+        if (uinter) atomicAdd(&P.acc[b * 8 + 3], uinter);
+        if (uarea) atomicAdd(&P.acc[b * 8 + 4], uarea);
     }
 }
 
-// Work queues of cells_kernel: item i lives in queue i % C_NQ; one counter per queue, 128 bytes apart (atomics on
-// one address serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).
-__device__ __forceinline__ int atom_inc(int *p) {
-    int v;
-    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(C_WARPS * 32) cells_kernel(const __grid_constant__ K3Params P) {
-    const int lane = threadIdx.x & 31;
-    const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items;
-    int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) % C_NQ, left = C_NQ;   // lane 0: current queue, queues not yet seen empty
-    int j = 0;
-    if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);
-    for (;;) {
-        int item = -1;
-        if (lane == 0) {
-            item = q + C_NQ * j;
-            while (item >= total && --left > 0) {   // this queue is drained: try the next ones
-                q = (q + 1) % C_NQ;
-                item = total;
-                if (*reinterpret_cast<volatile int *>(P.work + q * C_QSTRIDE) * C_NQ + q < total)
-                    item = q + C_NQ * atom_inc(P.work + q * C_QSTRIDE);
-            }
-            if (item >= total) item = -1;
-        }
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item < 0) break;
-        if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);   // next item of this queue: in flight while this one is processed
-        if (item < ndet) {
-            // detections in rank-major order: the high-score (large) boxes of every image first
-            const int k = item / P.B;
-            det_item(P, item - k * P.B, k, lane);
-        } else {
-            const int m = item - ndet, b = m / P.m1_items;
-            m1_item(P, b, (m - b * P.m1_items) * 32 + lane, lane);
-        }
-    }
-}
-
-// per-image epilogue: union counters, |G|, Dice / IoU (test_model.py:15-23), optional dense union mask
-constexpr int F_THREADS = 1024;
-__global__ void __launch_bounds__(F_THREADS) finalize_kernel(const __grid_constant__ K3Params P) {
-    constexpr int C_THREADS = F_THREADS;   // (this kernel only)
-    __shared__ int s_red[(C_THREADS / 32) * 3];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nblk = P.NBY * P.NBX;
-    int ui = 0, up = 0, gg = 0;
-    const u64 *un = P.unc + (size_t)b * nblk, *gt = P.gtc + (size_t)b * nblk;
-#pragma unroll 4
-    for (int q = tid; q < nblk; q += C_THREADS) {
-        const u64 u = __ldg(un + q), g = __ldg(gt + q);
-        up += __popcll(u); ui += __popcll(u & g);
-    }
-    for (int q = tid; q < P.NBY; q += C_THREADS) gg += __ldg(P.gpart + b * P.NBY + q);
-    int v3[3] = {ui, up, gg};
+// per-image epilogue by the warp that completes the image: |G|, Dice / IoU (test_model.py:15-23)
+__device__ __forceinline__ void finalize_image(const K3Params &P, int b, int lane) {
+    __threadfence();
+    int gg = 0;
+    for (int q = lane; q < P.NBY; q += 32) gg += __ldcg(P.gpart + b * P.NBY + q);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        int v = v3[i];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-        if (lane == 0) s_red[wid * 3 + i] = v;
-    }
-    __syncthreads();
-    if (tid < 2) {
-        long long s3[3] = {0, 0, 0};
-        for (int w = 0; w < C_THREADS / 32; ++w)
-            for (int i = 0; i < 3; ++i) s3[i] += s_red[w * 3 + i];
-        long long inter, pp;
-        const long long gsum = s3[2];
-        if (tid == 0) { inter = P.acc[b * 8 + 0]; pp = P.acc[b * 8 + 1]; }
-        else { inter = s3[0]; pp = s3[1]; }
+    for (int d = 16; d > 0; d >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, d);
+    if (lane < 2) {
+        const long long inter = __ldcg(P.acc + b * 8 + 3 * lane), pp = __ldcg(P.acc + b * 8 + 3 * lane + 1), gsum = gg;
         const long long total = (long long)P.S_h * P.S_w;
-        long long *img3 = tid ? P.uni_img3 : P.seg_img3;
-        long long *cnt4 = tid ? P.uni_cnt4 : P.seg_cnt4;
-        float *dice = tid ? P.uni_dice : P.seg_dice, *iou = tid ? P.uni_iou : P.seg_iou;
+        long long *img3 = lane ? P.uni_img3 : P.seg_img3;
+        long long *cnt4 = lane ? P.uni_cnt4 : P.seg_cnt4;
+        float *dice = lane ? P.uni_dice : P.seg_dice, *iou = lane ? P.uni_iou : P.seg_iou;
         if (img3) { img3[b * 3 + 0] = inter; img3[b * 3 + 1] = pp; img3[b * 3 + 2] = gsum; }
         if (cnt4) {
             atomicAdd((unsigned long long *)&cnt4[0], (unsigned long long)inter);
@@ -791,24 +737,81 @@ __global__ void __launch_bounds__(F_THREADS) finalize_kernel(const __grid_consta
         if (iou) iou[b] = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
         if (dice) dice[b] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gsum), 1e-7f));
     }
-    if (P.uni_mask) {
-        // union words -> bytes: thread = (output row, block), 8 pixels of that row (6 in block column 0)
-        const int S_h = P.S_h, S_w = P.S_w;
-        for (int q = tid; q < S_h * P.NBX; q += C_THREADS) {
-            const int y = q / P.NBX, bx = q - y * P.NBX;
-            const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
-            const int by = (ci + 1) >> 1, a = (ci + 1) & 1;
-            const u64 w = __ldg(un + (size_t)by * P.NBX + bx);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int cj = 2 * bx - 1 + c;
-                if (cj > P.PW - 1) continue;
-                const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                const unsigned nib = (unsigned)(w >> (16 * (2 * a + c) + 4 * ry)) & 0xfu;
-                uint8_t *o = P.uni_mask + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
-                *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
-                if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
+}
+
+__device__ __forceinline__ int atom_inc(int *p) {
+    int v;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Work queues: item i lives in queue i % C_NQ; one counter per queue, 128 bytes apart (atomics on one address
+// serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).
+__global__ void __launch_bounds__(C_WARPS * 32, 7) cells_kernel(const __grid_constant__ K3Params P) {
+    const int lane = threadIdx.x & 31;
+    const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items, per_image = P.K + P.m1_items;
+    int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (C_NQ - 1), left = C_NQ;   // lane 0: current queue, queues not yet seen empty
+    int j = 0;
+    if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);
+    for (;;) {
+        int item = -1;
+        if (lane == 0) {
+            item = q + C_NQ * j;
+            while (item >= total && --left > 0) {   // this queue is drained: try the next ones
+                q = (q + 1) & (C_NQ - 1);
+                item = total;
+                if (*reinterpret_cast<volatile int *>(P.work + q * C_QSTRIDE) * C_NQ + q < total)
+                    item = q + C_NQ * atom_inc(P.work + q * C_QSTRIDE);
             }
+            if (item >= total) item = -1;
+        }
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item < 0) break;
+        if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);   // next item of this queue: in flight while this one is processed
+        int b;
+        if (item < ndet) {
+            // detections in rank-major order: the high-score (large) boxes of every image first
+            int k = __float2int_rz(((float)item + 0.5f) * P.inv_B);
+            b = item - k * P.B;
+            if (b < 0) { --k; b += P.B; } else if (b >= P.B) { ++k; b -= P.B; }
+            det_item(P, b, k, lane);
+        } else {
+            const int m = item - ndet;
+            b = __float2int_rz(((float)m + 0.5f) * P.inv_m1);
+            int c = m - b * P.m1_items;
+            if (c < 0) { --b; c += P.m1_items; } else if (c >= P.m1_items) { ++b; c -= P.m1_items; }
+            m1_item(P, b, c * 32 + lane, lane);
+        }
+        // ---- the warp that completes an image folds its counters (every item's atomics precede its arrival)
+        int last = 0;
+        if (lane == 0) {
+            __threadfence();
+            last = (atomicAdd(P.done + b, 1) + 1 == per_image);
+        }
+        if (__shfl_sync(0xffffffffu, last, 0)) finalize_image(P, b, lane);
+    }
+}
+
+// optional dense output: union words -> bytes
+__global__ void __launch_bounds__(C_THREADS) union_dense_kernel(const __grid_constant__ K3Params P) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const u64 *un = P.unc + (size_t)b * P.NBY * P.NBX;
+    const int S_h = P.S_h, S_w = P.S_w;
+    // thread = (output row, block), 8 pixels of that row (6 in block column 0)
+    for (int q = tid; q < S_h * P.NBX; q += C_THREADS) {
+        const int y = q / P.NBX, bx = q - y * P.NBX;
+        const int ci = (y < 2) ? -1 : (y - 2) >> 2, ry = (y < 2) ? y : (y - 2) & 3;
+        const int by = (ci + 1) >> 1, a = (ci + 1) & 1;
+        const u64 w = __ldg(un + (size_t)by * P.NBX + bx);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int cj = 2 * bx - 1 + c;
+            if (cj > P.PW - 1) continue;
+            const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+            const unsigned nib = (unsigned)(w >> (16 * (2 * a + c) + 4 * ry)) & 0xfu;
+            uint8_t *o = P.uni_mask + ((size_t)b * S_h + y) * S_w + xbase;   // 2-byte aligned
+            *reinterpret_cast<uchar2 *>(o) = make_uchar2(nib & 1u, (nib >> 1) & 1u);
+            if (nrx == 4) *reinterpret_cast<uchar2 *>(o + 2) = make_uchar2((nib >> 2) & 1u, (nib >> 3) & 1u);
         }
     }
 }
@@ -845,7 +848,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
     P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region; P.scr_off = w.scr_off;
     P.pool = w.pool; P.lm = w.lm; P.gtc = w.gtc; P.unc = w.unc; P.gpart = w.gpart;
-    P.work = w.work; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.work = w.work; P.done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
@@ -855,6 +858,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
     P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
     P.m1_items = (P.NBY * P.NBX + 31) / 32;
+    P.inv_B = 1.0f / (float)p.batch; P.inv_m1 = 1.0f / (float)P.m1_items;
     CUtensorMap tm;
     if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 
@@ -886,7 +890,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
         if (parts & BT_MASKS_CELLS) {
             cells_kernel<<<(unsigned)(want < cap ? want : cap), C_WARPS * 32, 0, s>>>(P);
-            finalize_kernel<<<p.batch, F_THREADS, 0, s>>>(P);
+            if (io.uni_mask) union_dense_kernel<<<p.batch, C_THREADS, 0, s>>>(P);
         }
     }
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
