@@ -228,7 +228,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- warm-up; the step is captured once into a CUDA graph (7 kernels per replay)
+    # ---------------- warm-up; the step is captured once into a CUDA graph (8 kernels per replay)
     pipe.capture(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], bias)
     graph = pipe.graphs[0]
     out = pp.out
@@ -359,9 +359,9 @@ def main():
                      "achieved_gbs": ab["total"] * B / (ms / args.steps / 1e3) / 1e9,
                      "frac_of_peak": ab["total"] * B / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
                      "stage_ms": stage_ms, "ms_per_step_one_batch_in_flight": serial_ms},
-        "clocks": clocks, "gpu_launches": 7 * args.steps,
+        "clocks": clocks, "gpu_launches": 8 * args.steps,
         "kernels_per_step": ["gt_pack_kernel", "decode_filter_l2_kernel", "nms_kernel", "coeff_gather_kernel", "match_kernel",
-                             "contract_kernel", "cells_kernel"],
+                             "contract_kernel", "cells_kernel", "finalize_kernel"],
     }
     if e2e:
         line["e2e"] = e2e

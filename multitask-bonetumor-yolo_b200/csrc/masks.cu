@@ -44,7 +44,7 @@ constexpr int C_NQ = 32, C_QSTRIDE = 32;   // work queues of cells_kernel: count
 typedef unsigned long long u64;
 
 struct K3Params {
-    int B, S_h, S_w, PH, PW, K, gt_f32, NBY, NBX, ntx, nty, m1_items;
+    int B, S_h, S_w, PH, PW, K, gt_f32, NBY, NBX, ntx, nty, m1_items, nq;
     float bias, inv_B, inv_m1;
     const float *protos, *proj_weight, *det_coeff;
     const int32_t *det_count, *scr_off;
@@ -713,9 +713,8 @@ __device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int la
     }
 }
 
-// per-image epilogue by the warp that completes the image: |G|, Dice / IoU (test_model.py:15-23)
+// per-image epilogue: |G|, Dice / IoU (test_model.py:15-23)
 __device__ __forceinline__ void finalize_image(const K3Params &P, int b, int lane) {
-    __threadfence();
     int gg = 0;
     for (int q = lane; q < P.NBY; q += 32) gg += __ldcg(P.gpart + b * P.NBY + q);
 #pragma unroll
@@ -745,51 +744,42 @@ __device__ __forceinline__ int atom_inc(int *p) {
     return v;
 }
 
-// Work queues: item i lives in queue i % C_NQ; one counter per queue, 128 bytes apart (atomics on one address
-// serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).
+// Work queues: item i lives in queue i % nq; one counter per queue, 128 bytes apart (atomics on one address
+// serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).  A warp serves its home queue
+// until it is drained and then leaves: every queue holds the same mix of items and has the same number of warps, so
+// they drain together (stealing from the other queues cost a scan of 31 counters per warp at the end).
 __global__ void __launch_bounds__(C_WARPS * 32, 7) cells_kernel(const __grid_constant__ K3Params P) {
     const int lane = threadIdx.x & 31;
-    const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items, per_image = P.K + P.m1_items;
-    int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (C_NQ - 1), left = C_NQ;   // lane 0: current queue, queues not yet seen empty
+    const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items;
+    const int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (P.nq - 1);
+    int *ctr = P.work + q * C_QSTRIDE;
     int j = 0;
-    if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);
+    if (lane == 0) j = atom_inc(ctr);
     for (;;) {
-        int item = -1;
-        if (lane == 0) {
-            item = q + C_NQ * j;
-            while (item >= total && --left > 0) {   // this queue is drained: try the next ones
-                q = (q + 1) & (C_NQ - 1);
-                item = total;
-                if (*reinterpret_cast<volatile int *>(P.work + q * C_QSTRIDE) * C_NQ + q < total)
-                    item = q + C_NQ * atom_inc(P.work + q * C_QSTRIDE);
-            }
-            if (item >= total) item = -1;
-        }
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item < 0) break;
-        if (lane == 0) j = atom_inc(P.work + q * C_QSTRIDE);   // next item of this queue: in flight while this one is processed
-        int b;
+        const int item = __shfl_sync(0xffffffffu, q + P.nq * j, 0);
+        if (item >= total) break;
+        if (lane == 0) j = atom_inc(ctr);   // next item of the queue: in flight while this one is processed
         if (item < ndet) {
             // detections in rank-major order: the high-score (large) boxes of every image first
             int k = __float2int_rz(((float)item + 0.5f) * P.inv_B);
-            b = item - k * P.B;
+            int b = item - k * P.B;
             if (b < 0) { --k; b += P.B; } else if (b >= P.B) { ++k; b -= P.B; }
             det_item(P, b, k, lane);
         } else {
             const int m = item - ndet;
-            b = __float2int_rz(((float)m + 0.5f) * P.inv_m1);
+            int b = __float2int_rz(((float)m + 0.5f) * P.inv_m1);
             int c = m - b * P.m1_items;
             if (c < 0) { --b; c += P.m1_items; } else if (c >= P.m1_items) { ++b; c -= P.m1_items; }
             m1_item(P, b, c * 32 + lane, lane);
         }
-        // ---- the warp that completes an image folds its counters (every item's atomics precede its arrival)
-        int last = 0;
-        if (lane == 0) {
-            __threadfence();
-            last = (atomicAdd(P.done + b, 1) + 1 == per_image);
-        }
-        if (__shfl_sync(0xffffffffu, last, 0)) finalize_image(P, b, lane);
     }
+}
+
+// per-image epilogue, one warp per image: |G|, Dice / IoU (test_model.py:15-23)
+__global__ void __launch_bounds__(C_THREADS) finalize_kernel(const __grid_constant__ K3Params P) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (C_THREADS / 32) + (threadIdx.x >> 5);
+    if (b < P.B) finalize_image(P, b, lane);
 }
 
 // optional dense output: union words -> bytes
@@ -889,7 +879,11 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);
         const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
         if (parts & BT_MASKS_CELLS) {
-            cells_kernel<<<(unsigned)(want < cap ? want : cap), C_WARPS * 32, 0, s>>>(P);
+            const long long ctas = want < cap ? want : cap;
+            P.nq = 1;   // queues: a power of two <= warps in the grid (every queue needs a home warp), at most C_NQ
+            while (P.nq * 2 <= C_NQ && P.nq * 2 <= ctas * C_WARPS) P.nq *= 2;
+            cells_kernel<<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            finalize_kernel<<<(p.batch + C_THREADS / 32 - 1) / (C_THREADS / 32), C_THREADS, 0, s>>>(P);
             if (io.uni_mask) union_dense_kernel<<<p.batch, C_THREADS, 0, s>>>(P);
         }
     }
