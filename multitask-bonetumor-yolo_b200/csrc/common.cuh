@@ -64,6 +64,9 @@ struct Workspace {
     int32_t *gpart;       // [B, NBY] GT pixels per row of cell blocks
     unsigned long long *gtc, *unc;   // [B, NBY, NBX] GT / union-of-instance-masks bits per 2x2 block of cells
     float *lm;            // [B, PH, PW] projector logits at prototype resolution
+    int2 *items;          // [item_cap] work items of cells_kernel: (image * K + detection, chunk of C_CHUNK blocks)
+    int32_t *n_items;     // [1]
+    long long item_cap;
     float *pool;          // [pool_cap] logits of the detections' crop boxes, back to back
     long long pool_cap;
     size_t bytes;
@@ -85,6 +88,14 @@ static inline long long mask_pool_floats(const BtParams *p) {
     long long v = (long long)p->batch * 16 * p->proto_h * p->proto_w;
     const long long full = (long long)p->batch * p->max_det * p->proto_h * p->proto_w;
     if (v > full) v = full;
+    return v > 0x7fffff00ll ? 0x7fffff00ll : v;
+}
+
+// cells_kernel works on chunks of C_CHUNK 2x2 cell blocks of one detection's crop box
+constexpr int C_CHUNK = 128;
+static inline long long mask_item_cap(const BtParams *p) {
+    const long long per_det = ((long long)mask_blocks(p->proto_h) * mask_blocks(p->proto_w) + C_CHUNK - 1) / C_CHUNK;
+    const long long v = (long long)p->batch * p->max_det * per_det;
     return v > 0x7fffff00ll ? 0x7fffff00ll : v;
 }
 
@@ -123,6 +134,9 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.gtc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
     w.unc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
     w.lm = reinterpret_cast<float *>(take(B * (size_t)p->proto_h * p->proto_w * sizeof(float)));
+    w.item_cap = mask_item_cap(p);
+    w.items = reinterpret_cast<int2 *>(take((size_t)w.item_cap * sizeof(int2)));
+    w.n_items = reinterpret_cast<int32_t *>(take(sizeof(int32_t)));
     w.pool_cap = mask_pool_floats(p);
     w.pool = reinterpret_cast<float *>(take((size_t)w.pool_cap * sizeof(float)));
     w.bytes = off;

@@ -39,20 +39,24 @@ constexpr int TA_W = 32, TA_H = 8;      // contract_kernel tile (prototype pixel
 constexpr int A_THREADS = 128;          // 4 warps, each an 8 x 8 pixel block, 2 pixels per thread
 constexpr int A_LCAP = 32;              // detections staged per round
 constexpr int C_THREADS = 256;
+constexpr int G_THREADS = 96;   // gt_pack_kernel: 160 row words, then 81 blocks per CTA at 640^2
 constexpr int C_NQ = 32, C_QSTRIDE = 32;   // work queues of cells_kernel: counters 128 bytes apart
 
 typedef unsigned long long u64;
 
 struct K3Params {
     int B, S_h, S_w, PH, PW, K, gt_f32, NBY, NBX, ntx, nty, m1_items, nq;
-    float bias, inv_B, inv_m1;
+    float bias, inv_K, inv_m1;
+    const int2 *items;      // plan of the cells kernel: (image * K + detection, chunk)
+    const int32_t *n_items;
+    int item_cap;
     const float *protos, *proj_weight, *det_coeff;
     const int32_t *det_count, *scr_off;
     const short4 *det_region;
     const void *masks_gt;
     float *pool, *lm;
     u64 *gtc, *unc;
-    int32_t *gpart, *work, *done, *acc, *inst_area, *inst_inter;
+    int32_t *gpart, *work, *acc, *inst_area, *inst_inter;
     long long *seg_cnt4, *uni_cnt4, *seg_img3, *uni_img3;
     float *seg_dice, *seg_iou, *uni_dice, *uni_iou;
     uint8_t *seg_mask, *uni_mask;
@@ -263,19 +267,18 @@ __device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
     return bits;
 }
 
-__global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constant__ K3Params P) {
+__global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constant__ K3Params P) {
     extern __shared__ uint32_t s_rows[];   // [8][wpr + 1]
-    __shared__ int s_cnt[C_THREADS / 32];
+    __shared__ int s_cnt[G_THREADS / 32];
     const int by = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int S_h = P.S_h, S_w = P.S_w, wpr = S_w >> 5, tp = wpr + 1;
     const int y_lo = by ? 8 * by - 2 : 0, y_hi = min(8 * by + 6, S_h);   // output rows of the block row
     const int nyr = y_hi - y_lo;
     if (by == 0) {
         if (tid < 8) P.acc[b * 8 + tid] = 0;
-        if (tid == 8) P.done[b] = 0;
         if (b == 0 && tid >= 32 && tid < 32 + C_NQ) P.work[(tid - 32) * C_QSTRIDE] = 0;
     }
-    for (int q = tid; q < 8 * tp; q += C_THREADS) {
+    for (int q = tid; q < 8 * tp; q += G_THREADS) {
         const int yr = q / tp, w = q - yr * tp;
         uint32_t bits = 0;
         if (yr < nyr && w < wpr) {
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constan
     }
     __syncthreads();
     int cnt = 0;
-    for (int bx = tid; bx < P.NBX; bx += C_THREADS) {
+    for (int bx = tid; bx < P.NBX; bx += G_THREADS) {
         u64 word = 0;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(C_THREADS) gt_pack_kernel(const __grid_constan
     __syncthreads();
     if (tid == 0) {
         int v = 0;
-        for (int w = 0; w < C_THREADS / 32; ++w) v += s_cnt[w];
+        for (int w = 0; w < G_THREADS / 32; ++w) v += s_cnt[w];
         P.gpart[b * P.NBY + by] = v;
     }
 }
@@ -623,19 +626,21 @@ __device__ __forceinline__ void m1_item(const K3Params &P, int b, int q, int lan
     }
 }
 
-__device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int lane) {
+// One item of a detection: blocks [chunk * C_CHUNK, (chunk + 1) * C_CHUNK) of its crop box (the plan lists them).
+__device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, int lane) {
     const int PH = P.PH, PW = P.PW, K = P.K, NBX = P.NBX, NBY = P.NBY;
-    const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
-    if (!(rg.x <= rg.y && rg.z <= rg.w)) return;
+    int b = __float2int_rz(((float)bk + 0.5f) * P.inv_K), k = bk - b * K;
+    if (k < 0) { --b; k += K; } else if (k >= K) { ++b; k -= K; }
+    const short4 rg = __ldg(P.det_region + bk);
     const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w, bw = c_hi - c_lo + 1;
     const int by0 = r_lo >> 1, bx0 = c_lo >> 1, nbx = ((c_hi + 1) >> 1) - bx0 + 1, nby = ((r_hi + 1) >> 1) - by0 + 1;
-    const int nblk = nbx * nby;
-    const int off = __ldg(P.scr_off + (size_t)b * K + k);
+    const int nblk = nbx * nby, i_end = min(nblk, (chunk + 1) * C_CHUNK);
+    const int off = __ldg(P.scr_off + bk);
     const float inv = 1.0f / (float)nbx;
     int area = 0, inter = 0, uarea = 0, uinter = 0;   // uarea / uinter: pixels this detection ADDS to the image's union
-    for (int i0 = 0; i0 < nblk; i0 += 32) {
+    for (int i0 = chunk * C_CHUNK; i0 < i_end; i0 += 32) {
         const int i = i0 + lane;
-        const bool act = i < nblk;
+        const bool act = i < i_end;
         int yy = __float2int_rz(((float)i + 0.5f) * inv);
         int xx = i - yy * nbx;
         if (xx < 0) { --yy; xx += nbx; } else if (xx >= nbx) { ++yy; xx -= nbx; }
@@ -706,8 +711,9 @@ __device__ __forceinline__ void det_item(const K3Params &P, int b, int k, int la
         uarea += __shfl_down_sync(0xffffffffu, uarea, d);
     }
     if (lane == 0) {
-        if (P.inst_area) P.inst_area[(size_t)b * K + k] = area;
-        if (P.inst_inter) P.inst_inter[(size_t)b * K + k] = inter;
+        // zeroed by the NMS kernel; a detection of several chunks adds up
+        if (P.inst_area && area) atomicAdd(&P.inst_area[bk], area);
+        if (P.inst_inter && inter) atomicAdd(&P.inst_inter[bk], inter);
         if (uinter) atomicAdd(&P.acc[b * 8 + 3], uinter);
         if (uarea) atomicAdd(&P.acc[b * 8 + 4], uarea);
     }
@@ -750,7 +756,7 @@ __device__ __forceinline__ int atom_inc(int *p) {
 // they drain together (stealing from the other queues cost a scan of 31 counters per warp at the end).
 __global__ void __launch_bounds__(C_WARPS * 32, 7) cells_kernel(const __grid_constant__ K3Params P) {
     const int lane = threadIdx.x & 31;
-    const int ndet = P.B * P.K, total = ndet + P.B * P.m1_items;
+    const int ndet = min(__ldg(P.n_items), P.item_cap), total = ndet + P.B * P.m1_items;
     const int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (P.nq - 1);
     int *ctr = P.work + q * C_QSTRIDE;
     int j = 0;
@@ -760,11 +766,8 @@ __global__ void __launch_bounds__(C_WARPS * 32, 7) cells_kernel(const __grid_con
         if (item >= total) break;
         if (lane == 0) j = atom_inc(ctr);   // next item of the queue: in flight while this one is processed
         if (item < ndet) {
-            // detections in rank-major order: the high-score (large) boxes of every image first
-            int k = __float2int_rz(((float)item + 0.5f) * P.inv_B);
-            int b = item - k * P.B;
-            if (b < 0) { --k; b += P.B; } else if (b >= P.B) { ++k; b -= P.B; }
-            det_item(P, b, k, lane);
+            const int2 it = __ldg(P.items + item);
+            det_item(P, it.x, it.y, lane);
         } else {
             const int m = item - ndet;
             int b = __float2int_rz(((float)m + 0.5f) * P.inv_m1);
@@ -838,7 +841,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
     P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region; P.scr_off = w.scr_off;
     P.pool = w.pool; P.lm = w.lm; P.gtc = w.gtc; P.unc = w.unc; P.gpart = w.gpart;
-    P.work = w.work; P.done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.work = w.work; P.acc = w.acc; P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
@@ -848,13 +851,13 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
     P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
     P.m1_items = (P.NBY * P.NBX + 31) / 32;
-    P.inv_B = 1.0f / (float)p.batch; P.inv_m1 = 1.0f / (float)P.m1_items;
+    P.inv_K = 1.0f / (float)p.max_det; P.inv_m1 = 1.0f / (float)P.m1_items;
     CUtensorMap tm;
     if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 
     if (parts & BT_MASKS_PACK) {
         const size_t smem_g = (size_t)8 * (p.img_w / 32 + 1) * sizeof(uint32_t);
-        gt_pack_kernel<<<dim3(P.NBY, p.batch), C_THREADS, smem_g, s>>>(P);
+        gt_pack_kernel<<<dim3(P.NBY, p.batch), G_THREADS, smem_g, s>>>(P);
     }
 
     const size_t kc = p.max_det < A_KCACHE ? p.max_det : A_KCACHE;
@@ -876,7 +879,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         if (smem_a > 100 * 1024) return BT_ERR_UNSUPPORTED;
         const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * 4;
         if (parts & BT_MASKS_CONTRACT) contract_kernel<<<ntiles < cta_a ? ntiles : cta_a, A_THREADS, smem_a, s>>>(P, tm);
-        const long long items = (long long)p.batch * (p.max_det + P.m1_items);
+        const long long items = (long long)p.batch * (p.max_det + P.m1_items);   // grid sizing only: the kernel reads the real count
         const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
         if (parts & BT_MASKS_CELLS) {
             const long long ctas = want < cap ? want : cap;

@@ -128,6 +128,7 @@ struct K2Params {
     int region0_bytes;    // shared region 0: list of candidate indices in NMS order
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
     int32_t *scr_off; unsigned long long *pool_used; long long pool_cap;   // logit-pool plan of the mask stage
+    int2 *items; int32_t *n_items; int item_cap;                            // work items of cells_kernel
     int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
     int gx, gy; float inv_cw, inv_ch;   // centre-cell grid
     int coco_smem_doubles;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
     if (tid < 8) P.acc[b * 8 + tid] = 0;
     if (tid == 8) P.strip_done[b] = 0;
     if (tid == 10 && b == 0) *P.pool_used = 0ull;
+    if (tid == 11 && b == 0) *P.n_items = 0;
     if (tid == 9 && P.seg_prob_sum) P.seg_prob_sum[b] = 0.0;
     for (int i = tid; i < K; i += K2_THREADS) {
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
@@ -552,12 +554,16 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
     const int tid = threadIdx.x;
     const int per = (K + GM_THREADS - 1) / GM_THREADS;
     const short4 *reg = P.det_region + (size_t)b * K;
-    int mine = 0;
+    auto chunks_of = [](const short4 &rg) {   // 2x2 cell blocks under the crop box, in chunks of C_CHUNK
+        const int nb = (((rg.w + 1) >> 1) - (rg.z >> 1) + 1) * (((rg.y + 1) >> 1) - (rg.x >> 1) + 1);
+        return (nb + C_CHUNK - 1) / C_CHUNK;
+    };
+    int mine = 0, mych = 0;
     for (int i = 0; i < per; ++i) {
         const int kk = tid * per + i;
         if (kk < K) {
             const short4 rg = reg[kk];
-            if (rg.x <= rg.y && rg.z <= rg.w) mine += (rg.y - rg.x + 1) * (rg.w - rg.z + 1);
+            if (rg.x <= rg.y && rg.z <= rg.w) { mine += (rg.y - rg.x + 1) * (rg.w - rg.z + 1); mych += chunks_of(rg); }
         }
     }
     // a full-image box is < 2^16 * 2^16; the running sum is kept in 64 bits only across warps
@@ -567,15 +573,27 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
         const long long u = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += u;
     }
+    int cincl = mych;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, cincl, d);
+        if (lane >= d) cincl += u;
+    }
     __shared__ long long s_wtot[GM_THREADS / 32];
-    if (lane == 31) s_wtot[wid] = incl;
+    __shared__ int s_ctot[GM_THREADS / 32], s_ibase;
+    if (lane == 31) { s_wtot[wid] = incl; s_ctot[wid] = cincl; }
     __syncthreads();
     long long before = 0, total = 0;
-    for (int w = 0; w < GM_THREADS / 32; ++w) { const long long v = s_wtot[w]; if (w < wid) before += v; total += v; }
+    int cbefore = 0, ctotal = 0;
+    for (int w = 0; w < GM_THREADS / 32; ++w) {
+        const long long v = s_wtot[w]; if (w < wid) before += v; total += v;
+        const int c = s_ctot[w]; if (w < wid) cbefore += c; ctotal += c;
+    }
     if (tid == 0) {
         // the counter saturates instead of wrapping: images that find the pool full use no pool at all
         const long long want = total > P.pool_cap ? P.pool_cap : total;
         s_base = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(P.pool_used), (unsigned long long)want);
+        s_ibase = atomicAdd(P.n_items, ctotal);
     }
     __syncthreads();
     long long off = s_base + before + incl - mine;
@@ -590,6 +608,19 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
                 off += area;
             }
             P.scr_off[(size_t)b * K + kk] = o;
+        }
+    }
+    // work items of cells_kernel (any order; the capacity covers every detection at full-image size)
+    int ci = s_ibase + cbefore + cincl - mych;
+    for (int i = 0; i < per; ++i) {
+        const int kk = tid * per + i;
+        if (kk < K) {
+            const short4 rg = reg[kk];
+            if (rg.x <= rg.y && rg.z <= rg.w) {
+                const int nc = chunks_of(rg);
+                for (int c = 0; c < nc; ++c, ++ci)
+                    if (ci < P.item_cap) P.items[ci] = make_int2(b * K + kk, c);
+            }
         }
     }
 }
@@ -763,6 +794,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.ry = (float)((double)p.proto_h / (double)p.img_h);
     P.det_region = w.det_region;
     P.scr_off = w.scr_off; P.pool_used = w.pool_used; P.pool_cap = w.pool_cap;
+    P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap;
     // centre-cell grid: cells of >= 64 px, at most 16 x 16
     P.gx = p.img_w / 64 < 1 ? 1 : (p.img_w / 64 > 16 ? 16 : p.img_w / 64);
     P.gy = p.img_h / 64 < 1 ? 1 : (p.img_h / 64 > 16 ? 16 : p.img_h / 64);
