@@ -64,6 +64,8 @@ struct Workspace {
     int32_t *gpart;       // [B, NBY] GT pixels per row of cell blocks
     unsigned long long *gtc, *unc;   // [B, NBY, NBX] GT / union-of-instance-masks bits per 2x2 block of cells
     float *lm;            // [B, PH, PW] projector logits at prototype resolution
+    int32_t *tile_cnt;    // [B, tiles] detections listed on each contract_kernel tile
+    unsigned short *tile_list;   // [B, tiles, K]
     int2 *items;          // [item_cap] work items of cells_kernel: (image * K + detection, chunk of C_CHUNK blocks)
     int32_t *n_items;     // [1]
     long long item_cap;
@@ -90,6 +92,11 @@ static inline long long mask_pool_floats(const BtParams *p) {
     if (v > full) v = full;
     return v > 0x7fffff00ll ? 0x7fffff00ll : v;
 }
+
+// contract_kernel tile (prototype pixels); the plan bins every detection into the tiles its crop box touches
+constexpr int TA_W = 32, TA_H = 8;
+constexpr int PLAN_MAX_TILES = 4096;
+static inline int mask_tiles(const BtParams *p) { return ((p->proto_w + TA_W - 1) / TA_W) * ((p->proto_h + TA_H - 1) / TA_H); }
 
 // cells_kernel works on chunks of C_CHUNK 2x2 cell blocks of one detection's crop box
 constexpr int C_CHUNK = 128;
@@ -134,6 +141,8 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.gtc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
     w.unc = reinterpret_cast<unsigned long long *>(take(B * nby * nbx * 8));
     w.lm = reinterpret_cast<float *>(take(B * (size_t)p->proto_h * p->proto_w * sizeof(float)));
+    w.tile_cnt = reinterpret_cast<int32_t *>(take(B * (size_t)mask_tiles(p) * sizeof(int32_t)));
+    w.tile_list = reinterpret_cast<unsigned short *>(take(B * (size_t)mask_tiles(p) * p->max_det * sizeof(unsigned short)));
     w.item_cap = mask_item_cap(p);
     w.items = reinterpret_cast<int2 *>(take((size_t)w.item_cap * sizeof(int2)));
     w.n_items = reinterpret_cast<int32_t *>(take(sizeof(int32_t)));

@@ -35,7 +35,6 @@
 namespace bt {
 
 constexpr int NM = 32;
-constexpr int TA_W = 32, TA_H = 8;      // contract_kernel tile (prototype pixels)
 constexpr int A_THREADS = 128;          // 4 warps, each an 8 x 8 pixel block, 2 pixels per thread
 constexpr int A_LCAP = 32;              // detections staged per round
 constexpr int C_THREADS = 256;
@@ -51,7 +50,8 @@ struct K3Params {
     const int32_t *n_items;
     int item_cap;
     const float *protos, *proj_weight, *det_coeff;
-    const int32_t *det_count, *scr_off;
+    const int32_t *det_count, *scr_off, *tile_cnt;
+    const unsigned short *tile_list;
     const short4 *det_region;
     const void *masks_gt;
     float *pool, *lm;
@@ -303,6 +303,20 @@ __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constan
     int cnt = 0;
     for (int bx = tid; bx < P.NBX; bx += G_THREADS) {
         u64 word = 0;
+        if (by > 0 && bx > 0 && 2 * by < P.PH - 1 && 2 * bx < P.PW - 1) {
+            // interior block: 8 output rows x 8 pixels starting at (8by-2, 8bx-2), one funnel shift per row
+            const int xb = 8 * bx - 2;
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const uint32_t *row = s_rows + rr * tp + (xb >> 5);
+                const unsigned g8 = __funnelshift_r(row[0], row[1], xb & 31) & 0xffu;
+                // pixels 0-3 -> cell column A, 4-7 -> cell column B; rows 0-3 -> cell row A, 4-7 -> cell row B
+                const unsigned two = (g8 & 0xfu) | ((g8 & 0xf0u) << 12);
+                if (rr < 4) lo |= two << (4 * rr); else hi |= two << (4 * (rr - 4));
+            }
+            word = ((u64)hi << 32) | lo;
+        } else
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const int ci = 2 * by - 1 + a;
@@ -341,30 +355,23 @@ __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constan
 // =================================================================================================
 // contract_kernel: one pass over the prototypes
 // =================================================================================================
-constexpr int A_KCACHE = 1024;   // detections of an image whose crop regions / pool offsets are cached in shared memory
-
 __global__ void __launch_bounds__(A_THREADS, 4)
 contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
-    // the swizzled TMA destinations must be 1024-byte aligned: align by hand (1024 spare bytes are allocated)
+    // the swizzled TMA destination must be 1024-byte aligned: align by hand (1024 spare bytes are allocated)
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     constexpr int TILE_FLOATS = NM * TA_H * TA_W;
     float *s_tile = reinterpret_cast<float *>(smem);                                   // [NM][TA_H][TA_W], 16-byte chunks XOR row
-    const int KC = min(P.K, A_KCACHE);
-    short4 *s_creg = reinterpret_cast<short4 *>(smem + TILE_FLOATS * 4);           // [KC] crop regions of the current image
-    int *s_coff = reinterpret_cast<int *>(s_creg + KC);                                // [KC] pool offsets
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_coff + KC);          // [K] detections listed on the tile
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) float s_cf[A_LCAP][NM];
     __shared__ short4 s_reg[A_LCAP];
     __shared__ int s_off[A_LCAP];        // pool offset of the box origin minus (r_lo * bw + c_lo): + r * bw + c addresses a pixel
     __shared__ __align__(16) float s_w[NM];
-    __shared__ int s_n;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tiles = P.ntx * P.nty, total = tiles * P.B;
     const int PH = P.PH, PW = P.PW, K = P.K;
-    // this CTA's contiguous range of tiles (mostly one image: its regions are cached once)
+    // this CTA's contiguous range of tiles
     const int t_begin = (int)(((long long)blockIdx.x * total) / gridDim.x), t_end = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
     if (t_begin >= t_end) return;
 
@@ -379,9 +386,9 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         issue(t_begin);
-        s_n = 0;
     }
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
+    __syncthreads();
 
     // this thread's two pixels: rows {0,2,4,6} in lanes 0-15 and {1,3,5,7} in lanes 16-31 keep the 8-byte shared
     // loads of the swizzled tile free of bank conflicts
@@ -389,56 +396,41 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     const int row = 2 * (i16 >> 2) + (lane >> 4), colp = (wid << 3) + 2 * (i16 & 3);   // tile-local row / first column
     const int soff = row * TA_W + (((colp >> 2) ^ row) << 2) + (colp & 3);
 
-    int cur_b = -1, n = 0;
+    // The tile's detections were binned by the plan (coeff_gather_kernel).  List length and the list entries this
+    // thread needs for the first round are fetched one tile ahead, so that a tile starts with ONE round of
+    // independent loads (coefficients, regions, pool offsets) that travel under the tile wait and the projection.
+    struct Meta { int nlist, kq0, kq1, k0; };
+    auto fetch_meta = [&](int tile) {
+        Meta m;
+        m.nlist = min(__ldg(P.tile_cnt + tile), K);
+        const unsigned short *list = P.tile_list + (size_t)tile * K;
+        const int nch0 = min(A_LCAP, m.nlist);
+        m.kq0 = (tid < nch0 * (NM / 4)) ? __ldg(list + (tid >> 3)) : 0;
+        m.kq1 = (tid + A_THREADS < nch0 * (NM / 4)) ? __ldg(list + ((tid + A_THREADS) >> 3)) : 0;
+        m.k0 = (tid < nch0) ? __ldg(list + tid) : 0;
+        return m;
+    };
+    Meta cur = fetch_meta(t_begin);
+
     for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
         const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
         const int R0 = ty * TA_H, C0 = tx * TA_W;
         const int r = R0 + row, c = C0 + colp;
 
-        if (b != cur_b) {
-            // new image: its crop regions and pool offsets -> shared memory (detections without pool room are dropped here)
-            cur_b = b;
-            n = min(__ldg(P.det_count + b), K);
-            for (int k = tid; k < min(n, KC); k += A_THREADS) {
-                short4 rg = __ldg(P.det_region + (size_t)b * K + k);
-                const int off = __ldg(P.scr_off + (size_t)b * K + k);
-                if (off < 0) rg = make_short4(1, 0, 1, 0);
-                s_creg[k] = rg; s_coff[k] = off;
-            }
-        }
-        __syncthreads();   // region cache (and, first tile, the barriers / projector weights)
-
-        // ---- detections whose crop box touches the tile (any order: every (detection, pixel) logit is independent)
-        for (int k0 = 0; k0 < n; k0 += A_THREADS) {
-            const int k = k0 + tid;
-            bool ok = false;
-            if (k < n) {
-                short4 rg;
-                if (k < KC) rg = s_creg[k];
-                else {
-                    rg = __ldg(P.det_region + (size_t)b * K + k);
-                    if (__ldg(P.scr_off + (size_t)b * K + k) < 0) rg = make_short4(1, 0, 1, 0);
-                }
-                ok = rg.x <= rg.y && rg.z <= rg.w && rg.x <= R0 + TA_H - 1 && rg.y >= R0 && rg.z <= C0 + TA_W - 1 && rg.w >= C0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (ok) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-        }
-        __syncthreads();
-        const int nlist = s_n;
-
-        // ---- first round's coefficients: global loads in flight under the tile wait and the projection
+        const int nlist = cur.nlist;
+        const unsigned short *list = P.tile_list + (size_t)tile * K;
         const int nch0 = min(A_LCAP, nlist);
         float4 cfr[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int q = tid + j * A_THREADS;
-            if (q < nch0 * (NM / 4))
-                cfr[j] = __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + s_list[q >> 3]) * NM) + (q & 7));
+        if (tid < nch0 * (NM / 4)) cfr[0] = __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + cur.kq0) * NM) + (tid & 7));
+        if (tid + A_THREADS < nch0 * (NM / 4))
+            cfr[1] = __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + cur.kq1) * NM) + (tid & 7));
+        short4 rg0 = make_short4(1, 0, 1, 0);
+        int off0 = 0;
+        if (tid < nch0) {
+            rg0 = __ldg(P.det_region + (size_t)b * K + cur.k0);
+            off0 = __ldg(P.scr_off + (size_t)b * K + cur.k0);
         }
+        if (tile + 1 < t_end) cur = fetch_meta(tile + 1);
 
         // ---- the tile: shared memory -> registers, then the buffer is free for the next tile
         mbar_wait(&s_bar, (uint32_t)(it & 1));
@@ -449,10 +441,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
             for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
         }
         __syncthreads();
-        if (tid == 0) {
-            if (tile + 1 < t_end) issue(tile + 1);
-            s_n = 0;   // every warp has read it (two barriers ago)
-        }
+        if (tid == 0 && tile + 1 < t_end) issue(tile + 1);
 
         // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
         {
@@ -479,19 +468,18 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                     const int q = tid + j * A_THREADS;
                     if (q < nch * (NM / 4)) reinterpret_cast<float4 *>(&s_cf[q >> 3][0])[q & 7] = cfr[j];
                 }
+                if (tid < nch) { s_reg[tid] = rg0; s_off[tid] = off0 - (rg0.x * (rg0.w - rg0.z + 1) + rg0.z); }
             } else {
                 __syncthreads();   // the previous round's tables are still being read
                 for (int q = tid; q < nch * (NM / 4); q += A_THREADS)
                     reinterpret_cast<float4 *>(&s_cf[q >> 3][0])[q & 7] =
-                        __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + s_list[r0 + (q >> 3)]) * NM) + (q & 7));
-            }
-            if (tid < nch) {
-                const int k = s_list[r0 + tid];
-                short4 rg; int off;
-                if (k < KC) { rg = s_creg[k]; off = s_coff[k]; }
-                else { rg = __ldg(P.det_region + (size_t)b * K + k); off = __ldg(P.scr_off + (size_t)b * K + k); }
-                s_reg[tid] = rg;
-                s_off[tid] = off - (rg.x * (rg.w - rg.z + 1) + rg.z);
+                        __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + __ldg(list + r0 + (q >> 3))) * NM) + (q & 7));
+                if (tid < nch) {
+                    const int k = __ldg(list + r0 + tid);
+                    const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
+                    s_reg[tid] = rg;
+                    s_off[tid] = __ldg(P.scr_off + (size_t)b * K + k) - (rg.x * (rg.w - rg.z + 1) + rg.z);
+                }
             }
             __syncthreads();
             // the round's detections that touch this warp's block: one lane tests one detection
@@ -542,7 +530,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                 store(e, acc);
             }
         }
-        __syncthreads();   // list, round tables and region cache may be rebuilt for the next tile
+        if (nlist) __syncthreads();   // the round tables are rewritten for the next tile
     }
 }
 
@@ -841,7 +829,8 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
     P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region; P.scr_off = w.scr_off;
     P.pool = w.pool; P.lm = w.lm; P.gtc = w.gtc; P.unc = w.unc; P.gpart = w.gpart;
-    P.work = w.work; P.acc = w.acc; P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.work = w.work; P.acc = w.acc; P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap;
+    P.tile_cnt = w.tile_cnt; P.tile_list = w.tile_list; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_cnt4 = (long long *)io.seg_cnt4; P.uni_cnt4 = (long long *)io.uni_cnt4;
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
@@ -860,8 +849,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         gt_pack_kernel<<<dim3(P.NBY, p.batch), G_THREADS, smem_g, s>>>(P);
     }
 
-    const size_t kc = p.max_det < A_KCACHE ? p.max_det : A_KCACHE;
-    const size_t smem_a = (size_t)NM * TA_H * TA_W * sizeof(float) + kc * 12 + align_up((size_t)p.max_det * sizeof(unsigned short), 16) + 1024;
+    const size_t smem_a = (size_t)NM * TA_H * TA_W * sizeof(float) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)

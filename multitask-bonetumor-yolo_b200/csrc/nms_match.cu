@@ -129,6 +129,7 @@ struct K2Params {
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
     int32_t *scr_off; unsigned long long *pool_used; long long pool_cap;   // logit-pool plan of the mask stage
     int2 *items; int32_t *n_items; int item_cap;                            // work items of cells_kernel
+    int32_t *tile_cnt; unsigned short *tile_list; int ntiles, ntx;         // tile lists of contract_kernel
     int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
     int gx, gy; float inv_cw, inv_ch;   // centre-cell grid
     int coco_smem_doubles;
@@ -610,6 +611,32 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
             P.scr_off[(size_t)b * K + kk] = o;
         }
     }
+    // tile lists of contract_kernel: every detection with pool room goes into the tiles its crop box touches
+    __shared__ int s_tcnt[PLAN_MAX_TILES];
+    for (int t = tid; t < P.ntiles; t += GM_THREADS) s_tcnt[t] = 0;
+    __syncthreads();
+    {
+        long long off2 = s_base + before + incl - mine;
+        for (int i = 0; i < per; ++i) {
+            const int kk = tid * per + i;
+            if (kk < K) {
+                const short4 rg = reg[kk];
+                if (rg.x <= rg.y && rg.z <= rg.w) {
+                    const long long area = (long long)(rg.y - rg.x + 1) * (rg.w - rg.z + 1);
+                    if (off2 + area <= P.pool_cap) {
+                        for (int ty = rg.x / TA_H; ty <= rg.y / TA_H; ++ty)
+                            for (int tx = rg.z / TA_W; tx <= rg.w / TA_W; ++tx) {
+                                const int t = ty * P.ntx + tx;
+                                P.tile_list[((size_t)b * P.ntiles + t) * K + atomicAdd(&s_tcnt[t], 1)] = (unsigned short)kk;
+                            }
+                    }
+                    off2 += area;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < P.ntiles; t += GM_THREADS) P.tile_cnt[(size_t)b * P.ntiles + t] = s_tcnt[t];
     // work items of cells_kernel (any order; the capacity covers every detection at full-image size)
     int ci = s_ibase + cbefore + cincl - mych;
     for (int i = 0; i < per; ++i) {
@@ -795,6 +822,8 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.det_region = w.det_region;
     P.scr_off = w.scr_off; P.pool_used = w.pool_used; P.pool_cap = w.pool_cap;
     P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap;
+    P.tile_cnt = w.tile_cnt; P.tile_list = w.tile_list; P.ntiles = mask_tiles(&p); P.ntx = (p.proto_w + TA_W - 1) / TA_W;
+    if (P.ntiles > PLAN_MAX_TILES) return BT_ERR_UNSUPPORTED;
     // centre-cell grid: cells of >= 64 px, at most 16 x 16
     P.gx = p.img_w / 64 < 1 ? 1 : (p.img_w / 64 > 16 ? 16 : p.img_w / 64);
     P.gy = p.img_h / 64 < 1 ? 1 : (p.img_h / 64 > 16 ? 16 : p.img_h / 64);
