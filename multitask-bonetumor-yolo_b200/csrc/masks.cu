@@ -355,14 +355,15 @@ __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constan
 // =================================================================================================
 // contract_kernel: one pass over the prototypes
 // =================================================================================================
-__global__ void __launch_bounds__(A_THREADS, 4)
+template <int NBUF, int MINB>
+__global__ void __launch_bounds__(A_THREADS, MINB)
 contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destination must be 1024-byte aligned: align by hand (1024 spare bytes are allocated)
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     constexpr int TILE_FLOATS = NM * TA_H * TA_W;
-    float *s_tile = reinterpret_cast<float *>(smem);                                   // [NM][TA_H][TA_W], 16-byte chunks XOR row
-    __shared__ __align__(8) uint64_t s_bar;
+    float *s_tiles = reinterpret_cast<float *>(smem);                                  // [NBUF][NM][TA_H][TA_W], 16-byte chunks XOR row
+    __shared__ __align__(8) uint64_t s_bar[NBUF];
     __shared__ __align__(16) float s_cf[A_LCAP][NM];
     __shared__ short4 s_reg[A_LCAP];
     __shared__ int s_off[A_LCAP];        // pool offset of the box origin minus (r_lo * bw + c_lo): + r * bw + c addresses a pixel
@@ -377,15 +378,16 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
 
     // The tile buffer is dead as soon as every thread holds its pixels in registers: the next tile's TMA is issued
     // right then and lands under this tile's arithmetic (one buffer, four CTAs per SM).
-    auto issue = [&](int tile) {   // thread 0
+    auto issue = [&](int tile, int buf) {   // thread 0
         const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
-        mbar_expect_tx(&s_bar, (uint32_t)(TILE_FLOATS * sizeof(float)));
-        tma_tile_g2s(s_tile, &tmap, tx * TA_W, ty * TA_H, b * NM, &s_bar);
+        mbar_expect_tx(&s_bar[buf], (uint32_t)(TILE_FLOATS * sizeof(float)));
+        tma_tile_g2s(s_tiles + buf * TILE_FLOATS, &tmap, tx * TA_W, ty * TA_H, b * NM, &s_bar[buf]);
     };
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+        for (int i = 0; i < NBUF; ++i) mbar_init(&s_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        issue(t_begin);
+        for (int i = 0; i < NBUF; ++i)
+            if (t_begin + i < t_end) issue(t_begin + i, i);
     }
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
     __syncthreads();
@@ -433,15 +435,16 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         if (tile + 1 < t_end) cur = fetch_meta(tile + 1);
 
         // ---- the tile: shared memory -> registers, then the buffer is free for the next tile
-        mbar_wait(&s_bar, (uint32_t)(it & 1));
+        const int buf = it % NBUF;
+        mbar_wait(&s_bar[buf], (uint32_t)((it / NBUF) & 1));
         u64 p[NM];
         {
-            const float *src = s_tile + soff;
+            const float *src = s_tiles + buf * TILE_FLOATS + soff;
 #pragma unroll
             for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
         }
         __syncthreads();
-        if (tid == 0 && tile + 1 < t_end) issue(tile + 1);
+        if (tid == 0 && tile + NBUF < t_end) issue(tile + NBUF, buf);
 
         // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
         {
@@ -815,8 +818,12 @@ static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, 
     const cuuint64_t gstride[2] = {(cuuint64_t)PW * sizeof(float), (cuuint64_t)PW * PH * sizeof(float)};
     const cuuint32_t box[3] = {(cuuint32_t)TA_W, (cuuint32_t)TA_H, (cuuint32_t)NM};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
+    static const char *pe = getenv("BTPOST_A_PROMO");   // developer switch (scripts/): L2 promotion of the prototype loads
+    const int pv = pe ? atoi(pe) : 0;   // measured: no promotion 47.7 us, 128 B 48.0 us, 256 B 50.5 us
+    const CUtensorMapL2promotion promo = pv == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : pv == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(protos), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
 }
@@ -849,10 +856,14 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         gt_pack_kernel<<<dim3(P.NBY, p.batch), G_THREADS, smem_g, s>>>(P);
     }
 
-    const size_t smem_a = (size_t)NM * TA_H * TA_W * sizeof(float) + 1024;
+    static const char *nb_env = getenv("BTPOST_A_NBUF");   // developer switch (scripts/): tile buffers per CTA
+    const int nbuf = nb_env ? atoi(nb_env) : 1;
+    const size_t smem_a = (size_t)nbuf * NM * TA_H * TA_W * sizeof(float) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(contract_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(contract_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(contract_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
         attr_set = true;
     }
@@ -864,9 +875,13 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
                 cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
                 return BT_ERR_CUDA;
         }
-        if (smem_a > 100 * 1024) return BT_ERR_UNSUPPORTED;
-        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * 4;
-        if (parts & BT_MASKS_CONTRACT) contract_kernel<<<ntiles < cta_a ? ntiles : cta_a, A_THREADS, smem_a, s>>>(P, tm);
+        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * (nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
+        const int grid_a = ntiles < cta_a ? ntiles : cta_a;
+        if (parts & BT_MASKS_CONTRACT) {
+            if (nbuf == 2) contract_kernel<2, 3><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+            else if (nbuf == 3) contract_kernel<3, 2><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+            else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+        }
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);   // grid sizing only: the kernel reads the real count
         const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
         if (parts & BT_MASKS_CELLS) {

@@ -1,4 +1,4 @@
-"""Developer tool: per-phase cycle breakdown of the NMS and mask kernels (debug build, `make dbg`)."""
+"""Developer tool: per-phase cycle breakdown of the NMS kernel (debug build, `make dbg`)."""
 import ctypes as C, os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -22,8 +22,8 @@ n = 10
 for _ in range(n): pp.run(*args)
 torch.cuda.synchronize(); L.btpost_debug_phase_cycles(buf, 1)
 names = {1: {0: "sort", 1: "stage window", 3: "chunks (tail mark)", 8: "chunk A", 12: "A: sum of per-warp max (warps 0-7)", 13: "A: warp-chunks counted", 14: "A: sum per-warp max (idle warps)", 11: "chunk B", 9: "chunk C", 10: "chunk insert", 6: "package", 7: "COCO match (other kernel)"},
-         2: {0: "GT words+tiles", 1: "list+tables | GT cells", 2: "coef + M1 proj", 9: "M1 cells + contraction", 10: "cells", 5: "counters+dense out"}}
-for k, nb in ((1, B), (2, None)):
+         }
+for k, nb in ((1, B),):   # the mask stage is four plain kernels now: time them with bench.py / ncu
     tot = sum(buf[k * 16 + i] for i in range(16))
     print(f"kernel {k}: total cycles/launch {tot / n:.0f}")
     for i in range(16):
