@@ -875,7 +875,8 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
                 cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
                 return BT_ERR_CUDA;
         }
-        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * (nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
+        static const char *ca_env = getenv("BTPOST_A_CTAS"), *cc_env = getenv("BTPOST_C_CTAS");   // developer switches: CTAs per SM
+        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * (ca_env ? atoi(ca_env) : nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
         const int grid_a = ntiles < cta_a ? ntiles : cta_a;
         if (parts & BT_MASKS_CONTRACT) {
             if (nbuf == 2) contract_kernel<2, 3><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
@@ -883,7 +884,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
         }
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);   // grid sizing only: the kernel reads the real count
-        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * 7;
+        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * (cc_env ? atoi(cc_env) : 7);
         if (parts & BT_MASKS_CELLS) {
             const long long ctas = want < cap ? want : cap;
             P.nq = 1;   // queues: a power of two <= warps in the grid (every queue needs a home warp), at most C_NQ
