@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--iou", type=float, default=0.6)
     ap.add_argument("--max-det", dest="max_det", type=int, default=300)
     ap.add_argument("--cpu-sample", type=int, default=8, help="images the cpu_baseline leg times (0 = skip)")
-    ap.add_argument("--pipeline", type=int, default=4,
+    ap.add_argument("--pipeline", type=int, default=6,
                     help="batches in flight: steps are replayed round-robin on this many streams (1 = strictly serial steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period during the timed region (0 = off)")

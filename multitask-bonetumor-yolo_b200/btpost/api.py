@@ -65,6 +65,7 @@ class PostConfig:
     with_coco: bool = True
     with_seg_map: bool = False           # v3 segmentation-mAP prep (score numerator per image)
     num_anchors: int | None = None
+    nms_threads: int = 0                 # 0 = auto; 512 / 1024 force a variant of the NMS kernel
 
 
 class PostProcessor:
@@ -91,6 +92,7 @@ class PostProcessor:
         p.clamp_boxes, p.gt_mode, p.max_gt = int(cfg.clamp_boxes), cfg.gt_mode, cfg.max_gt
         p.iou_match_thresh, p.crop, p.gt_mask_dtype = cfg.iou_match_thresh, int(cfg.crop), cfg.gt_mask_dtype
         p.num_iou_thrs = len(cfg.iou_thrs)
+        p.nms_threads = cfg.nms_threads
         for i, v in enumerate(cfg.iou_thrs):
             p.iou_thrs[i] = v
         self.params = p

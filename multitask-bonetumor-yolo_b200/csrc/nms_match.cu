@@ -39,9 +39,10 @@
 
 namespace bt {
 
-constexpr int K2_THREADS = 1024;
+constexpr int K2_MAX_THREADS = 1024;   // nms_kernel<NT>: NT = 1024 or 512 threads per image
 constexpr int NMS_CHUNK = 64;
 constexpr int SORT_REG_MAX = 16384;  // keys sorted in registers (16 per thread) up to this many
+constexpr int SORT_SMALL_MAX = 4096; // same for the 512-thread variant (8 per thread): its shared memory stays below 80 KB
 constexpr int GM_THREADS = 256;      // match_kernel block
 constexpr int MAX_CELLS = 256;
 
@@ -220,7 +221,8 @@ __device__ __forceinline__ void sort_to_smem(const float *cscore, int M, int nth
 // =================================================================================================
 // fused NMS kernel
 // =================================================================================================
-__global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__ K2Params P) {
+template <int K2_THREADS>
+__global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = P.max_det;
@@ -275,11 +277,15 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
     const unsigned long long *gkeys = nullptr;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        if (M <= 1024) sort_to_smem<1>(cscore, M, 1024, s_x, s_sidx);
-        else if (M <= 2048) sort_to_smem<2>(cscore, M, 1024, s_x, s_sidx);
-        else if (M <= 4096) sort_to_smem<4>(cscore, M, 1024, s_x, s_sidx);
-        else if (M <= 8192) sort_to_smem<16>(cscore, M, 512, s_x, s_sidx);
-        else if (M <= SORT_REG_MAX) sort_to_smem<16>(cscore, M, 1024, s_x, s_sidx);
+        if (K2_THREADS == 512 && M <= 512) sort_to_smem<1>(cscore, M, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M <= 1024) sort_to_smem<2>(cscore, M, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M <= 2048) sort_to_smem<4>(cscore, M, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M <= SORT_SMALL_MAX) sort_to_smem<8>(cscore, M, 512, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M <= 1024) sort_to_smem<1>(cscore, M, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M <= 2048) sort_to_smem<2>(cscore, M, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M <= 4096) sort_to_smem<4>(cscore, M, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M <= 8192) sort_to_smem<16>(cscore, M, 512, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M <= SORT_REG_MAX) sort_to_smem<16>(cscore, M, 1024, s_x, s_sidx);
         else {
             // very long lists (30k-candidate stress case): bitonic network in global memory
             int P2 = 1;
@@ -312,27 +318,27 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
     for (int w0 = 0; w0 < M && nkept < K; w0 += WIN) {
         const int wn = min(WIN, M - w0);
         // (a) stage the window in NMS order; bucket its candidates by the cell of their centre
-        if (tid < wn) {
-            const int idx = gkeys ? (int)(unsigned)gkeys[w0 + tid] : (int)s_sidx[w0 + tid];
+        for (int t = tid; t < wn; t += K2_THREADS) {
+            const int idx = gkeys ? (int)(unsigned)gkeys[w0 + t] : (int)s_sidx[w0 + t];
             float4 bx = __ldg(cbox + idx);
             const int lb = __ldg(clabel + idx);
-            s_sscore[tid] = __ldg(cscore + idx);
-            s_sanchor[tid] = __ldg(canchor + idx);
-            s_sorig[tid] = idx;
+            s_sscore[t] = __ldg(cscore + idx);
+            s_sanchor[t] = __ldg(canchor + idx);
+            s_sorig[t] = idx;
             if (P.class_mode == BT_CLASS_OFFSET) {
                 const float off = __fmul_rn((float)lb, P.max_wh);
                 bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
                 bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
             }
-            s_sbox[tid] = bx;
-            s_sctr[tid] = make_float2(__fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f), __fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f));
+            s_sbox[t] = bx;
+            s_sctr[t] = make_float2(__fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f), __fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f));
             {   // cells under the box: x0 | y0 << 4 | nx << 8 | ny << 13 (nx = 1, ny = 0 for an inverted box)
                 const int gx0 = cell_x(bx.x), gy0 = cell_y(bx.y);
                 const int ncx = max(cell_x(bx.z) - gx0 + 1, 1), ncy = max(cell_y(bx.w) - gy0 + 1, 0);
-                s_scell[tid] = gx0 | (gy0 << 4) | (ncx << 8) | (ncy << 13);
+                s_scell[t] = gx0 | (gy0 << 4) | (ncx << 8) | (ncy << 13);
             }
-            s_sarea[tid] = box_area(bx);
-            s_slabel[tid] = lb;
+            s_sarea[t] = box_area(bx);
+            s_slabel[t] = lb;
         }
         __syncthreads();
         BT_PHASE_MARK(1, 1);   // stage window
@@ -378,18 +384,20 @@ __global__ void __launch_bounds__(K2_THREADS) nms_kernel(const __grid_constant__
                     if ((lane & 3) == 0 && ((m >> lane) & 0xfu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
                 }
             } else {
-                const int ci = tid >> 4, sub = tid & 15;
-                bool f = false;
-                if (ci < n_in) {
-                    const float4 bj = s_sbox[c0 + ci];
-                    const float aj = s_sarea[c0 + ci];
-                    const int lj = s_slabel[c0 + ci];
-                    for (int k = sub; k < nkept && !f; k += 16)
-                        f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
-                                       P.class_mode, 0, 0.0f, 0.0f, P.fast);
+                for (int ci = tid >> 4; ci < NMS_CHUNK; ci += K2_THREADS >> 4) {   // warp-uniform trip count
+                    const int sub = tid & 15;
+                    bool f = false;
+                    if (ci < n_in) {
+                        const float4 bj = s_sbox[c0 + ci];
+                        const float aj = s_sarea[c0 + ci];
+                        const int lj = s_slabel[c0 + ci];
+                        for (int k = sub; k < nkept && !f; k += 16)
+                            f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                           P.class_mode, 0, 0.0f, 0.0f, P.fast);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, f);
+                    if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, f);
-                if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
             }
 #ifdef BT_PHASE_TIMING
             {
@@ -834,7 +842,15 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
 
     // shared memory of nms_kernel: [sorted-index list | window (48 B/candidate) + kept arrays (48 B/slot)];
     // the sort's exchange buffer overlays everything.
-    const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > SORT_REG_MAX ? SORT_REG_MAX : P.cap_pow2);
+    // 512 threads per image (32 k registers, < 80 KB of shared memory) leave room on the SM for CTAs of the mask kernels
+    // of other batches in flight, or for a second image; the 1024-thread variant sorts long candidate lists in
+    // registers (dense configurations: conf_thres < 0.01), the small one falls back to the global-memory network
+    // above 4096 candidates
+    static const char *nt_env = getenv("BTPOST_NMS_NT");
+    const int nt_req = p.nms_threads ? p.nms_threads : nt_env ? atoi(nt_env) : (p.conf_thres < 0.01f ? 1024 : 512);
+    const int nt = nt_req == 512 ? 512 : 1024;
+    const int sort_max = nt == 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
+    const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > sort_max ? sort_max : P.cap_pow2);
     const size_t region0 = align_up((size_t)sort_slots * 4, 16);
     P.region0_bytes = (int)region0;
     size_t smem_a = region0 + (size_t)K2_TAIL_WIN * 48 + (size_t)p.max_det * 48 + 64;
@@ -847,7 +863,8 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     if (smem_b > 220 * 1024) return BT_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+        if (cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(nms_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
         attr_set = true;
@@ -864,12 +881,13 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
             prio = (pe && atoi(pe) != 0) ? hi : 0;   // hi = numerically lowest = highest priority
         }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(p.batch); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = smem_a; cfg.stream = s;
+        cfg.gridDim = dim3(p.batch); cfg.blockDim = dim3(nt == 512 ? 512 : 1024); cfg.dynamicSmemBytes = smem_a; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributePriority;
         at[0].val.priority = prio;
         cfg.attrs = at; cfg.numAttrs = prio != 0 ? 1 : 0;
-        if (cudaLaunchKernelEx(&cfg, nms_kernel, P) != cudaSuccess) return BT_ERR_CUDA;
+        if ((nt == 512 ? cudaLaunchKernelEx(&cfg, nms_kernel<512>, P) : cudaLaunchKernelEx(&cfg, nms_kernel<1024>, P)) != cudaSuccess)
+            return BT_ERR_CUDA;
         coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);
     }
     if ((parts & BT_NMS_COCO) && io.dt_match) match_kernel<<<p.batch, GM_THREADS, smem_b, s>>>(P);

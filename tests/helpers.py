@@ -22,7 +22,7 @@ def run_cuda(batch, dev="cuda:0", gt_f32=False, l1=False, **kw):
                      class_mode=kw.get("class_mode", 0), clamp_boxes=bool(kw.get("clamp", 1)),
                      gt_mode=kw.get("gt_mode", 0), crop=bool(kw.get("crop", 1)),
                      iou_match_thresh=kw.get("iou_match_thresh", 0.5),
-                     gt_mask_dtype=_lib.MASK_F32 if gt_f32 else _lib.MASK_U8,
+                     gt_mask_dtype=_lib.MASK_F32 if gt_f32 else _lib.MASK_U8, nms_threads=kw.get("nms_threads", 0),
                      with_seg_mask=True, with_seg_logits=True, with_uni_mask=True, with_coco=True, with_seg_map=True)
     pp = PostProcessor(cfg, dev)
     d = to_dev(batch, dev, gt_f32)

@@ -20,21 +20,24 @@ pytestmark = pytest.mark.gpu
     dict(conf_thres=0.5, iou_thres=0.3),
     dict(max_cand=500),
     dict(crop=0, max_det=100),                      # every detection on every strip: several rounds / scratch batches
-    dict(max_det=400),                              # more detections than the mask kernel's register cache of regions
+    dict(max_det=400),                              # more detections than fit one round of the contract kernel's tables
+    dict(nms_threads=1024), dict(nms_threads=512, class_mode=1),   # both NMS kernel variants whatever the heuristic picks
 ])
 def test_pipeline_matches_oracle_640(kw):
     batch = helpers.make(batch=2, img_size=640)
-    ref = oracle.run_pipeline(batch, **kw)
+    ref = oracle.run_pipeline(batch, **{k: v for k, v in kw.items() if k != "nms_threads"})   # a scheduling knob, not semantics
     got, _ = helpers.run_cuda(batch, **kw)
     helpers.assert_same(got, ref, 2, kw.get("max_det", 300))
 
 
-def test_pipeline_dense_candidates():
-    """conf 0.001: every anchor is a candidate (8400 per image) -> exercises the global-memory sort."""
+@pytest.mark.parametrize("nms_threads", [0, 512, 1024])
+def test_pipeline_dense_candidates(nms_threads):
+    """conf 0.001: every anchor is a candidate (8400 per image) -> the 16-keys-per-thread register sort of the
+    1024-thread NMS kernel (auto / 1024) and the global-memory sort of the 512-thread one."""
     batch = helpers.make(batch=2, img_size=640, seed=20264)
     kw = dict(conf_thres=0.001, max_det=300)
     ref = oracle.run_pipeline(batch, with_instances=False, **kw)
-    got, _ = helpers.run_cuda(batch, **kw)
+    got, _ = helpers.run_cuda(batch, nms_threads=nms_threads, **kw)
     assert int(ref["n_cand"].min()) > 8000
     helpers.assert_same(got, ref, 2, 300)
 
