@@ -210,7 +210,7 @@ def main():
     bias = float(batch["proj_bias"])
     cfg = PostConfig(batch=B, img_size=S, conf_thres=args.conf, iou_thres=args.iou, max_det=args.max_det, with_coco=True)
     pipe = Pipeline(cfg, dev, depth=max(1, args.pipeline))
-    pp = pipe.procs[0]
+    pp = PostProcessor(cfg, dev)   # one batch in flight: strictly serial steps, per-stage timings, e2e
     counters = torch.zeros(3 * 3 + 4 + 4 + 4, dtype=torch.float64, device=dev)
 
     def step(inp=d, stage="run"):
@@ -228,10 +228,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- warm-up; the step is captured once into a CUDA graph (8 kernels per replay)
+    # ---------------- warm-up; the step is captured once into a CUDA graph (9 kernels per replay)
     pipe.capture(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], bias)
-    graph = pipe.graphs[0]
-    out = pp.out
+    graph = pp.capture(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], bias)
+    out = pipe.procs[0].out
     pipe.fork()
     for _ in range(args.warmup):
         pipe.replay()
@@ -359,8 +359,8 @@ def main():
                      "achieved_gbs": ab["total"] * B / (ms / args.steps / 1e3) / 1e9,
                      "frac_of_peak": ab["total"] * B / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
                      "stage_ms": stage_ms, "ms_per_step_one_batch_in_flight": serial_ms},
-        "clocks": clocks, "gpu_launches": 8 * args.steps,
-        "kernels_per_step": ["gt_pack_kernel", "decode_filter_l2_kernel", "nms_kernel", "coeff_gather_kernel", "match_kernel",
+        "clocks": clocks, "gpu_launches": 9 * args.steps,
+        "kernels_per_step": ["gt_pack_kernel", "decode_filter_l2_kernel", "nms_kernel", "plan_kernel", "coeff_gather_kernel", "match_kernel",
                              "contract_kernel", "cells_kernel", "finalize_kernel"],
     }
     if e2e:

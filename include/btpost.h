@@ -74,7 +74,7 @@ typedef struct BtParams {
     int32_t num_iou_thrs;     /* T (10 for mAP50-95, 1 for mAP50)                             */
     double iou_thrs[BT_MAX_IOU_THRS]; /* float64(fp32 linspace(0.5,0.95,10))                  */
     int32_t image_offset;     /* global index of image 0 (for sweep records / sharding)       */
-    int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = auto (512; 1024 when conf_thres < 0.01), 512, 1024 */
+    int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = default (1024), 512 (small footprint: several batches in flight), 1024 */
     int32_t reserved[6];
 } BtParams;
 

@@ -15,6 +15,7 @@ memory and the stream.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass, field
 
 import torch
@@ -245,6 +246,11 @@ class Pipeline:
     uni_cnt4) are the sums over the processors (``counters()``)."""
 
     def __init__(self, cfg: PostConfig, device="cuda:0", depth: int = 2):
+        conf = cfg.conf_thres if cfg.conf_thres is not None else CONF_TH
+        if depth > 1 and cfg.nms_threads == 0 and conf >= 0.01:
+            # small-footprint NMS kernel: its CTAs share SMs with the mask kernels of the other batches in flight
+            # (dense candidate lists keep the 1024-thread variant, which sorts them in registers)
+            cfg = dataclasses.replace(cfg, nms_threads=512)
         self.procs = [PostProcessor(cfg, device) for _ in range(depth)]
         self.device = self.procs[0].device
         self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]

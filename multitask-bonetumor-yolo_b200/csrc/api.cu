@@ -74,7 +74,7 @@ static int check_stage3(const BtParams *p, const BtIO *io) {
 // on the caller's stream and capturable into a CUDA graph.  Calls on the same device are not re-entrant.
 struct SideStream {
     cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, pack = nullptr, nms = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, pack = nullptr, nms = nullptr, gather = nullptr, join = nullptr;
 };
 static SideStream *side_stream() {
     static SideStream tab[64];
@@ -83,7 +83,7 @@ static SideStream *side_stream() {
     SideStream &t = tab[dev];
     if (!t.stream) {
         if (cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking) != cudaSuccess) { t.stream = nullptr; return nullptr; }
-        cudaEvent_t *ev[4] = {&t.fork, &t.pack, &t.nms, &t.join};
+        cudaEvent_t *ev[5] = {&t.fork, &t.pack, &t.nms, &t.gather, &t.join};
         for (auto e : ev)
             if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
@@ -176,12 +176,16 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     rc = launch_masks(*p, *io, w, side->stream, BT_MASKS_PACK);
     if (rc == BT_OK && !ok(cudaEventRecord(side->pack, side->stream))) rc = BT_ERR_CUDA;
     if (rc == BT_OK) rc = launch_decode_filter(*p, *io, w, s);
+    // NMS, then the mask-stage plan on the caller's stream while the helper stream gathers the kept detections' mask
+    // coefficients and runs the COCO matching (beside the mask kernels)
     if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s, BT_NMS_SORT_SWEEP);
-    // COCO matching on the helper stream, beside the mask kernels
     if (rc == BT_OK && (!ok(cudaEventRecord(side->nms, s)) || !ok(cudaStreamWaitEvent(side->stream, side->nms, 0)))) rc = BT_ERR_CUDA;
+    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s, BT_NMS_PLAN);
+    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_GATHER);
+    if (rc == BT_OK && !ok(cudaEventRecord(side->gather, side->stream))) rc = BT_ERR_CUDA;
     if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_COCO);
     if (rc == BT_OK && !ok(cudaEventRecord(side->join, side->stream))) rc = BT_ERR_CUDA;
-    if (rc == BT_OK && !ok(cudaStreamWaitEvent(s, side->pack, 0))) rc = BT_ERR_CUDA;
+    if (rc == BT_OK && (!ok(cudaStreamWaitEvent(s, side->pack, 0)) || !ok(cudaStreamWaitEvent(s, side->gather, 0)))) rc = BT_ERR_CUDA;
     if (rc == BT_OK) rc = launch_masks(*p, *io, w, s, BT_MASKS_CONTRACT | BT_MASKS_CELLS);
     // join (always, so that a capture never ends with an unjoined stream)
     if (!ok(cudaStreamWaitEvent(s, side->join, 0)) && rc == BT_OK) rc = BT_ERR_CUDA;

@@ -154,9 +154,10 @@ static inline Workspace carve(const BtParams *p, void *base) {
 
 int check_params(const BtParams *p, const BtIO *io);
 int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s);
-// parts: BT_NMS_SORT_SWEEP (NMS + coefficient gather + mask-stage plan), BT_NMS_COCO (evaluateImg matching)
-enum { BT_NMS_SORT_SWEEP = 1, BT_NMS_COCO = 2 };
-int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts = 3);
+// parts: BT_NMS_SORT_SWEEP (the NMS kernel) and, each needing only its results: BT_NMS_GATHER (mask coefficients of the
+// kept detections), BT_NMS_PLAN (plan of the mask stage), BT_NMS_COCO (evaluateImg matching)
+enum { BT_NMS_SORT_SWEEP = 1, BT_NMS_COCO = 2, BT_NMS_GATHER = 4, BT_NMS_PLAN = 8 };
+int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts = 15);
 // parts: BT_MASKS_PACK (GT bits; independent of the detections), BT_MASKS_CONTRACT (the pass over the prototypes),
 // BT_MASKS_CELLS (upsample + threshold + counters + per-image finalize)
 int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts = 7);

@@ -558,9 +558,16 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
         }
         P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
     }
-    if (blockIdx.x != 0) return;
-    // ---- plan of the mask stage (first CTA of the image): where each detection's crop-box logits live in the
-    // pool.  Exclusive prefix sum of the box areas; the image's base comes from one bump of the pool counter.
+}
+
+// =================================================================================================
+// plan of the mask stage, one CTA per image: where each detection's crop-box logits live in the pool (exclusive
+// prefix sum of the box areas; the image's base comes from one bump of the pool counter), which contract_kernel
+// tiles each detection touches, and the work items of cells_kernel.  Independent of the coefficient gather.
+// =================================================================================================
+__global__ void __launch_bounds__(GM_THREADS) plan_kernel(const __grid_constant__ K2Params P) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int K = P.max_det;
     __shared__ long long s_base;
     const int tid = threadIdx.x;
     const int per = (K + GM_THREADS - 1) / GM_THREADS;
@@ -842,12 +849,12 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
 
     // shared memory of nms_kernel: [sorted-index list | window (48 B/candidate) + kept arrays (48 B/slot)];
     // the sort's exchange buffer overlays everything.
-    // 512 threads per image (32 k registers, < 80 KB of shared memory) leave room on the SM for CTAs of the mask kernels
-    // of other batches in flight, or for a second image; the 1024-thread variant sorts long candidate lists in
-    // registers (dense configurations: conf_thres < 0.01), the small one falls back to the global-memory network
-    // above 4096 candidates
+    // BtParams.nms_threads = 512: 32 k registers and < 80 KB of shared memory per image leave room on the SM for CTAs of
+    // the mask kernels of other batches in flight, or for a second image (btpost.Pipeline asks for it: +8 % images/s
+    // with six batches in flight, but a single step is 11 us slower).  The 1024-thread variant (default) also sorts
+    // long candidate lists in registers; the small one falls back to the global-memory network above 4096 candidates.
     static const char *nt_env = getenv("BTPOST_NMS_NT");
-    const int nt_req = p.nms_threads ? p.nms_threads : nt_env ? atoi(nt_env) : (p.conf_thres < 0.01f ? 1024 : 512);
+    const int nt_req = p.nms_threads ? p.nms_threads : nt_env ? atoi(nt_env) : 1024;
     const int nt = nt_req == 512 ? 512 : 1024;
     const int sort_max = nt == 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
     const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > sort_max ? sort_max : P.cap_pow2);
@@ -888,8 +895,9 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
         cfg.attrs = at; cfg.numAttrs = prio != 0 ? 1 : 0;
         if ((nt == 512 ? cudaLaunchKernelEx(&cfg, nms_kernel<512>, P) : cudaLaunchKernelEx(&cfg, nms_kernel<1024>, P)) != cudaSuccess)
             return BT_ERR_CUDA;
-        coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);
     }
+    if (parts & BT_NMS_GATHER) coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);
+    if (parts & BT_NMS_PLAN) plan_kernel<<<p.batch, GM_THREADS, 0, s>>>(P);
     if ((parts & BT_NMS_COCO) && io.dt_match) match_kernel<<<p.batch, GM_THREADS, smem_b, s>>>(P);
     return cudaGetLastError() == cudaSuccess ? BT_OK : BT_ERR_CUDA;
 }
