@@ -38,7 +38,7 @@ constexpr int NM = 32;
 constexpr int A_THREADS = 128;          // 4 warps, each an 8 x 8 pixel block, 2 pixels per thread
 constexpr int A_LCAP = 32;              // detections staged per round
 constexpr int C_THREADS = 256;
-constexpr int G_THREADS = 96;   // gt_pack_kernel: 160 row words, then 81 blocks per CTA at 640^2
+constexpr int G_THREADS = 128, G_ROWS = 4;   // gt_pack_kernel: threads, rows of blocks per CTA
 constexpr int C_NQ = 32, C_QSTRIDE = 32;   // work queues of cells_kernel: counters 128 bytes apart
 
 typedef unsigned long long u64;
@@ -268,20 +268,26 @@ __device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
 }
 
 __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constant__ K3Params P) {
-    extern __shared__ uint32_t s_rows[];   // [8][wpr + 1]
-    __shared__ int s_cnt[G_THREADS / 32];
-    const int by = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    // one CTA packs G_ROWS rows of blocks of one image: their 8 * G_ROWS (+2 above) output rows -> row bits -> words
+    extern __shared__ uint32_t s_rows[];   // [8 * G_ROWS + 2][wpr + 1]
+    __shared__ int s_cnt[G_ROWS];
+    const int by_lo = blockIdx.x * G_ROWS, b = blockIdx.y, tid = threadIdx.x;
+    const int nby = min(G_ROWS, P.NBY - by_lo);
     const int S_h = P.S_h, S_w = P.S_w, wpr = S_w >> 5, tp = wpr + 1;
-    const int y_lo = by ? 8 * by - 2 : 0, y_hi = min(8 * by + 6, S_h);   // output rows of the block row
+    const int y_lo = by_lo ? 8 * by_lo - 2 : 0, y_hi = min(8 * (by_lo + nby) - 2, S_h);   // output rows of these block rows
     const int nyr = y_hi - y_lo;
-    if (by == 0) {
+    if (blockIdx.x == 0) {
         if (tid < 8) P.acc[b * 8 + tid] = 0;
         if (b == 0 && tid >= 32 && tid < 32 + C_NQ) P.work[(tid - 32) * C_QSTRIDE] = 0;
     }
-    for (int q = tid; q < 8 * tp; q += G_THREADS) {
-        const int yr = q / tp, w = q - yr * tp;
-        uint32_t bits = 0;
-        if (yr < nyr && w < wpr) {
+    if (tid < G_ROWS) s_cnt[tid] = 0;
+    // ---- bytes -> row bits: 32 pixels per job, (row, word) advanced without divisions
+    {
+        int yr = tid / wpr, w = tid - yr * wpr;
+        const int dyr = G_THREADS / wpr, dw = G_THREADS - dyr * wpr;
+        for (; yr < nyr; yr += dyr, w += dw) {
+            if (w >= wpr) { w -= wpr; ++yr; if (yr >= nyr) break; }
+            uint32_t bits = 0;
             if (!P.gt_f32) {
                 const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
                                                                   ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
@@ -296,60 +302,61 @@ __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constan
                             ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
                 }
             }
+            s_rows[yr * tp + w] = bits;
         }
-        s_rows[q] = bits;
+        for (int q = tid; q < nyr; q += G_THREADS) s_rows[q * tp + wpr] = 0;   // pad word: the funnel shifts read one past
     }
     __syncthreads();
-    int cnt = 0;
-    for (int bx = tid; bx < P.NBX; bx += G_THREADS) {
+    // ---- row bits -> block words.  Interior blocks first (uniform: one funnel shift per row), then the border ones.
+    const int NBX = P.NBX;
+    for (int q = tid; q < nby * NBX; q += G_THREADS) {
+        // blocks of a row in the order 1 .. NBX-2, 0, NBX-1: the two border columns share the last lanes
+        const int a_row = q / NBX, qq = q - a_row * NBX;
+        const int bx = (qq < NBX - 2) ? qq + 1 : (qq == NBX - 2 ? 0 : NBX - 1);
+        const int by = by_lo + a_row;
         u64 word = 0;
         if (by > 0 && bx > 0 && 2 * by < P.PH - 1 && 2 * bx < P.PW - 1) {
-            // interior block: 8 output rows x 8 pixels starting at (8by-2, 8bx-2), one funnel shift per row
+            // interior block: 8 output rows x 8 pixels starting at (8by-2, 8bx-2)
             const int xb = 8 * bx - 2;
+            const uint32_t *row = s_rows + (8 * by - 2 - y_lo) * tp + (xb >> 5);
             uint32_t lo = 0, hi = 0;
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
-                const uint32_t *row = s_rows + rr * tp + (xb >> 5);
-                const unsigned g8 = __funnelshift_r(row[0], row[1], xb & 31) & 0xffu;
+                const unsigned g8 = __funnelshift_r(row[rr * tp], row[rr * tp + 1], xb & 31) & 0xffu;
                 // pixels 0-3 -> cell column A, 4-7 -> cell column B; rows 0-3 -> cell row A, 4-7 -> cell row B
                 const unsigned two = (g8 & 0xfu) | ((g8 & 0xf0u) << 12);
                 if (rr < 4) lo |= two << (4 * rr); else hi |= two << (4 * (rr - 4));
             }
             word = ((u64)hi << 32) | lo;
-        } else
+        } else {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int ci = 2 * by - 1 + a;
-            if (ci > P.PH - 1) continue;
-            const int ybase = (ci < 0) ? 0 : 4 * ci + 2, nry = (ci < 0) ? 2 : min(4, S_h - ybase);
+            for (int a = 0; a < 2; ++a) {
+                const int ci = 2 * by - 1 + a;
+                if (ci > P.PH - 1) continue;
+                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, nry = (ci < 0) ? 2 : min(4, S_h - ybase);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int cj = 2 * bx - 1 + c;
-                if (cj > P.PW - 1) continue;
-                const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                unsigned bits = 0;
-                for (int ry = 0; ry < nry; ++ry) {
-                    const uint32_t *row = s_rows + (ybase + ry - y_lo) * tp + (xbase >> 5);
-                    const unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
-                    bits |= gb << (4 * ry);
+                for (int c = 0; c < 2; ++c) {
+                    const int cj = 2 * bx - 1 + c;
+                    if (cj > P.PW - 1) continue;
+                    const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
+                    unsigned bits = 0;
+                    for (int ry = 0; ry < nry; ++ry) {
+                        const uint32_t *row = s_rows + (ybase + ry - y_lo) * tp + (xbase >> 5);
+                        const unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
+                        bits |= gb << (4 * ry);
+                    }
+                    word |= (u64)bits << (16 * (2 * a + c));
                 }
-                word |= (u64)bits << (16 * (2 * a + c));
             }
         }
-        const size_t o = ((size_t)b * P.NBY + by) * P.NBX + bx;
+        const size_t o = ((size_t)b * P.NBY + by) * NBX + bx;
         P.gtc[o] = word;
         P.unc[o] = 0ull;
-        cnt += __popcll(word);
+        const int cnt = __popcll(word);
+        if (cnt) atomicAdd(&s_cnt[a_row], cnt);
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
-    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
     __syncthreads();
-    if (tid == 0) {
-        int v = 0;
-        for (int w = 0; w < G_THREADS / 32; ++w) v += s_cnt[w];
-        P.gpart[b * P.NBY + by] = v;
-    }
+    if (tid < nby) P.gpart[b * P.NBY + by_lo + tid] = s_cnt[tid];
 }
 
 // =================================================================================================
@@ -852,8 +859,8 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 
     if (parts & BT_MASKS_PACK) {
-        const size_t smem_g = (size_t)8 * (p.img_w / 32 + 1) * sizeof(uint32_t);
-        gt_pack_kernel<<<dim3(P.NBY, p.batch), G_THREADS, smem_g, s>>>(P);
+        const size_t smem_g = (size_t)(8 * G_ROWS + 2) * (p.img_w / 32 + 1) * sizeof(uint32_t);
+        gt_pack_kernel<<<dim3((P.NBY + G_ROWS - 1) / G_ROWS, p.batch), G_THREADS, smem_g, s>>>(P);
     }
 
     static const char *nb_env = getenv("BTPOST_A_NBUF");   // developer switch (scripts/): tile buffers per CTA
