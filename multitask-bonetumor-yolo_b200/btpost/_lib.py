@@ -75,6 +75,8 @@ def load():
             f = getattr(L, name)
             f.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p]
             f.restype = C.c_int
+    L.btpost_synth_batch.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 7
+    L.btpost_synth_batch.restype = C.c_int
     L.btpost_masks_parts.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     L.btpost_masks_parts.restype = C.c_int
     _lib = L

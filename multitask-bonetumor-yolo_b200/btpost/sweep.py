@@ -60,10 +60,16 @@ class SweepState:
         rank = torch.arange(K, device=dets.device)[None, :].expand(B, K)
         matched = (out["dt_match"] > 0).permute(0, 3, 1, 2)                                         # [B,K,A,T]
         ignored = (out["dt_ignore"] > 0).permute(0, 3, 1, 2)
+        # padded per-batch records + their validity mask: the ragged compaction (a host sync per batch) happens once,
+        # in _records(); the library reuses its output buffers, so everything kept here is a copy
         self._rec.append({
-            "score": dets[..., 4][valid], "label": labels[valid], "img": img[valid], "rank": rank[valid],
-            "class_rank": class_rank[valid], "matched": matched[valid], "ignored": ignored[valid],
+            "score": dets[..., 4].reshape(-1).clone(), "label": labels.reshape(-1), "img": img.reshape(-1),
+            "rank": rank.reshape(-1), "class_rank": class_rank.reshape(-1),
+            "matched": matched.reshape(B * K, self.A, self.T), "ignored": ignored.reshape(B * K, self.A, self.T),
+            "_valid": valid.reshape(-1),
         })
+        if len(self._rec) >= 64:   # bound the padded backlog: one compaction (and host sync) per 64 batches
+            self._rec = [self._records()]
         G = out["gt_labels"].shape[1]
         gvalid = torch.arange(G, device=dets.device)[None, :] < out["gt_count"].long()[:, None]     # [B,G]
         gl = out["gt_labels"].long()
@@ -109,7 +115,13 @@ class SweepState:
             return {"score": z(0, dt=torch.float32), "label": z(0, dt=torch.int64), "img": z(0, dt=torch.int64),
                     "rank": z(0, dt=torch.int64), "class_rank": z(0, dt=torch.int64),
                     "matched": z(0, self.A, self.T, dt=torch.bool), "ignored": z(0, self.A, self.T, dt=torch.bool)}
-        return {k: torch.cat([r[k] for r in self._rec]) for k in self._rec[0]}
+        parts = []
+        for r in self._rec:
+            if "_valid" in r:   # a padded batch as `add` left it
+                v = r["_valid"]
+                r = {k: t[v] for k, t in r.items() if k != "_valid"}
+            parts.append(r)
+        return {k: torch.cat([r[k] for r in parts]) for k in parts[0]}
 
     @torch.no_grad()
     def gather(self, group=None):

@@ -3,7 +3,8 @@
 Every element is a pure function of ``(seed, tensor_id, image_idx, element_idx)`` through a
 splitmix64 finaliser, and every floating-point step is a single correctly-rounded fp32 operation
 (no transcendental functions), so the numpy generator here and the CUDA generator in
-``csrc/synth.cu`` materialise bit-identical tensors on any shard without moving data.
+``csrc/synth.cu`` (``make_batch_device`` below, `include/btpost_synth.h`) materialise bit-identical
+tensors on any shard without moving data (`tests/test_gpu_synth.py`).
 
 Layouts produced (reference producers cited):
   * L2 ``head``  [B, 4+nc+nm, N]  = ``segment_preds_cat`` (`/root/reference/src/main_modelv2.py:367-375`):
@@ -244,4 +245,43 @@ def make_batch(cfg: SynthConfig, l1: bool = False) -> dict:
     h = hash_elems(key, np.arange(cfg.nm + 1))
     out["proj_weight"] = gauss16(h[:cfg.nm]) * np.float32(0.25)
     out["proj_bias"] = gauss16(h[cfg.nm:])[0] * np.float32(0.1)
+    return out
+
+
+def make_batch_device(cfg: SynthConfig, device="cuda:0", stream=None) -> dict:
+    """Same batch as ``make_batch`` (L2 layout), generated on the GPU by ``btpost_synth_batch``: only the stream
+    keys, the object table (3 rows per image) and the GT rows are made on the host.  Returns torch tensors on
+    ``device`` (``head``, ``protos``, ``masks_gt``, ``det_boxes_gt``, ``proj_weight``) and ``proj_bias``."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    dev = torch.device(device)
+    tab = object_table(cfg)
+    inv = np.float32(1.0) / np.float32(cfg.img_size)
+    rows = [[np.float32(b), tab[b, o, 1], tab[b, o, 2] * inv, tab[b, o, 3] * inv, tab[b, o, 4] * inv, tab[b, o, 5] * inv]
+            for b in range(cfg.batch) for o in range(MAX_OBJ) if tab[b, o, 0] != 0]
+    gt = np.asarray(rows, np.float32).reshape(-1, 6)
+    keys = np.array([[stream_key(cfg.seed, TID_HEAD, cfg.image_offset + b), stream_key(cfg.seed, TID_PROTO, cfg.image_offset + b)]
+                     for b in range(cfg.batch)], dtype=np.uint64)
+    # uint64 has no torch dtype everywhere: ship the keys as int64 bit patterns
+    kh = torch.from_numpy(np.ascontiguousarray(keys[:, 0]).view(np.int64)).to(dev)
+    kp = torch.from_numpy(np.ascontiguousarray(keys[:, 1]).view(np.int64)).to(dev)
+    objs = torch.from_numpy(tab).to(dev)
+    P = cfg.proto_hw
+    head = torch.empty(cfg.batch, 4 + cfg.nc + cfg.nm, cfg.num_anchors, dtype=torch.float32, device=dev)
+    protos = torch.empty(cfg.batch, cfg.nm, P, P, dtype=torch.float32, device=dev)
+    masks = torch.empty(cfg.batch, 1, cfg.img_size, cfg.img_size, dtype=torch.uint8, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().btpost_synth_batch(cfg.batch, cfg.img_size, cfg.nc, cfg.nm, C.c_void_p(kh.data_ptr()), C.c_void_p(kp.data_ptr()),
+                                           C.c_void_p(objs.data_ptr()), C.c_void_p(head.data_ptr()), C.c_void_p(protos.data_ptr()),
+                                           C.c_void_p(masks.data_ptr()), C.c_void_p(st.cuda_stream))
+    _lib.check(rc, "btpost_synth_batch")
+    key = stream_key(cfg.seed, 99, 0)
+    h = hash_elems(key, np.arange(cfg.nm + 1))
+    out = {"objects": tab, "head": head, "protos": protos, "masks_gt": masks, "det_boxes_gt": torch.from_numpy(gt).to(dev),
+           "proj_weight": torch.from_numpy(gauss16(h[:cfg.nm]) * np.float32(0.25)).to(dev),
+           "proj_bias": float(gauss16(h[cfg.nm:])[0] * np.float32(0.1)), "_keepalive": (kh, kp, objs)}
     return out

@@ -90,6 +90,8 @@ static SideStream *side_stream() {
     return &t;
 }
 
+int g_debug_skip = 0;   // developer tool (scripts/ablate.py): launches left out of btpost_run, see btpost_debug_skip
+
 }  // namespace bt
 
 using namespace bt;
@@ -107,6 +109,11 @@ extern "C" BTPOST_API int btpost_debug_phase_cycles(unsigned long long *out48, i
 #endif
 
 extern "C" {
+
+// Developer tool, not part of the product ABI (not declared in btpost.h): leave kernels out of the following
+// btpost_run calls to measure what each costs with several batches in flight (results are then stale / invalid).
+// bits: 1 gt_pack, 2 decode_filter, 4 nms, 8 plan, 16 gather, 32 match, 64 contract, 128 cells + finalize
+BTPOST_API int btpost_debug_skip(int mask) { bt::g_debug_skip = mask; return BT_OK; }
 
 int btpost_version(void) { return BTPOST_VERSION; }
 
@@ -172,21 +179,23 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     if (!side) return BT_ERR_CUDA;
     auto ok = [](cudaError_t e) { return e == cudaSuccess; };
     // fork: GT bits on the helper stream while the caller's stream decodes, filters and runs the NMS
+    const int skip = g_debug_skip;
     if (!ok(cudaEventRecord(side->fork, s)) || !ok(cudaStreamWaitEvent(side->stream, side->fork, 0))) return BT_ERR_CUDA;
-    rc = launch_masks(*p, *io, w, side->stream, BT_MASKS_PACK);
+    if (!(skip & 1)) rc = launch_masks(*p, *io, w, side->stream, BT_MASKS_PACK);
     if (rc == BT_OK && !ok(cudaEventRecord(side->pack, side->stream))) rc = BT_ERR_CUDA;
-    if (rc == BT_OK) rc = launch_decode_filter(*p, *io, w, s);
+    if (rc == BT_OK && !(skip & 2)) rc = launch_decode_filter(*p, *io, w, s);
     // NMS, then the mask-stage plan on the caller's stream while the helper stream gathers the kept detections' mask
     // coefficients and runs the COCO matching (beside the mask kernels)
-    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s, BT_NMS_SORT_SWEEP);
+    if (rc == BT_OK && !(skip & 4)) rc = launch_nms_match(*p, *io, w, s, BT_NMS_SORT_SWEEP);
     if (rc == BT_OK && (!ok(cudaEventRecord(side->nms, s)) || !ok(cudaStreamWaitEvent(side->stream, side->nms, 0)))) rc = BT_ERR_CUDA;
-    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, s, BT_NMS_PLAN);
-    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_GATHER);
+    if (rc == BT_OK && !(skip & 8)) rc = launch_nms_match(*p, *io, w, s, BT_NMS_PLAN);
+    if (rc == BT_OK && !(skip & 16)) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_GATHER);
     if (rc == BT_OK && !ok(cudaEventRecord(side->gather, side->stream))) rc = BT_ERR_CUDA;
-    if (rc == BT_OK) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_COCO);
+    if (rc == BT_OK && !(skip & 32)) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_COCO);
     if (rc == BT_OK && !ok(cudaEventRecord(side->join, side->stream))) rc = BT_ERR_CUDA;
     if (rc == BT_OK && (!ok(cudaStreamWaitEvent(s, side->pack, 0)) || !ok(cudaStreamWaitEvent(s, side->gather, 0)))) rc = BT_ERR_CUDA;
-    if (rc == BT_OK) rc = launch_masks(*p, *io, w, s, BT_MASKS_CONTRACT | BT_MASKS_CELLS);
+    if (rc == BT_OK && (skip & (64 | 128)) != (64 | 128))
+        rc = launch_masks(*p, *io, w, s, ((skip & 64) ? 0 : BT_MASKS_CONTRACT) | ((skip & 128) ? 0 : BT_MASKS_CELLS));
     // join (always, so that a capture never ends with an unjoined stream)
     if (!ok(cudaStreamWaitEvent(s, side->join, 0)) && rc == BT_OK) rc = BT_ERR_CUDA;
     return rc;

@@ -1,0 +1,42 @@
+"""Developer tool: what does each kernel cost with several batches in flight?  Captures the step with one kernel
+left out (btpost_debug_skip; the buffers keep the valid data of a complete eager step) and times the replays."""
+import ctypes as C, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "multitask-bonetumor-yolo_b200")]
+import numpy as np, torch
+from btpost import Pipeline, PostConfig, synth, _lib
+
+B, S, depth = 64, 640, int(sys.argv[1]) if len(sys.argv) > 1 else 6
+b = synth.make_batch(synth.SynthConfig(batch=B, img_size=S, seed=20262))
+dev = torch.device("cuda:0")
+d = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("head", "protos", "det_boxes_gt", "masks_gt", "proj_weight")}
+args = (d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], float(b["proj_bias"]))
+L = _lib.load()
+names = {0: "nothing", 1: "gt_pack", 2: "decode_filter", 4: "nms", 8: "plan", 16: "gather", 32: "match", 64: "contract", 128: "cells+finalize"}
+base = None
+for mask, name in names.items():
+    pipe = Pipeline(PostConfig(batch=B, img_size=S), dev, depth=depth)
+    for p in pipe.procs:
+        p.run(*args)                       # complete eager step: valid data in every buffer
+    torch.cuda.synchronize()
+    L.btpost_debug_skip(mask)
+    pipe.graphs = []
+    for p in pipe.procs:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            p.run(*args)
+        pipe.graphs.append(g)
+    L.btpost_debug_skip(0)
+    n = 300
+    pipe.fork()
+    for _ in range(30): pipe.replay()
+    pipe.join(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); pipe.fork()
+    for _ in range(n): pipe.replay()
+    pipe.join(); e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / n * 1e3
+    base = us if base is None else base
+    print(f"without {name:16s} {us:7.1f} us/step   (marginal cost {base - us:6.1f} us)")
+    del pipe

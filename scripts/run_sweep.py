@@ -36,10 +36,10 @@ pp.reset_metrics()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 gpu_ms, t_host = 0.0, time.perf_counter()
 for i in mine:
-    b = synth.make_batch(synth.SynthConfig(batch=B, img_size=args.img, seed=20265, image_offset=i * B))
-    d = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("head", "protos", "det_boxes_gt", "masks_gt", "proj_weight")}
+    # this rank's images, generated on the device (bit-identical to the numpy generator: tests/test_gpu_synth.py)
+    d = synth.make_batch_device(synth.SynthConfig(batch=B, img_size=args.img, seed=20265, image_offset=i * B), dev)
     ev0.record()
-    out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], float(b["proj_bias"]))
+    out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
     st.add(out, i * B)
     st_seg.add(seg_map_outputs(out, map_iou_thresholds()), i * B)
     ev1.record()
