@@ -44,6 +44,7 @@ enum { BT_LAYOUT_L2 = 0, BT_LAYOUT_L1 = 1 };
 enum { BT_CLASS_AGNOSTIC = 0, BT_CLASS_AWARE = 1, BT_CLASS_OFFSET = 2 };
 enum { BT_GT_LITERAL = 0, BT_GT_INTENDED = 1 };
 enum { BT_MASK_U8 = 0, BT_MASK_F32 = 1 };
+enum { BT_PROTO_F32 = 0, BT_PROTO_BF16 = 1 };
 
 /* Problem description.  Mirrors the reference's module constants CONF_TH / NMS_IOU / TOP_K
  * (src/running_main_v2.py:51-53) and hparams img_size / nc_det / proto_ch / iou_match_thresh
@@ -75,7 +76,9 @@ typedef struct BtParams {
     double iou_thrs[BT_MAX_IOU_THRS]; /* float64(fp32 linspace(0.5,0.95,10))                  */
     int32_t image_offset;     /* global index of image 0 (for sweep records / sharding)       */
     int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = default (1024), 512 (small footprint: several batches in flight), 1024 */
-    int32_t reserved[6];
+    int32_t proto_dtype;      /* BT_PROTO_F32 (default) or BT_PROTO_BF16: dtype of `protos`; bf16 values are widened exactly, so the
+                                 results equal those of the reference on `protos.float()` (it validates under bf16-mixed) */
+    int32_t reserved[5];
 } BtParams;
 
 /* Device buffers.  Inputs are read-only.  Any OUTPUT pointer may be NULL to skip that output
@@ -86,7 +89,7 @@ typedef struct BtIO {
     const float *head;          /* L2: [B, 4+nc+nm, N] fp32 (segment_preds_cat, main_modelv2.py:367) */
     const float *maps[3];       /* L1: [B, 4*reg_max+nc, H_l, W_l], strides 8/16/32            */
     const float *coeffs;        /* L1: mask coefficients [B, nm, N] (Segment `mc`)             */
-    const float *protos;        /* [B, nm, proto_h, proto_w] fp32, 16-byte aligned             */
+    const void *protos;         /* [B, nm, proto_h, proto_w] fp32 (or bf16: proto_dtype), 16-byte aligned */
     const float *det_boxes_gt;  /* [num_gt_rows, 6] (batch_idx, cls, cx, cy, w, h) normalised  */
     const void *masks_gt;       /* [B, 1, S, S] u8 or f32 {0,1}                                */
     const float *proj_weight;   /* [nm] seg_proto_projector weight                             */

@@ -67,6 +67,7 @@ class PostConfig:
     with_seg_map: bool = False           # v3 segmentation-mAP prep (score numerator per image)
     num_anchors: int | None = None
     nms_threads: int = 0                 # 0 = auto; 512 / 1024 force a variant of the NMS kernel
+    proto_bf16: bool = False             # prototypes arrive as torch.bfloat16 (widened exactly in the kernel)
 
 
 class PostProcessor:
@@ -94,6 +95,7 @@ class PostProcessor:
         p.iou_match_thresh, p.crop, p.gt_mask_dtype = cfg.iou_match_thresh, int(cfg.crop), cfg.gt_mask_dtype
         p.num_iou_thrs = len(cfg.iou_thrs)
         p.nms_threads = cfg.nms_threads
+        p.proto_dtype = _lib.PROTO_BF16 if cfg.proto_bf16 else _lib.PROTO_F32
         for i, v in enumerate(cfg.iou_thrs):
             p.iou_thrs[i] = v
         self.params = p
@@ -158,7 +160,7 @@ class PostProcessor:
             if coeffs is not None:
                 self._check_in(coeffs, (B, cfg.nm, N), torch.float32, "coeffs")
                 io.coeffs = coeffs.data_ptr()
-        self._check_in(protos, (B, cfg.nm, S // 4, S // 4), torch.float32, "protos")
+        self._check_in(protos, (B, cfg.nm, S // 4, S // 4), torch.bfloat16 if cfg.proto_bf16 else torch.float32, "protos")
         io.protos = protos.data_ptr()
         if det_boxes_gt is None or det_boxes_gt.numel() == 0:
             det_boxes_gt, rows = self._empty_gt, 0

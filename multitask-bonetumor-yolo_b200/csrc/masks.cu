@@ -44,12 +44,13 @@ constexpr int C_NQ = 32, C_QSTRIDE = 32;   // work queues of cells_kernel: count
 typedef unsigned long long u64;
 
 struct K3Params {
-    int B, S_h, S_w, PH, PW, K, gt_f32, NBY, NBX, ntx, nty, m1_items, nq;
+    int B, S_h, S_w, PH, PW, K, gt_f32, proto_bf16, NBY, NBX, ntx, nty, m1_items, nq;
     float bias, inv_K, inv_m1;
     const int2 *items;      // plan of the cells kernel: (image * K + detection, chunk)
     const int32_t *n_items;
     int item_cap;
-    const float *protos, *proj_weight, *det_coeff;
+    const void *protos;     // [B, NM, PH, PW] fp32 or bfloat16 (proto_bf16)
+    const float *proj_weight, *det_coeff;
     const int32_t *det_count, *scr_off, *tile_cnt;
     const unsigned short *tile_list;
     const short4 *det_region;
@@ -73,11 +74,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // One [NM][TA_H][TA_W] box of the [B*NM, PH, PW] prototype tensor -> shared memory.
+// The prototypes are read exactly once: L2 evict-first keeps the logit pool, the projector logits and the GT / union
+// words resident for cells_kernel instead of 210 MB of stream-through data.
 __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *tm, int col, int row, int chan0, uint64_t *bar) {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
             smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(chan0), "r"(smem_u32(bar))
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(chan0), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -362,13 +367,15 @@ __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constan
 // =================================================================================================
 // contract_kernel: one pass over the prototypes
 // =================================================================================================
-template <int NBUF, int MINB>
+// BF16: the prototypes arrive as bfloat16 (the reference validates under bf16-mixed autocast and upcasts with
+// .float()): a 16 KB tile with the 64-byte swizzle, widened exactly to fp32 on the way into the registers.
+template <int NBUF, int MINB, bool BF16 = false>
 __global__ void __launch_bounds__(A_THREADS, MINB)
 contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destination must be 1024-byte aligned: align by hand (1024 spare bytes are allocated)
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    constexpr int TILE_FLOATS = NM * TA_H * TA_W;
+    constexpr int TILE_FLOATS = NM * TA_H * TA_W / (BF16 ? 2 : 1);                     // tile size in 4-byte words
     float *s_tiles = reinterpret_cast<float *>(smem);                                  // [NBUF][NM][TA_H][TA_W], 16-byte chunks XOR row
     __shared__ __align__(8) uint64_t s_bar[NBUF];
     __shared__ __align__(16) float s_cf[A_LCAP][NM];
@@ -403,7 +410,9 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     // loads of the swizzled tile free of bank conflicts
     const int i16 = lane & 15;
     const int row = 2 * (i16 >> 2) + (lane >> 4), colp = (wid << 3) + 2 * (i16 & 3);   // tile-local row / first column
-    const int soff = row * TA_W + (((colp >> 2) ^ row) << 2) + (colp & 3);
+    // fp32: 128-byte rows, chunk ^= row; bf16: 64-byte rows, chunk ^= (row >> 1) & 3 (offsets in 4-byte words)
+    const int soff = BF16 ? row * (TA_W / 2) + ((((colp >> 3) ^ (row >> 1)) & 3) << 2) + ((colp & 7) >> 1)
+                          : row * TA_W + (((colp >> 2) ^ row) << 2) + (colp & 3);
 
     // The tile's detections were binned by the plan (coeff_gather_kernel).  List length and the list entries this
     // thread needs for the first round are fetched one tile ahead, so that a tile starts with ONE round of
@@ -447,8 +456,16 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         u64 p[NM];
         {
             const float *src = s_tiles + buf * TILE_FLOATS + soff;
+            if (BF16) {
 #pragma unroll
-            for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
+                for (int k = 0; k < NM; ++k) {
+                    const uint32_t two = *reinterpret_cast<const uint32_t *>(src + k * (TA_H * TA_W / 2));
+                    p[k] = ((u64)(two & 0xffff0000u) << 32) | (u64)(two << 16);   // bf16 -> fp32 is a 16-bit shift
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
+            }
         }
         __syncthreads();
         if (tid == 0 && tile + NBUF < t_end) issue(tile + NBUF, buf);
@@ -671,7 +688,7 @@ __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, i
         } else {
             // no room in the logit pool (huge crop boxes / crop off): contract the 9 corners here,
             // same sequential order
-            const float *pr = P.protos + (size_t)b * NM * PH * PW;
+            const size_t pr0 = (size_t)b * NM * PH * PW;
             const float mycf = __ldg(P.det_coeff + ((size_t)b * K + k) * NM + lane);
 #pragma unroll
             for (int a = 0; a < 3; ++a)
@@ -679,12 +696,18 @@ __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, i
                 for (int c = 0; c < 3; ++c) v[a][c] = 0.0f;
             for (int ch = 0; ch < NM; ++ch) {
                 const float w = __shfl_sync(0xffffffffu, mycf, ch);
-                const float *pc = pr + (size_t)ch * PH * PW;
+                const size_t pc = pr0 + (size_t)ch * PH * PW;
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(w, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
+                        if (rin[a] && cin[c]) {
+                            const size_t idx = pc + rr[a] * PW + cc[c];
+                            const float x = P.proto_bf16
+                                                ? __uint_as_float((uint32_t)__ldg(static_cast<const unsigned short *>(P.protos) + idx) << 16)
+                                                : __ldg(static_cast<const float *>(P.protos) + idx);
+                            v[a][c] = __fmaf_rn(w, x, v[a][c]);
+                        }
             }
         }
         const size_t o = ((size_t)b * NBY + by) * NBX + bx;
@@ -811,7 +834,7 @@ __global__ void __launch_bounds__(C_THREADS) union_dense_kernel(const __grid_con
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, int PW) {
+static int make_proto_tmap(CUtensorMap *tm, const void *protos, int bf16, int B, int PH, int PW) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *sym = nullptr;
@@ -822,15 +845,17 @@ static int make_proto_tmap(CUtensorMap *tm, const float *protos, int B, int PH, 
         fn = reinterpret_cast<EncodeTiledFn>(sym);
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)B * NM};
-    const cuuint64_t gstride[2] = {(cuuint64_t)PW * sizeof(float), (cuuint64_t)PW * PH * sizeof(float)};
+    const cuuint64_t esz = bf16 ? 2 : 4;
+    const cuuint64_t gstride[2] = {(cuuint64_t)PW * esz, (cuuint64_t)PW * PH * esz};
     const cuuint32_t box[3] = {(cuuint32_t)TA_W, (cuuint32_t)TA_H, (cuuint32_t)NM};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     static const char *pe = getenv("BTPOST_A_PROMO");   // developer switch (scripts/): L2 promotion of the prototype loads
     const int pv = pe ? atoi(pe) : 0;   // measured: no promotion 47.7 us, 128 B 48.0 us, 256 B 50.5 us
     const CUtensorMapL2promotion promo = pv == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                        : pv == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(protos), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+    const CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(protos),
+                          gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, promo,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? BT_OK : BT_ERR_CUDA;
 }
@@ -840,7 +865,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.B = p.batch; P.S_h = p.img_h; P.S_w = p.img_w; P.PH = p.proto_h; P.PW = p.proto_w;
     P.K = p.max_det; P.gt_f32 = p.gt_mask_dtype == BT_MASK_F32;
     P.bias = p.proj_bias;
-    P.protos = io.protos; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
+    P.protos = io.protos; P.proto_bf16 = p.proto_dtype == BT_PROTO_BF16; P.proj_weight = io.proj_weight; P.det_coeff = io.det_coeff;
     P.det_count = io.det_count; P.masks_gt = io.masks_gt; P.det_region = w.det_region; P.scr_off = w.scr_off;
     P.pool = w.pool; P.lm = w.lm; P.gtc = w.gtc; P.unc = w.unc; P.gpart = w.gpart;
     P.work = w.work; P.acc = w.acc; P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap;
@@ -850,13 +875,13 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
     P.seg_mask = io.seg_mask; P.uni_mask = io.uni_mask; P.seg_logits = io.seg_logits;
     P.seg_prob_sum = io.seg_prob_sum;
-    if (p.proto_w % 4 != 0) return BT_ERR_UNSUPPORTED;   // 16-byte global strides for the tensor map
+    if (p.proto_w % (P.proto_bf16 ? 8 : 4) != 0) return BT_ERR_UNSUPPORTED;   // 16-byte global strides for the tensor map
     P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
     P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
     P.m1_items = (P.NBY * P.NBX + 31) / 32;
     P.inv_K = 1.0f / (float)p.max_det; P.inv_m1 = 1.0f / (float)P.m1_items;
     CUtensorMap tm;
-    if (make_proto_tmap(&tm, io.protos, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
+    if (make_proto_tmap(&tm, io.protos, P.proto_bf16, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 
     if (parts & BT_MASKS_PACK) {
         const size_t smem_g = (size_t)(8 * G_ROWS + 2) * (p.img_w / 32 + 1) * sizeof(uint32_t);
@@ -864,11 +889,12 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     }
 
     static const char *nb_env = getenv("BTPOST_A_NBUF");   // developer switch (scripts/): tile buffers per CTA
-    const int nbuf = nb_env ? atoi(nb_env) : 1;
-    const size_t smem_a = (size_t)nbuf * NM * TA_H * TA_W * sizeof(float) + 1024;
+    const int nbuf = (nb_env && !P.proto_bf16) ? atoi(nb_env) : 1;
+    const size_t smem_a = (size_t)nbuf * NM * TA_H * TA_W * (P.proto_bf16 ? 2 : 4) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(contract_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(contract_kernel<1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(contract_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(contract_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
@@ -886,7 +912,8 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * (ca_env ? atoi(ca_env) : nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
         const int grid_a = ntiles < cta_a ? ntiles : cta_a;
         if (parts & BT_MASKS_CONTRACT) {
-            if (nbuf == 2) contract_kernel<2, 3><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+            if (P.proto_bf16) contract_kernel<1, 4, true><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+            else if (nbuf == 2) contract_kernel<2, 3><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
             else if (nbuf == 3) contract_kernel<3, 2><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
             else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
         }

@@ -50,6 +50,19 @@ def test_pipeline_1024():
     helpers.assert_same(got, ref, 1, 50)
 
 
+@pytest.mark.parametrize("kw", [dict(max_det=300), dict(crop=0, max_det=40)])
+def test_bf16_prototypes(kw):
+    """Prototypes as bfloat16 (the reference validates under bf16-mixed and upcasts with .float()): the kernel widens
+    them exactly, so every output equals the oracle's on the bf16-rounded prototypes, bit for bit (pool path and the
+    on-the-fly corner contraction of detections without pool room)."""
+    import torch
+    batch = helpers.make(batch=2, img_size=640, seed=41)
+    batch["protos"] = torch.from_numpy(batch["protos"]).bfloat16().float().numpy()
+    ref = oracle.run_pipeline(batch, **kw)
+    got, _ = helpers.run_cuda(batch, proto_bf16=True, **kw)
+    helpers.assert_same(got, ref, 2, kw["max_det"])
+
+
 def test_gt_mask_f32():
     batch = helpers.make(batch=2, img_size=640, seed=7)
     kw = dict(max_det=30)
