@@ -1,5 +1,5 @@
 """Developer tool: step time of the BASELINE configs that are not the bench headline (graph replays, CUDA events).
-usage: python scripts/config_timing.py dense|hires|l1"""
+usage: python scripts/config_timing.py dense|hires|l1|bf16"""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -13,6 +13,8 @@ if which == "dense":      # config 4: conf 0.001, every anchor a candidate, max_
     B, S, kw, l1 = 128, 640, dict(conf_thres=0.001), False
 elif which == "hires":    # config 3: 1024^2, 21504 anchors, 256^2 protos
     B, S, kw, l1 = 64, 1024, dict(), False
+elif which == "bf16":     # headline shapes with bfloat16 prototypes (what the reference's bf16-mixed forward produces)
+    B, S, kw, l1 = 64, 640, dict(proto_bf16=True), False
 else:                     # the reference's own layout: three raw maps, DFL decode in the kernel
     B, S, kw, l1 = 64, 640, dict(layout=_lib.LAYOUT_L1), True
 small = synth.make_batch(synth.SynthConfig(batch=8, img_size=S, seed=20264), l1=l1)   # 8 distinct images, tiled to B
@@ -21,7 +23,10 @@ gt = np.concatenate([small["det_boxes_gt"] + np.array([8 * i, 0, 0, 0, 0, 0], np
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 pp = PostProcessor(PostConfig(batch=B, img_size=S, **kw), dev)
 extra = dict(maps=[t(rep(m)) for m in small["maps"]], coeffs=t(rep(small["coeffs"]))) if l1 else {}
-args = (None if l1 else t(rep(small["head"])), t(rep(small["protos"])), t(gt), t(rep(small["masks_gt"])), t(small["proj_weight"]),
+protos = t(rep(small["protos"]))
+if which == "bf16":
+    protos = protos.bfloat16()
+args = (None if l1 else t(rep(small["head"])), protos, t(gt), t(rep(small["masks_gt"])), t(small["proj_weight"]),
         float(small["proj_bias"]))
 
 def timeit(g, n=30):
@@ -37,5 +42,5 @@ out = pp.run(*args, **extra)
 print(which, "B", B, "S", S, "n_cand", out["n_cand"][:4].tolist(), "dets", out["det_count"][:4].tolist())
 us = timeit(pp.capture(*args, **extra))
 print(f"whole step us: {us:.1f}  -> {B / us * 1e6:.0f} images/s")
-for st in ("decode_filter", "nms_match", "masks"):
+for st in ("decode_filter", "nms_match", "masks", "masks_contract"):
     print(f"  {st:14s} us: {timeit(pp.capture(*args, stage=st, **extra)):.1f}")
