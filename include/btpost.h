@@ -45,6 +45,7 @@ enum { BT_CLASS_AGNOSTIC = 0, BT_CLASS_AWARE = 1, BT_CLASS_OFFSET = 2 };
 enum { BT_GT_LITERAL = 0, BT_GT_INTENDED = 1 };
 enum { BT_MASK_U8 = 0, BT_MASK_F32 = 1 };
 enum { BT_PROTO_F32 = 0, BT_PROTO_BF16 = 1 };
+enum { BT_HEAD_F32 = 0, BT_HEAD_BF16 = 1 };
 
 /* Problem description.  Mirrors the reference's module constants CONF_TH / NMS_IOU / TOP_K
  * (src/running_main_v2.py:51-53) and hparams img_size / nc_det / proto_ch / iou_match_thresh
@@ -78,7 +79,8 @@ typedef struct BtParams {
     int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = default (1024), 512 (small footprint: several batches in flight), 1024 */
     int32_t proto_dtype;      /* BT_PROTO_F32 (default) or BT_PROTO_BF16: dtype of `protos`; bf16 values are widened exactly, so the
                                  results equal those of the reference on `protos.float()` (it validates under bf16-mixed) */
-    int32_t reserved[5];
+    int32_t head_dtype;       /* BT_HEAD_F32 (default) or BT_HEAD_BF16: dtype of the L2 `head` (same exact widening)            */
+    int32_t reserved[4];
 } BtParams;
 
 /* Device buffers.  Inputs are read-only.  Any OUTPUT pointer may be NULL to skip that output
@@ -86,7 +88,7 @@ typedef struct BtParams {
  * A=BT_NUM_AREA, T=num_iou_thrs. */
 typedef struct BtIO {
     /* ---- inputs ---- */
-    const float *head;          /* L2: [B, 4+nc+nm, N] fp32 (segment_preds_cat, main_modelv2.py:367) */
+    const void *head;           /* L2: [B, 4+nc+nm, N] fp32 or bf16 (head_dtype) (segment_preds_cat, main_modelv2.py:367) */
     const float *maps[3];       /* L1: [B, 4*reg_max+nc, H_l, W_l], strides 8/16/32            */
     const float *coeffs;        /* L1: mask coefficients [B, nm, N] (Segment `mc`)             */
     const void *protos;         /* [B, nm, proto_h, proto_w] fp32 (or bf16: proto_dtype), 16-byte aligned */

@@ -33,7 +33,7 @@ class BtParams(C.Structure):
         ("iou_match_thresh", C.c_float), ("crop", C.c_int32), ("gt_mask_dtype", C.c_int32),
         ("proj_bias", C.c_float), ("num_iou_thrs", C.c_int32),
         ("iou_thrs", C.c_double * BT_MAX_IOU_THRS),
-        ("image_offset", C.c_int32), ("nms_threads", C.c_int32), ("proto_dtype", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("image_offset", C.c_int32), ("nms_threads", C.c_int32), ("proto_dtype", C.c_int32), ("head_dtype", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -84,6 +84,7 @@ def load():
 
 
 PROTO_F32, PROTO_BF16 = 0, 1
+HEAD_F32, HEAD_BF16 = 0, 1
 MASKS_PACK, MASKS_CONTRACT, MASKS_CELLS = 1, 2, 4   # btpost_masks_parts
 
 

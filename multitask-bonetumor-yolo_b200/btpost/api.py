@@ -68,6 +68,7 @@ class PostConfig:
     num_anchors: int | None = None
     nms_threads: int = 0                 # 0 = auto; 512 / 1024 force a variant of the NMS kernel
     proto_bf16: bool = False             # prototypes arrive as torch.bfloat16 (widened exactly in the kernel)
+    head_bf16: bool = False              # same for the L2 head tensor
 
 
 class PostProcessor:
@@ -96,6 +97,7 @@ class PostProcessor:
         p.num_iou_thrs = len(cfg.iou_thrs)
         p.nms_threads = cfg.nms_threads
         p.proto_dtype = _lib.PROTO_BF16 if cfg.proto_bf16 else _lib.PROTO_F32
+        p.head_dtype = _lib.HEAD_BF16 if cfg.head_bf16 else _lib.HEAD_F32
         for i, v in enumerate(cfg.iou_thrs):
             p.iou_thrs[i] = v
         self.params = p
@@ -151,7 +153,7 @@ class PostProcessor:
         io = BtIO()
         cfg, B, S, N = self.cfg, self.B, self.S, self.N
         if cfg.layout == _lib.LAYOUT_L2:
-            self._check_in(head, (B, 4 + cfg.nc + cfg.nm, N), torch.float32, "head")
+            self._check_in(head, (B, 4 + cfg.nc + cfg.nm, N), torch.bfloat16 if cfg.head_bf16 else torch.float32, "head")
             io.head = head.data_ptr()
         else:
             for l, (m, s) in enumerate(zip(maps, (8, 16, 32))):

@@ -21,6 +21,8 @@ int check_params(const BtParams *p, const BtIO *io) {
     if (!(p->iou_thres == p->iou_thres)) return BT_ERR_BAD_ARG;
     if (p->nms_threads != 0 && p->nms_threads != 512 && p->nms_threads != 1024) return BT_ERR_BAD_ARG;
     if (p->proto_dtype != BT_PROTO_F32 && p->proto_dtype != BT_PROTO_BF16) return BT_ERR_BAD_ARG;
+    if (p->head_dtype != BT_HEAD_F32 && p->head_dtype != BT_HEAD_BF16) return BT_ERR_BAD_ARG;
+    if (p->head_dtype == BT_HEAD_BF16 && p->layout != BT_LAYOUT_L2) return BT_ERR_UNSUPPORTED;
     if (p->layout == BT_LAYOUT_L1) {
         if (p->reg_max <= 0 || p->reg_max > 32) return BT_ERR_UNSUPPORTED;
         if (p->img_w % 32 != 0 || p->img_h % 32 != 0) return BT_ERR_UNSUPPORTED;

@@ -29,7 +29,7 @@ constexpr int K1_CLUSTER = 8;
 constexpr int K1_MAX_GT = 32;
 
 struct K1Params {
-    const float *head;   // L2
+    const void *head;    // L2 (fp32 or bf16)
     const float *maps[3];  // L1
     int lvl_off[4];      // anchor offset of each level (L1)
     int lvl_w[3];
@@ -83,12 +83,25 @@ struct Decoded {
 };
 
 // ---- L2 decoder: rows 0..3 = cx, cy, w, h in pixels; rows 4..4+nc = class scores.
-template <int VEC>
+// BF16: the head arrives as bfloat16 (the reference validates under bf16-mixed and upcasts with .float()); every
+// value is widened exactly (a 16-bit shift), so the results equal the fp32 path's on the upcast tensor.
+template <int VEC, bool BF16 = false>
 struct L2Decoder {
-    const float *img;  // head + b*C*N
+    const void *img;  // head + b*C*N (fp32 or bf16 elements)
     int N, nc;
     __device__ __forceinline__ void load_row(int row, int n, float (&v)[VEC]) const {
-        const float *p = img + (size_t)row * N + n;
+        if (BF16) {
+            const unsigned short *p = static_cast<const unsigned short *>(img) + (size_t)row * N + n;
+            if (VEC == 4) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+                v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+                v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+            } else {
+                v[0] = __uint_as_float((unsigned)__ldg(p) << 16);
+            }
+            return;
+        }
+        const float *p = static_cast<const float *>(img) + (size_t)row * N + n;
         if (VEC == 4) {
             float4 t = __ldg(reinterpret_cast<const float4 *>(p));
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -406,11 +419,11 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
 // MAXT = 320: blocks of <= 320 threads, at least 4 resident per SM so that the 8 x B CTAs of a
 // 64-image batch form a single wave (ncu r01c: 64 registers -> 3 CTAs/SM -> a second wave doubled
 // the kernel time).  MAXT = 1024: large anchor counts.
-template <int VEC, int MAXT>
+template <int VEC, int MAXT, bool BF16 = false>
 __global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(MAXT, MAXT <= 320 ? 4 : 1)
 decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
-    L2Decoder<VEC> dec{P.head + (size_t)b * P.C * P.N, P.N, P.nc};
+    L2Decoder<VEC, BF16> dec{static_cast<const char *>(P.head) + (size_t)b * P.C * P.N * (BF16 ? 2 : 4), P.N, P.nc};
     k1_body<VEC, false>(P, dec, b);
 }
 
@@ -464,11 +477,17 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
     dim3 grid(K1_CLUSTER, p.batch);
     if (p.layout == BT_LAYOUT_L2) {
         P.head = io.head; P.C = 4 + p.nc + p.nm;
+        const bool bf16 = p.head_dtype == BT_HEAD_BF16;
         bool vec = (p.num_anchors % 4 == 0) && ((reinterpret_cast<uintptr_t>(io.head) & 15) == 0);
         if (block_for(vec ? 4 : 1) > K1_MAX_THREADS) return BT_ERR_UNSUPPORTED;  // > 32768 (262144 vectorised) anchors
         dim3 block(block_for(vec ? 4 : 1));
         const bool small = block.x <= 320;
-        if (vec && small) decode_filter_l2_kernel<4, 320><<<grid, block, 0, s>>>(P);
+        if (bf16) {
+            if (vec && small) decode_filter_l2_kernel<4, 320, true><<<grid, block, 0, s>>>(P);
+            else if (vec) decode_filter_l2_kernel<4, 1024, true><<<grid, block, 0, s>>>(P);
+            else if (small) decode_filter_l2_kernel<1, 320, true><<<grid, block, 0, s>>>(P);
+            else decode_filter_l2_kernel<1, 1024, true><<<grid, block, 0, s>>>(P);
+        } else if (vec && small) decode_filter_l2_kernel<4, 320><<<grid, block, 0, s>>>(P);
         else if (vec) decode_filter_l2_kernel<4, 1024><<<grid, block, 0, s>>>(P);
         else if (small) decode_filter_l2_kernel<1, 320><<<grid, block, 0, s>>>(P);
         else decode_filter_l2_kernel<1, 1024><<<grid, block, 0, s>>>(P);

@@ -106,7 +106,8 @@ struct K2Params {
     FastDiv fast;     // guarded approximate division (see suppresses)
     int early_out;    // iou_thres >= 0: pairs with zero intersection can never be suppressed
     float max_wh;
-    const float *head;    // L2: coefficients are rows 4+nc.. of the head
+    const void *head;     // L2: coefficients are rows 4+nc.. of the head (fp32 or bf16)
+    int head_bf16;
     const float *coeffs;  // L1: [B, nm, N]
     const float4 *cand_box;
     const float *cand_score;
@@ -552,9 +553,14 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
         const int a = P.det_anchor[(size_t)b * K + k];
         float v = 0.0f;
         if (a >= 0) {
-            const float *src = (P.layout == BT_LAYOUT_L2) ? P.head + ((size_t)b * P.C + 4 + P.nc) * P.N
-                                                          : P.coeffs + (size_t)b * P.nm * P.N;
-            v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
+            if (P.layout == BT_LAYOUT_L2 && P.head_bf16) {
+                const unsigned short *src = static_cast<const unsigned short *>(P.head) + ((size_t)b * P.C + 4 + P.nc) * P.N;
+                v = __uint_as_float((unsigned)__ldg(src + (size_t)m * P.N + a) << 16);
+            } else {
+                const float *src = (P.layout == BT_LAYOUT_L2) ? static_cast<const float *>(P.head) + ((size_t)b * P.C + 4 + P.nc) * P.N
+                                                              : P.coeffs + (size_t)b * P.nm * P.N;
+                v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
+            }
         }
         P.det_coeff[((size_t)b * K + k) * 32 + m] = v;
     }
@@ -821,7 +827,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.fast.hi = (float)((double)t * (1.0 + 1e-6));
     P.early_out = p.iou_thres >= 0.0 ? 1 : 0;
     P.max_wh = p.max_wh;
-    P.head = io.head; P.coeffs = io.coeffs;
+    P.head = io.head; P.head_bf16 = p.head_dtype == BT_HEAD_BF16; P.coeffs = io.coeffs;
     P.cand_box = w.cand_box; P.cand_score = w.cand_score; P.cand_label = w.cand_label;
     P.cand_anchor = w.cand_anchor; P.n_cand = io.n_cand; P.sort_keys = w.sort_keys;
     P.det_count = io.det_count; P.dets = io.dets; P.det_keep = io.det_keep;

@@ -6,11 +6,12 @@ from btpost import PostConfig, PostProcessor, _lib, synth
 from oracle import oracle
 
 
-def to_dev(batch, dev, gt_f32=False, proto_bf16=False):
+def to_dev(batch, dev, gt_f32=False, proto_bf16=False, head_bf16=False):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     m = batch["masks_gt"].astype(np.float32) if gt_f32 else batch["masks_gt"]
     protos = t(batch["protos"]).bfloat16() if proto_bf16 else t(batch["protos"])
-    return dict(head=t(batch["head"]), protos=protos, det_boxes_gt=t(batch["det_boxes_gt"]),
+    head = t(batch["head"]).bfloat16() if head_bf16 else t(batch["head"])
+    return dict(head=head, protos=protos, det_boxes_gt=t(batch["det_boxes_gt"]),
                 masks_gt=t(m), proj_weight=t(batch["proj_weight"]), proj_bias=float(batch["proj_bias"]))
 
 
@@ -24,10 +25,10 @@ def run_cuda(batch, dev="cuda:0", gt_f32=False, l1=False, **kw):
                      gt_mode=kw.get("gt_mode", 0), crop=bool(kw.get("crop", 1)),
                      iou_match_thresh=kw.get("iou_match_thresh", 0.5),
                      gt_mask_dtype=_lib.MASK_F32 if gt_f32 else _lib.MASK_U8, nms_threads=kw.get("nms_threads", 0),
-                     proto_bf16=bool(kw.get("proto_bf16", False)),
+                     proto_bf16=bool(kw.get("proto_bf16", False)), head_bf16=bool(kw.get("head_bf16", False)),
                      with_seg_mask=True, with_seg_logits=True, with_uni_mask=True, with_coco=True, with_seg_map=True)
     pp = PostProcessor(cfg, dev)
-    d = to_dev(batch, dev, gt_f32, bool(kw.get("proto_bf16", False)))
+    d = to_dev(batch, dev, gt_f32, bool(kw.get("proto_bf16", False)), bool(kw.get("head_bf16", False)))
     extra = {}
     if l1:
         extra = dict(maps=[torch.from_numpy(m).to(dev) for m in batch["maps"]], coeffs=torch.from_numpy(batch["coeffs"]).to(dev))

@@ -63,6 +63,18 @@ def test_bf16_prototypes(kw):
     helpers.assert_same(got, ref, 2, kw["max_det"])
 
 
+def test_bf16_head_and_prototypes():
+    """Both big inputs as bfloat16 (what the reference's bf16-mixed forward hands over): bit-exact against the oracle
+    on the rounded tensors, detections and masks alike."""
+    import torch
+    batch = helpers.make(batch=2, img_size=640, seed=42)
+    for k in ("head", "protos"):
+        batch[k] = torch.from_numpy(batch[k]).bfloat16().float().numpy()
+    ref = oracle.run_pipeline(batch)
+    got, _ = helpers.run_cuda(batch, proto_bf16=True, head_bf16=True)
+    helpers.assert_same(got, ref, 2, 300)
+
+
 def test_gt_mask_f32():
     batch = helpers.make(batch=2, img_size=640, seed=7)
     kw = dict(max_det=30)
