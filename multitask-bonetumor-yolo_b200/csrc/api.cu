@@ -185,11 +185,16 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     const int skip = g_debug_skip;
     if (!ok(cudaEventRecord(side->fork, s)) || !ok(cudaStreamWaitEvent(side->stream, side->fork, 0))) return BT_ERR_CUDA;
     if (!(skip & 1)) rc = launch_masks(*p, *io, w, side->stream, BT_MASKS_PACK);
+    else cudaMemsetAsync(w.work, 0, 32 * 32 * sizeof(int32_t), side->stream);   // ablation: the queue counters gt_pack resets
     if (rc == BT_OK && !ok(cudaEventRecord(side->pack, side->stream))) rc = BT_ERR_CUDA;
     if (rc == BT_OK && !(skip & 2)) rc = launch_decode_filter(*p, *io, w, s);
     // NMS, then the mask-stage plan on the caller's stream while the helper stream gathers the kept detections' mask
     // coefficients and runs the COCO matching (beside the mask kernels)
     if (rc == BT_OK && !(skip & 4)) rc = launch_nms_match(*p, *io, w, s, BT_NMS_SORT_SWEEP);
+    else if (rc == BT_OK) {   // ablation: the counters the NMS kernel resets for the plan
+        cudaMemsetAsync(w.pool_used, 0, sizeof(unsigned long long), s);
+        cudaMemsetAsync(w.n_items, 0, sizeof(int32_t), s);
+    }
     if (rc == BT_OK && (!ok(cudaEventRecord(side->nms, s)) || !ok(cudaStreamWaitEvent(side->stream, side->nms, 0)))) rc = BT_ERR_CUDA;
     if (rc == BT_OK && !(skip & 8)) rc = launch_nms_match(*p, *io, w, s, BT_NMS_PLAN);
     if (rc == BT_OK && !(skip & 16)) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_GATHER);

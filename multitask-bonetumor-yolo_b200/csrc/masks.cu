@@ -392,16 +392,28 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
 
     // The tile buffer is dead as soon as every thread holds its pixels in registers: the next tile's TMA is issued
     // right then and lands under this tile's arithmetic (one buffer, four CTAs per SM).
-    auto issue = [&](int tile, int buf) {   // thread 0
-        const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
-        mbar_expect_tx(&s_bar[buf], (uint32_t)(TILE_FLOATS * sizeof(float)));
-        tma_tile_g2s(s_tiles + buf * TILE_FLOATS, &tmap, tx * TA_W, ty * TA_H, b * NM, &s_bar[buf]);
+    // tile coordinates are stepped, not divided out, per tile (the divisions were a fifth of the kernel's instructions)
+    struct TileAt { int b, ty, tx; };
+    auto tile_at = [&](int tile) {
+        TileAt a;
+        a.b = tile / tiles;
+        const int t = tile - a.b * tiles;
+        a.ty = t / P.ntx; a.tx = t - a.ty * P.ntx;
+        return a;
     };
+    auto step = [&](TileAt &a) {
+        if (++a.tx == P.ntx) { a.tx = 0; if (++a.ty == P.nty) { a.ty = 0; ++a.b; } }
+    };
+    auto issue = [&](const TileAt &a, int buf) {   // thread 0
+        mbar_expect_tx(&s_bar[buf], (uint32_t)(TILE_FLOATS * sizeof(float)));
+        tma_tile_g2s(s_tiles + buf * TILE_FLOATS, &tmap, a.tx * TA_W, a.ty * TA_H, a.b * NM, &s_bar[buf]);
+    };
+    TileAt at = tile_at(t_begin), at_issue = at;   // current tile; next tile to load (thread 0)
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) mbar_init(&s_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < NBUF; ++i)
-            if (t_begin + i < t_end) issue(t_begin + i, i);
+            if (t_begin + i < t_end) { issue(at_issue, i); step(at_issue); }
     }
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
     __syncthreads();
@@ -430,9 +442,9 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     };
     Meta cur = fetch_meta(t_begin);
 
-    for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
-        const int b = tile / tiles, t = tile - b * tiles, ty = t / P.ntx, tx = t - ty * P.ntx;
-        const int R0 = ty * TA_H, C0 = tx * TA_W;
+    for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it, step(at)) {
+        const int b = at.b;
+        const int R0 = at.ty * TA_H, C0 = at.tx * TA_W;
         const int r = R0 + row, c = C0 + colp;
 
         const int nlist = cur.nlist;
@@ -468,7 +480,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
             }
         }
         __syncthreads();
-        if (tid == 0 && tile + NBUF < t_end) issue(tile + NBUF, buf);
+        if (tid == 0 && tile + NBUF < t_end) { issue(at_issue, buf); step(at_issue); }
 
         // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
         {

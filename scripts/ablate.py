@@ -13,7 +13,8 @@ dev = torch.device("cuda:0")
 d = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("head", "protos", "det_boxes_gt", "masks_gt", "proj_weight")}
 args = (d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], float(b["proj_bias"]))
 L = _lib.load()
-names = {0: "nothing", 1: "gt_pack", 2: "decode_filter", 4: "nms", 8: "plan", 16: "gather", 32: "match", 64: "contract", 128: "cells+finalize"}
+# the plan cannot be left out without starving cells_kernel of its work items
+names = {0: "nothing", 1: "gt_pack", 2: "decode_filter", 4: "nms", 16: "gather", 32: "match", 64: "contract", 128: "cells+finalize"}
 base = None
 for mask, name in names.items():
     pipe = Pipeline(PostConfig(batch=B, img_size=S), dev, depth=depth)
