@@ -193,7 +193,7 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     if (rc == BT_OK && !(skip & 4)) rc = launch_nms_match(*p, *io, w, s, BT_NMS_SORT_SWEEP);
     else if (rc == BT_OK) {   // ablation: the counters the NMS kernel resets for the plan
         cudaMemsetAsync(w.pool_used, 0, sizeof(unsigned long long), s);
-        cudaMemsetAsync(w.n_items, 0, sizeof(int32_t), s);
+        cudaMemsetAsync(w.n_items, 0, 2 * sizeof(int32_t), s);
     }
     if (rc == BT_OK && (!ok(cudaEventRecord(side->nms, s)) || !ok(cudaStreamWaitEvent(side->stream, side->nms, 0)))) rc = BT_ERR_CUDA;
     if (rc == BT_OK && !(skip & 8)) rc = launch_nms_match(*p, *io, w, s, BT_NMS_PLAN);

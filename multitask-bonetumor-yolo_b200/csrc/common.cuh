@@ -67,7 +67,7 @@ struct Workspace {
     int32_t *tile_cnt;    // [B, tiles] detections listed on each contract_kernel tile
     unsigned short *tile_list;   // [B, tiles, K]
     int2 *items;          // [item_cap] work items of cells_kernel: (image * K + detection, chunk of C_CHUNK blocks)
-    int32_t *n_items;     // [1]
+    int32_t *n_items;     // [2]: number of items; [1] = 1 when some detection found no room in the pool
     long long item_cap;
     float *pool;          // [pool_cap] logits of the detections' crop boxes, back to back
     long long pool_cap;
@@ -145,7 +145,7 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.tile_list = reinterpret_cast<unsigned short *>(take(B * (size_t)mask_tiles(p) * p->max_det * sizeof(unsigned short)));
     w.item_cap = mask_item_cap(p);
     w.items = reinterpret_cast<int2 *>(take((size_t)w.item_cap * sizeof(int2)));
-    w.n_items = reinterpret_cast<int32_t *>(take(sizeof(int32_t)));
+    w.n_items = reinterpret_cast<int32_t *>(take(2 * sizeof(int32_t)));
     w.pool_cap = mask_pool_floats(p);
     w.pool = reinterpret_cast<float *>(take((size_t)w.pool_cap * sizeof(float)));
     w.bytes = off;

@@ -76,9 +76,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 // One [NM][TA_H][TA_W] box of the [B*NM, PH, PW] prototype tensor -> shared memory.
 // The prototypes are read exactly once: L2 evict-first keeps the logit pool, the projector logits and the GT / union
 // words resident for cells_kernel instead of 210 MB of stream-through data.
-__device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *tm, int col, int row, int chan0, uint64_t *bar) {
+__device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *tm, int col, int row, int chan0, uint64_t *bar,
+                                             bool keep) {
+    // keep: some detection has no room in the logit pool, cells_kernel will contract its corners from the prototypes
     uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
             smem_u32(dst)),
@@ -392,6 +395,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
 
     // The tile buffer is dead as soon as every thread holds its pixels in registers: the next tile's TMA is issued
     // right then and lands under this tile's arithmetic (one buffer, four CTAs per SM).
+    const bool keep_protos = __ldg(P.n_items + 1) != 0;
     // tile coordinates are stepped, not divided out, per tile (the divisions were a fifth of the kernel's instructions)
     struct TileAt { int b, ty, tx; };
     auto tile_at = [&](int tile) {
@@ -406,7 +410,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     };
     auto issue = [&](const TileAt &a, int buf) {   // thread 0
         mbar_expect_tx(&s_bar[buf], (uint32_t)(TILE_FLOATS * sizeof(float)));
-        tma_tile_g2s(s_tiles + buf * TILE_FLOATS, &tmap, a.tx * TA_W, a.ty * TA_H, a.b * NM, &s_bar[buf]);
+        tma_tile_g2s(s_tiles + buf * TILE_FLOATS, &tmap, a.tx * TA_W, a.ty * TA_H, a.b * NM, &s_bar[buf], keep_protos);
     };
     TileAt at = tile_at(t_begin), at_issue = at;   // current tile; next tile to load (thread 0)
     if (tid == 0) {
@@ -706,20 +710,29 @@ __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, i
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[a][c] = 0.0f;
-            for (int ch = 0; ch < NM; ++ch) {
-                const float w = __shfl_sync(0xffffffffu, mycf, ch);
-                const size_t pc = pr0 + (size_t)ch * PH * PW;
+            if (!P.proto_bf16) {
+                const float *pr = static_cast<const float *>(P.protos) + pr0;
+                for (int ch = 0; ch < NM; ++ch) {
+                    const float w = __shfl_sync(0xffffffffu, mycf, ch);
+                    const float *pc = pr + (size_t)ch * PH * PW;
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
+                    for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (rin[a] && cin[c]) {
-                            const size_t idx = pc + rr[a] * PW + cc[c];
-                            const float x = P.proto_bf16
-                                                ? __uint_as_float((uint32_t)__ldg(static_cast<const unsigned short *>(P.protos) + idx) << 16)
-                                                : __ldg(static_cast<const float *>(P.protos) + idx);
-                            v[a][c] = __fmaf_rn(w, x, v[a][c]);
-                        }
+                        for (int c = 0; c < 3; ++c)
+                            if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(w, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
+                }
+            } else {
+                const unsigned short *pr = static_cast<const unsigned short *>(P.protos) + pr0;
+                for (int ch = 0; ch < NM; ++ch) {
+                    const float w = __shfl_sync(0xffffffffu, mycf, ch);
+                    const unsigned short *pc = pr + (size_t)ch * PH * PW;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (rin[a] && cin[c])
+                                v[a][c] = __fmaf_rn(w, __uint_as_float((uint32_t)__ldg(pc + rr[a] * PW + cc[c]) << 16), v[a][c]);
+                }
             }
         }
         const size_t o = ((size_t)b * NBY + by) * NBX + bx;

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     if (tid < 8) P.acc[b * 8 + tid] = 0;
     if (tid == 8) P.strip_done[b] = 0;
     if (tid == 10 && b == 0) *P.pool_used = 0ull;
-    if (tid == 11 && b == 0) *P.n_items = 0;
+    if (tid == 11 && b == 0) { P.n_items[0] = 0; P.n_items[1] = 0; }
     if (tid == 9 && P.seg_prob_sum) P.seg_prob_sum[b] = 0.0;
     for (int i = tid; i < K; i += K2_THREADS) {
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
@@ -629,6 +629,7 @@ __global__ void __launch_bounds__(GM_THREADS) plan_kernel(const __grid_constant_
             if (rg.x <= rg.y && rg.z <= rg.w) {
                 const long long area = (long long)(rg.y - rg.x + 1) * (rg.w - rg.z + 1);
                 if (off + area <= P.pool_cap) o = (int)off;
+                else P.n_items[1] = 1;   // cells_kernel will read prototypes itself: contract_kernel keeps them in the L2
                 off += area;
             }
             P.scr_off[(size_t)b * K + kk] = o;

@@ -5,7 +5,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path[:0] = [str(ROOT), str(ROOT / "multitask-bonetumor-yolo_b200")]
 import numpy as np, torch
-from btpost import PostConfig, PostProcessor, synth, _lib
+from btpost import Pipeline, PostConfig, PostProcessor, synth, _lib
 
 which = sys.argv[1] if len(sys.argv) > 1 else "dense"
 dev = torch.device("cuda:0")
@@ -44,3 +44,17 @@ us = timeit(pp.capture(*args, **extra))
 print(f"whole step us: {us:.1f}  -> {B / us * 1e6:.0f} images/s")
 for st in ("decode_filter", "nms_match", "masks", "masks_contract"):
     print(f"  {st:14s} us: {timeit(pp.capture(*args, stage=st, **extra)):.1f}")
+
+# the same step with four batches in flight (own workspace each)
+if len(sys.argv) > 2 and sys.argv[2] == "pipe":
+    pipe = Pipeline(PostConfig(batch=B, img_size=S, **kw), dev, depth=4).capture(*args, **extra)
+    pipe.fork()
+    for _ in range(12): pipe.replay()
+    pipe.join(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 80
+    e0.record(); pipe.fork()
+    for _ in range(n): pipe.replay()
+    pipe.join(); e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / n * 1e3
+    print(f"four batches in flight: {us:.1f} us/step -> {B / us * 1e6:.0f} images/s")
