@@ -26,6 +26,8 @@ torch.cuda.set_device(lrank)
 dev = torch.device("cuda", lrank)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+    dist.all_reduce(torch.zeros(1, device=dev))   # connect the peers now: communicator set-up is not part of the sweep
+    dist.all_gather([torch.zeros(1, device=dev) for _ in range(world)], torch.zeros(1, device=dev))
 B = args.batch
 nbatches = args.images // B
 mine = [i for i in range(nbatches) if i % world == rank]          # whole batches b = r (mod G)
