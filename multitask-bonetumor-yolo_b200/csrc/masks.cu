@@ -916,14 +916,17 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     static const char *nb_env = getenv("BTPOST_A_NBUF");   // developer switch (scripts/): tile buffers per CTA
     const int nbuf = (nb_env && !P.proto_bf16) ? atoi(nb_env) : 1;
     const size_t smem_a = (size_t)nbuf * NM * TA_H * TA_W * (P.proto_bf16 ? 2 : 4) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: one flag per device ordinal
+    static bool attr_done[64] = {};
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev >= 64) return BT_ERR_CUDA;
+    if (!attr_done[attr_dev]) {
         if (cudaFuncSetAttribute(contract_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(contract_kernel<1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(contract_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(contract_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
-        attr_set = true;
+        attr_done[attr_dev] = true;
     }
     {
         static int sm_count = 0;

@@ -875,13 +875,16 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.coco_smem_doubles = coco_doubles;
     const size_t smem_b = (size_t)coco_doubles * 8 + (size_t)p.max_det * 12;
     if (smem_b > 220 * 1024) return BT_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: one flag per device ordinal
+    static bool attr_done[64] = {};
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev >= 64) return BT_ERR_CUDA;
+    if (!attr_done[attr_dev]) {
         if (cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(nms_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
-        attr_set = true;
+        attr_done[attr_dev] = true;
     }
     if (parts & BT_NMS_SORT_SWEEP) {
         // Developer switch BTPOST_NMS_PRIO=1: launch the NMS kernel (the long pole of a step; needs whole SMs) with the
