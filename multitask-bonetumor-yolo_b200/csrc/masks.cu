@@ -8,23 +8,27 @@
 //   counters       running_main_v2.py:704-713 (tp/fp/fn/tn, DiceScore) and test_model.py:15-23
 //                  (per-image IoU / Dice with eps 1e-7)
 //
-// B200 mapping: three kernels, each bound by one resource.
+// B200 mapping: four kernels, each bound by one resource (plan_kernel in nms_match.cu prepares their work lists).
 //   gt_pack_kernel    GT mask bytes -> bits, one 64-bit word per 2x2 block of cells (a cell = the 4x4
-//                     output pixels between four neighbouring prototype pixels).  Pure streaming.
-//   contract_kernel   THE pass over the prototypes (2/3 of the path's compulsory HBM bytes): a CTA takes a
-//                     32 x 8 pixel tile of all 32 channels with ONE 3-D tensor-map TMA (128-byte swizzle),
-//                     every thread moves its two pixels x 32 channels into registers once, and then the K=32
-//                     contraction of the projector and of every detection whose crop box touches the tile is
-//                     32 packed FFMA2 per (detection, pixel pair) with the coefficients broadcast from shared
-//                     memory: no prototype re-reads, no search, sequential fp32 order (bit parity with torch).
-//                     Logits go to an L2-resident scratch (projector: [B,PH,PW]; detections: their crop boxes
-//                     back to back in a pool).  HBM-bound.
+//                     output pixels between four neighbouring prototype pixels).  Pure streaming; independent of
+//                     the detections, so btpost_run runs it on its helper stream beside decode / NMS.
+//   contract_kernel   THE pass over the prototypes (2/3 of the path's compulsory HBM bytes): persistent CTAs, 4 per
+//                     SM, each a contiguous range of 32 x 8 pixel tiles; a tile of all 32 channels arrives with ONE
+//                     3-D tensor-map TMA (128-byte swizzle; bf16 prototypes: 64-byte swizzle) with an L2 evict-first
+//                     hint, every thread moves its two pixels x 32 channels into registers, the buffer is re-armed
+//                     for the next tile at once, and the K=32 contraction of the projector and of every detection
+//                     the plan binned into the tile is 32 packed FFMA2 per (detection, pixel pair) with the
+//                     coefficients broadcast from shared memory: no prototype re-reads, no search, sequential fp32
+//                     order (bit parity with torch).  Logits go to an L2-resident scratch (projector: [B,PH,PW];
+//                     detections: their crop boxes back to back in a pool).  HBM-bound (75 % of the measured peak).
 //   cells_kernel      bilinear x4 + threshold on 2x2 cell blocks: 9 corner logits -> 64 output pixels with
 //                     packed FMUL2/FFMA2 (two pixels per instruction), the threshold as the sign bit of a
-//                     packed subtraction gathered by one funnel shift per pixel.  One warp per detection,
-//                     the union of an image's instance masks is a 64-bit RED.OR per block; the projector mask
-//                     owns its cells.  The last CTA of an image folds the counters into Dice / IoU.
-//                     Instruction-issue bound (ALU pipe).
+//                     packed subtraction gathered by one funnel shift per pixel.  Persistent warps pull (detection,
+//                     chunk of 128 blocks) items and runs of 32 projector blocks off 32 queue counters; the union of
+//                     an image's instance masks is a 64-bit atomic OR per block whose returned old word gives the
+//                     newly set bits (union counters without a pass over the union); the projector mask owns its
+//                     cells.  Instruction-issue bound.
+//   finalize_kernel   one warp per image: counters -> Dice / IoU / tp-fp-fn-tn.
 // tcgen05 is deliberately not used: K = 32 at <= 0.5 FLOP/B, and TF32/BF16 accumulation would break the bit
 // parity of the thresholded masks with the fp32 reference.
 #include <cuda.h>
