@@ -62,6 +62,16 @@ def test_argument_validation_without_gpu():
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(260), n.value, None) == -4   # misaligned workspace
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), 16, None) == -3        # workspace too small
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1   # null head
+    for field, bad in (("nms_threads", 256), ("proto_dtype", 2), ("head_dtype", 7)):          # scheduling / dtype knobs
+        setattr(p, field, bad)
+        assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1, field
+        setattr(p, field, 0)
+    p.head_dtype, p.layout = _lib.HEAD_BF16, _lib.LAYOUT_L1
+    assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -2   # bf16 raw maps: not implemented
+    p.head_dtype, p.layout = 0, _lib.LAYOUT_L2
+    assert L.btpost_masks_parts(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None, 8) == -1   # unknown part bit / null inputs
+    assert L.btpost_synth_batch(0, 640, 3, 32, None, None, None, None, None, None, None) == -1
+    assert L.btpost_synth_batch(2, 640, 3, 32, None, None, None, C.c_void_p(256), None, None, None) == -1   # head without keys / objects
     with pytest.raises(ValueError):
         _lib.check(-2, "x")
     with pytest.raises(RuntimeError):
