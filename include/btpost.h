@@ -8,7 +8,9 @@
  * Each entry point below names the reference statements it replaces.  Everything is plain C:
  * pointers, sizes, POD structs; no torch types.  All pointers are DEVICE pointers owned by the
  * caller unless stated otherwise.  The library never allocates device memory, never synchronises, and orders
- * all work on the caller's stream (CUDA-graph capturable; btpost_run forks one helper stream, see below).
+ * all work on the caller's stream (CUDA-graph capturable).  Host-side state: btpost_run borrows a helper stream
+ * + five events from a small per-device pool that is created lazily and guarded by a mutex (see btpost_run);
+ * nothing else is kept between calls.
  *
  * Return value: 0 on success, a negative BT_ERR_* otherwise (btpost_error_string decodes it).
  */
@@ -62,12 +64,16 @@ typedef struct BtParams {
     float conf_thres;         /* CONF_TH, strict >                                            */
     double iou_thres;         /* NMS_IOU (torchvision takes a double)                         */
     int32_t max_det;          /* TOP_K                                                        */
-    int32_t max_cand;         /* candidate capacity per image (Ultralytics max_nms); 0 => N   */
+    int32_t max_cand;         /* Ultralytics max_nms: when more than max_cand anchors pass the filter only the
+                                 max_cand best-scoring ones (stable: ties -> lower anchor index) enter the NMS;
+                                 0 => no limit.  n_cand still reports every anchor that passed the filter and
+                                 det_keep still indexes that full (anchor-ordered) list.                      */
     int32_t class_mode;       /* BT_CLASS_*; reference = agnostic                             */
     float max_wh;             /* class offset for BT_CLASS_OFFSET (Ultralytics 7680)          */
     int32_t clamp_boxes;      /* clamp_(0, img) after the filter (reference: 1)               */
     int32_t gt_mode;          /* BT_GT_LITERAL reproduces cat(...).view(-1,4) as shipped      */
-    int32_t max_gt;           /* GT capacity per image (<= 32)                                */
+    int32_t max_gt;           /* GT capacity per image (<= 32); rows beyond it are dropped and reported
+                                 through BtIO.gt_overflow (the reference has no limit)                       */
     int32_t num_gt_rows;      /* rows of det_boxes_gt [G_total, 6]                            */
     float iou_match_thresh;   /* anchor<->GT confusion-matrix matching threshold (0.5)        */
     int32_t crop;             /* crop instance masks to their box at prototype resolution     */
@@ -75,12 +81,16 @@ typedef struct BtParams {
     float proj_bias;          /* bias of seg_proto_projector Conv2d(nm->1,k=1)                */
     int32_t num_iou_thrs;     /* T (10 for mAP50-95, 1 for mAP50)                             */
     double iou_thrs[BT_MAX_IOU_THRS]; /* float64(fp32 linspace(0.5,0.95,10))                  */
-    int32_t image_offset;     /* global index of image 0 (for sweep records / sharding)       */
+    int32_t image_offset;     /* global index of image 0 of this batch: written into the sweep records (BtIO.sweep)
+                                 so that the AP order does not depend on the sharding                         */
     int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = default (1024), 512 (small footprint: several batches in flight), 1024 */
     int32_t proto_dtype;      /* BT_PROTO_F32 (default) or BT_PROTO_BF16: dtype of `protos`; bf16 values are widened exactly, so the
                                  results equal those of the reference on `protos.float()` (it validates under bf16-mixed) */
-    int32_t head_dtype;       /* BT_HEAD_F32 (default) or BT_HEAD_BF16: dtype of the L2 `head` (same exact widening)            */
-    int32_t reserved[4];
+    int32_t head_dtype;       /* BT_HEAD_F32 (default) or BT_HEAD_BF16: dtype of the L2 `head` / the L1 raw maps + coeffs (same exact widening) */
+    int32_t drop_gt_no_cand;  /* 1 = v2 behaviour (running_main_v2.py:797-814): an image in which no anchor passes
+                                 CONF_TH gets an EMPTY target, i.e. its GT boxes leave the mAP denominator;
+                                 0 = v3 behaviour (running_main_v3.py:541-571): the target is kept             */
+    int32_t reserved[3];
 } BtParams;
 
 /* Device buffers.  Inputs are read-only.  Any OUTPUT pointer may be NULL to skip that output
@@ -89,8 +99,8 @@ typedef struct BtParams {
 typedef struct BtIO {
     /* ---- inputs ---- */
     const void *head;           /* L2: [B, 4+nc+nm, N] fp32 or bf16 (head_dtype) (segment_preds_cat, main_modelv2.py:367) */
-    const float *maps[3];       /* L1: [B, 4*reg_max+nc, H_l, W_l], strides 8/16/32            */
-    const float *coeffs;        /* L1: mask coefficients [B, nm, N] (Segment `mc`)             */
+    const void *maps[3];        /* L1: [B, 4*reg_max+nc, H_l, W_l], strides 8/16/32; fp32 or bf16 (head_dtype) */
+    const void *coeffs;         /* L1: mask coefficients [B, nm, N] (Segment `mc`), same dtype as the maps   */
     const void *protos;         /* [B, nm, proto_h, proto_w] fp32 (or bf16: proto_dtype), 16-byte aligned */
     const float *det_boxes_gt;  /* [num_gt_rows, 6] (batch_idx, cls, cx, cy, w, h) normalised  */
     const void *masks_gt;       /* [B, 1, S, S] u8 or f32 {0,1}                                */
@@ -125,7 +135,12 @@ typedef struct BtIO {
     uint8_t *seg_mask;          /* [B, S, S] projector mask (seg_preds, running_main_v2.py:703) */
     float *seg_logits;          /* [B, S, S] upsampled projector logits (seg_logits_for_logging) */
     uint8_t *uni_mask;          /* [B, S, S] union of instance masks                           */
-    uint8_t *inst_masks;        /* [B, K, S, S] every instance mask (Ultralytics process_mask) */
+    uint8_t *inst_bits;         /* [B, K, S, S/8] every instance mask, bit-packed: bit (x & 7) of byte x >> 3 of row y
+                                   (numpy packbits, bitorder="little"); planes k >= det_count[b] are zero.
+                                   src/test_model.py:80-85 (einsum -> bilinear -> sigmoid > 0.5) with the Ultralytics
+                                   crop (BtParams.crop).  16-byte aligned                                            */
+    uint8_t *inst_masks;        /* [B, K, S, S] the same masks as bytes {0,1} (the reference's bool tensor); needs
+                                   inst_bits as well (the bytes are expanded from the bits).  16-byte aligned        */
     /* ---- COCO matching outputs (a9) ---- */
     int32_t *dt_match;          /* [B, A, T, K] matched GT index + 1, 0 = unmatched            */
     uint8_t *dt_ignore;         /* [B, A, T, K]                                                */
@@ -133,6 +148,14 @@ typedef struct BtIO {
     /* ---- optional: v3 segmentation-mAP prep (a11, src/running_main_v3.py:478-498) ---- */
     double *seg_prob_sum;       /* [B] sum of sigmoid(logit) over the projector mask's foreground pixels:
                                    score = seg_prob_sum / (|P| + 1e-6); |P|, mask IoU from seg_img3     */
+    /* ---- optional ---- */
+    int32_t *gt_rows_total;     /* [B] rows of det_boxes_gt that belong to the image BEFORE the max_gt cut: a value
+                                   above max_gt means GT rows were dropped (the host wrapper raises)     */
+    void *sweep;                /* sweep state (btpost_sweep_*): per-detection AP records, GT counts, image count and
+                                   Dice / IoU sums of this batch are appended on the device (needs dt_match, dt_ignore,
+                                   gt_ignore)                                                            */
+    const int32_t *image_base;  /* [1] optional, device: added to BtParams.image_offset when the records are written, so
+                                   that a step captured into a CUDA graph can be replayed for different batches  */
 } BtIO;
 
 /* Library / build identification. */
@@ -173,6 +196,58 @@ BTPOST_API int btpost_masks_parts(const BtParams *p, const BtIO *io, void *ws, s
  * with events, so the call is still a unit of work on `stream` and capturable into a CUDA graph; concurrent
  * btpost_run calls on the same device from several host threads are not supported. */
 BTPOST_API int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Sweep state (a9 accumulate/summarize; replaces torchmetrics MeanAveragePrecision's state lists + COCOeval.accumulate,
+ * src/running_main_v2.py:884-892, :1017-1098, src/evaluate_model.py:180-182, :291-319).
+ *
+ * Caller-owned device memory: BT_SWEEP_HEADER_I64 int64 counters followed by a ring of 32-byte per-detection records.
+ * With BtIO.sweep set, btpost_run / btpost_nms_match / btpost_masks append to it on the device (no host work per
+ * batch): match_kernel writes one record per kept detection and adds the batch's non-ignored GT counts and image
+ * count, finalize_kernel adds the per-image Dice / IoU (2^-40 fixed point, so the sums do not depend on the order of
+ * the atomics).  Every header slot is a plain sum, so shards are merged by ONE all-reduce(SUM) over the header (the
+ * metric-counter all-reduce of the north star) plus one all-gather of the records (AP needs the global score order).
+ * The caller may point BtIO.cm / seg_cnt4 / uni_cnt4 into the header's user slots so that they travel with it. */
+#define BT_SWEEP_HEADER_I64 512
+enum {
+    BT_SWEEP_N_RECORDS = 0,  /* records offered so far; the first min(n, capacity) are in the ring, the excess was
+                                dropped (the caller sized the ring too small: the host wrapper raises)    */
+    BT_SWEEP_N_IMAGES = 2,
+    BT_SWEEP_FSUM = 3,       /* [4] sum of seg dice, seg iou, uni dice, uni iou, units of 2^-40           */
+    BT_SWEEP_CAPACITY = 7,   /* ring capacity in records (set by btpost_sweep_reset; not a sum)          */
+    BT_SWEEP_NPIG = 8,       /* [BT_NUM_AREA][BT_MAX_CLASSES] non-ignored GT boxes per (area range, class) */
+    BT_SWEEP_USER = 72       /* [440] free for the caller: cm [nc*nc], seg_cnt4 [4], uni_cnt4 [4], ...    */
+};
+typedef struct BtSweepRecord {   /* one kept detection */
+    uint64_t matched;        /* bit a * T + t: matched to a GT at area range a, IoU threshold t (dt_match != 0) */
+    uint64_t ignored;        /* same indexing: COCOeval dtIgnore                                        */
+    uint32_t score_key;      /* order-preserving image of the fp32 score: ascending key = descending score */
+    uint32_t image;          /* BtParams.image_offset + index in the batch                               */
+    uint16_t rank;           /* position in the image's detection list (descending score)                */
+    uint16_t class_rank;     /* earlier detections of the same class in the image (maxDets cut)          */
+    uint8_t label;
+    uint8_t pad[3];
+} BtSweepRecord;
+
+BTPOST_API int btpost_sweep_bytes(int64_t max_records, size_t *bytes);
+/* Zeroes the header and sets the capacity (async on `stream`). */
+BTPOST_API int btpost_sweep_reset(void *sweep, int64_t max_records, void *stream);
+
+/* COCOeval.accumulate on the device: stable LSD radix sort of the records by (class, score desc, image, rank) -- the
+ * order pycocotools gets from concatenating images in order + mergesort on -score -- then, per (class, maxDet, area,
+ * IoU threshold), running tp / fp counts and the 101-point interpolated precision (right-to-left running max of
+ * tp / (tp + fp + eps), looked up at the first position whose recall reaches each recall threshold) and the final
+ * recall.  `records` [n_records] (device; reordered in place), `npig` = header slot BT_SWEEP_NPIG of the merged
+ * header (device), `rec_thrs` [num_rec] doubles (device; numpy.linspace(0, 1, 101) for COCO), `max_dets` [num_max_dets]
+ * host ints (<= 4), `num_images` bounds BtSweepRecord.image (number of radix passes).  Outputs (device, doubles, the
+ * pycocotools layout): precision [T, num_rec, nc, BT_NUM_AREA, num_max_dets], recall [T, nc, BT_NUM_AREA, num_max_dets],
+ * -1 where a class has no non-ignored GT.  `scratch` from btpost_sweep_accumulate_bytes (256-byte aligned). */
+BTPOST_API int btpost_sweep_accumulate_bytes(int64_t n_records, size_t *bytes);
+BTPOST_API int btpost_sweep_accumulate(void *records, int64_t n_records, const int64_t *npig, const double *rec_thrs,
+                                       int32_t num_rec, int32_t nc, int32_t num_iou_thrs, const int32_t *max_dets,
+                                       int32_t num_max_dets, int32_t max_det_per_image, int64_t num_images,
+                                       double *precision, double *recall, void *scratch, size_t scratch_bytes,
+                                       void *stream);
 
 #ifdef __cplusplus
 }

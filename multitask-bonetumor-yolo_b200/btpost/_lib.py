@@ -33,7 +33,8 @@ class BtParams(C.Structure):
         ("iou_match_thresh", C.c_float), ("crop", C.c_int32), ("gt_mask_dtype", C.c_int32),
         ("proj_bias", C.c_float), ("num_iou_thrs", C.c_int32),
         ("iou_thrs", C.c_double * BT_MAX_IOU_THRS),
-        ("image_offset", C.c_int32), ("nms_threads", C.c_int32), ("proto_dtype", C.c_int32), ("head_dtype", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("image_offset", C.c_int32), ("nms_threads", C.c_int32), ("proto_dtype", C.c_int32), ("head_dtype", C.c_int32),
+        ("drop_gt_no_cand", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -43,9 +44,9 @@ _IO_FIELDS = [
     "gt_count", "gt_boxes", "gt_boxes_raw", "gt_labels",
     "cm", "seg_cnt4", "uni_cnt4",
     "cm_pos", "seg_img3", "seg_dice", "seg_iou", "uni_img3", "uni_dice", "uni_iou", "inst_area", "inst_inter",
-    "seg_mask", "seg_logits", "uni_mask", "inst_masks",
+    "seg_mask", "seg_logits", "uni_mask", "inst_bits", "inst_masks",
     "dt_match", "dt_ignore", "gt_ignore",
-    "seg_prob_sum",
+    "seg_prob_sum", "gt_rows_total", "sweep", "image_base",
 ]
 
 
@@ -70,19 +71,28 @@ def load():
     L.btpost_error_string.restype = C.c_char_p
     L.btpost_error_string.argtypes = [C.c_int]
     L.btpost_workspace_bytes.argtypes = [C.POINTER(BtParams), C.POINTER(C.c_size_t)]
-    for name in ("btpost_decode_filter", "btpost_nms_match", "btpost_masks", "btpost_run", "btpost_instance_masks"):
-        if hasattr(L, name):
-            f = getattr(L, name)
-            f.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p]
-            f.restype = C.c_int
+    for name in ("btpost_decode_filter", "btpost_nms_match", "btpost_masks", "btpost_run"):
+        f = getattr(L, name)
+        f.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p]
+        f.restype = C.c_int
     L.btpost_synth_batch.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 7
     L.btpost_synth_batch.restype = C.c_int
     L.btpost_masks_parts.argtypes = [C.POINTER(BtParams), C.POINTER(BtIO), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     L.btpost_masks_parts.restype = C.c_int
+    L.btpost_sweep_bytes.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
+    L.btpost_sweep_reset.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.btpost_sweep_accumulate_bytes.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
+    L.btpost_sweep_accumulate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]
+    for name in ("btpost_sweep_bytes", "btpost_sweep_reset", "btpost_sweep_accumulate_bytes", "btpost_sweep_accumulate"):
+        getattr(L, name).restype = C.c_int
     _lib = L
     return L
 
 
+SWEEP_HEADER_I64 = 512
+SWEEP_N_RECORDS, SWEEP_N_IMAGES, SWEEP_FSUM, SWEEP_CAPACITY, SWEEP_NPIG, SWEEP_USER = 0, 2, 3, 7, 8, 72
 PROTO_F32, PROTO_BF16 = 0, 1
 HEAD_F32, HEAD_BF16 = 0, 1
 MASKS_PACK, MASKS_CONTRACT, MASKS_CELLS = 1, 2, 4   # btpost_masks_parts

@@ -14,13 +14,24 @@ Per batch the CUDA library leaves integer counters and per-detection COCO match 
     reproduced with the sort key (score desc, global image index, rank in image), so the result does
     not depend on how images were sharded.
 
-The aggregation runs as tensor ops on whatever device the state lives on (the GPU in production, the
-CPU in the gloo tests); it is epoch-end bookkeeping over a few MB, not part of the per-batch hot path.
+`SweepState` runs as tensor ops on whatever device the state lives on; it is the host-logic restatement used by
+the gloo tests on CPU and by the v3 segmentation mAP (one record per image, `btpost.segmap`).
+
+`DeviceSweep` is the production path for the detection sweep (BASELINE config 5): the CUDA library itself appends the
+per-detection records, GT counts, image count and Dice / IoU sums to a caller-owned device buffer while it processes a
+batch (`BtIO.sweep`, zero host work per batch), shards are merged by ONE all-reduce of the 4 KB header and one
+`all_gather_into_tensor` of the records, and COCOeval.accumulate runs as CUDA kernels (`btpost_sweep_accumulate`:
+radix sort + scans + 101-point lookup).
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 AREA_NAMES = ("all", "small", "medium", "large")
 
@@ -215,5 +226,168 @@ class SweepState:
             "seg_dice": float(self.fsum[0].item()) / n, "seg_iou": float(self.fsum[1].item()) / n,
             "uni_dice": float(self.fsum[2].item()) / n, "uni_iou": float(self.fsum[3].item()) / n,
             "precision": precision, "recall": recall,
+        })
+        return res
+
+
+# ======================================================================================================================
+# device-resident sweep (include/btpost.h "Sweep state")
+# ======================================================================================================================
+HDR = _lib.SWEEP_HEADER_I64
+REC_BYTES = 32
+REC_DTYPE = np.dtype([("matched", "<u8"), ("ignored", "<u8"), ("score_key", "<u4"), ("image", "<u4"), ("rank", "<u2"),
+                      ("class_rank", "<u2"), ("label", "u1"), ("pad", "u1", (3,))])
+FSUM_SCALE = float(2 ** 40)
+
+
+def summarize(precision, recall, iou_thrs, max_dets):
+    """COCOeval.summarize as torchmetrics reports it from the accumulate tables
+    precision [T, R, nc, A, M] and recall [T, nc, A, M] (numpy float64, -1 = undefined)."""
+    nc = precision.shape[2]
+
+    def mean(x):
+        x = x[x > -1]
+        return float(x.mean()) if x.size else -1.0
+
+    def thr_idx(v):
+        for i, t in enumerate(iou_thrs):
+            if abs(float(t) - v) < 1e-6:
+                return i
+        return None
+    res = {"map": mean(precision[:, :, :, 0, -1])}
+    for name, v in (("map_50", 0.5), ("map_75", 0.75)):
+        ti = thr_idx(v)
+        res[name] = mean(precision[ti, :, :, 0, -1]) if ti is not None else -1.0
+    for ai in (1, 2, 3):
+        res[f"map_{AREA_NAMES[ai]}"] = mean(precision[:, :, :, ai, -1])
+        res[f"mar_{AREA_NAMES[ai]}"] = mean(recall[:, :, ai, -1])
+    for mi, md in enumerate(max_dets):
+        res[f"mar_{md}"] = mean(recall[:, :, 0, mi])
+    res["map_per_class"] = [mean(precision[:, :, c, 0, -1]) for c in range(nc)]
+    res[f"mar_{max_dets[-1]}_per_class"] = [mean(recall[:, c, 0, -1]) for c in range(nc)]
+    return res
+
+
+@torch.no_grad()
+def merge_shards(hdr: torch.Tensor, records: torch.Tensor, group=None):
+    """Merge the shards of a sweep over `torch.distributed`: `hdr` int64 [HDR] (summed in place by ONE all-reduce: the
+    metric-counter all-reduce), `records` uint8 [capacity, 32] of which the first min(hdr[0], capacity) rows are valid
+    (one `all_gather_into_tensor`, padded to the largest shard).  Returns (n_per_rank list, records of all ranks
+    concatenated in rank order).  Device-agnostic (NCCL on the GPU box, gloo in the CPU tests)."""
+    n_local = int(min(int(hdr[_lib.SWEEP_N_RECORDS]), records.shape[0]))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [n_local], records[:n_local]
+    W = dist.get_world_size(group)
+    counts = torch.zeros(W, dtype=torch.int64, device=hdr.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([n_local], dtype=torch.int64, device=hdr.device), group=group)
+    dist.all_reduce(hdr, group=group)
+    ns = [int(v) for v in counts.tolist()]
+    cap = max(max(ns), 1)
+    if records.shape[0] >= cap:
+        send = records[:cap]
+    else:   # a smaller ring than the largest shard: pad (rows beyond n_local are never read)
+        send = torch.zeros(cap, REC_BYTES, dtype=torch.uint8, device=records.device)
+        send[:n_local] = records[:n_local]
+    allrec = torch.empty(W * cap, REC_BYTES, dtype=torch.uint8, device=records.device)
+    dist.all_gather_into_tensor(allrec, send.contiguous(), group=group)
+    merged = torch.cat([allrec[r * cap: r * cap + ns[r]] for r in range(W)]) if sum(ns) else allrec[:0]
+    return ns, merged
+
+
+def decode_records(records: torch.Tensor, T: int):
+    """uint8 [n, 32] record rows -> dict of numpy arrays (tests / debugging): matched / ignored as bool [n, A, T]."""
+    raw = records.detach().cpu().numpy().reshape(-1).view(REC_DTYPE)
+    bits = np.arange(4 * T, dtype=np.uint64)
+    unpack = lambda w: ((w[:, None] >> bits[None, :]) & np.uint64(1)).astype(bool).reshape(-1, 4, T)
+    key = raw["score_key"].astype(np.uint32)
+    asc = ~key                                                   # undo desc_key: smaller key = higher score
+    u = np.where(asc & np.uint32(0x80000000), asc & np.uint32(0x7FFFFFFF), ~asc).astype(np.uint32)
+    return {"score": u.view(np.float32), "label": raw["label"].astype(np.int64), "image": raw["image"].astype(np.int64),
+            "rank": raw["rank"].astype(np.int64), "class_rank": raw["class_rank"].astype(np.int64),
+            "matched": unpack(raw["matched"]), "ignored": unpack(raw["ignored"])}
+
+
+class DeviceSweep:
+    """Sweep state on one GPU, filled by the CUDA library (`PostProcessor.sweep = DeviceSweep(...)` or
+    `Pipeline(..., sweep=...)`).  `capacity` = records the ring can hold (one per kept detection of this rank's
+    shard; 32 bytes each)."""
+
+    def __init__(self, nc: int, iou_thrs, max_dets=(1, 10, 100), capacity: int = 1 << 20, max_det_per_image: int = 300,
+                 device="cuda:0"):
+        self.lib = _lib.load()
+        self.nc, self.iou_thrs, self.max_dets = nc, [float(t) for t in iou_thrs], tuple(int(m) for m in max_dets)
+        self.T, self.capacity, self.K = len(self.iou_thrs), int(capacity), int(max_det_per_image)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceSweep lives on a CUDA device (the records are written by the CUDA library)")
+        if not (0 < len(self.max_dets) <= 4) or nc > 16 or 4 * self.T > 64:
+            raise ValueError("DeviceSweep: at most 4 maxDets, 16 classes, 16 IoU thresholds")
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.btpost_sweep_bytes(C.c_int64(self.capacity), C.byref(nbytes)), "btpost_sweep_bytes")
+        self.buf = torch.zeros((nbytes.value + 7) // 8, dtype=torch.int64, device=self.device)   # torch allocations are 512-byte aligned
+        self.ptr = self.buf.data_ptr()
+        self.hdr = self.buf[:HDR]
+        self.records = self.buf[HDR:].view(torch.uint8)[: self.capacity * REC_BYTES].view(self.capacity, REC_BYTES)
+        u = _lib.SWEEP_USER
+        self.cm = self.hdr[u: u + nc * nc].view(nc, nc)
+        self.seg_cnt4 = self.hdr[u + 256: u + 260]
+        self.uni_cnt4 = self.hdr[u + 260: u + 264]
+        self.rec_thrs = torch.from_numpy(np.linspace(0.0, 1.0, 101)).to(self.device)
+        self._md = (C.c_int32 * len(self.max_dets))(*self.max_dets)
+        self.reset()
+
+    def counters(self):
+        """cm / seg_cnt4 / uni_cnt4 views INSIDE the header: hand them to PostProcessor / Pipeline as accumulators and
+        they are merged by the same all-reduce."""
+        return {"cm": self.cm, "seg_cnt4": self.seg_cnt4, "uni_cnt4": self.uni_cnt4}
+
+    def reset(self, stream=None):
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.btpost_sweep_reset(C.c_void_p(self.ptr), C.c_int64(self.capacity), C.c_void_p(st.cuda_stream)),
+                       "btpost_sweep_reset")
+
+    @torch.no_grad()
+    def finish(self, group=None, num_images_bound: int | None = None) -> dict:
+        """End of the sweep: merge the shards (header all-reduce + record all-gather), run COCOeval.accumulate on the
+        device and summarize.  Every rank returns the same result."""
+        n_here = int(self.hdr[_lib.SWEEP_N_RECORDS])
+        if n_here > self.capacity:
+            raise RuntimeError(f"DeviceSweep ring too small: {n_here} records offered, capacity {self.capacity}")
+        hdr = self.hdr.clone()
+        ns, rec = merge_shards(hdr, self.records, group)
+        n = int(sum(ns))
+        rec = rec.contiguous().clone() if n else rec      # the sort reorders in place: keep the ring as it was
+        n_images = int(hdr[_lib.SWEEP_N_IMAGES])
+        T, A, M, nc = self.T, 4, len(self.max_dets), self.nc
+        precision = torch.empty(T, 101, nc, A, M, dtype=torch.float64, device=self.device)
+        recall = torch.empty(T, nc, A, M, dtype=torch.float64, device=self.device)
+        sb = C.c_size_t()
+        _lib.check(self.lib.btpost_sweep_accumulate_bytes(C.c_int64(n), C.byref(sb)), "btpost_sweep_accumulate_bytes")
+        scratch = torch.empty(sb.value, dtype=torch.uint8, device=self.device)
+        npig = hdr[_lib.SWEEP_NPIG: _lib.SWEEP_NPIG + 64]
+        bound = num_images_bound if num_images_bound is not None else (int(rec[:, 20:24].contiguous().view(torch.int32).max()) + 1 if n else 1)
+        st = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.btpost_sweep_accumulate(
+                C.c_void_p(rec.data_ptr() if n else 0), C.c_int64(n), C.c_void_p(npig.data_ptr()), C.c_void_p(self.rec_thrs.data_ptr()),
+                C.c_int32(101), C.c_int32(nc), C.c_int32(T), self._md, C.c_int32(M), C.c_int32(self.K), C.c_int64(bound),
+                C.c_void_p(precision.data_ptr()), C.c_void_p(recall.data_ptr()), C.c_void_p(scratch.data_ptr()), C.c_size_t(sb.value),
+                C.c_void_p(st.cuda_stream))
+        _lib.check(rc, "btpost_sweep_accumulate")
+        pr, rcl = precision.cpu().numpy(), recall.cpu().numpy()
+        h = hdr.cpu().numpy()
+        res = summarize(pr, rcl, self.iou_thrs, self.max_dets)
+        ni = max(n_images, 1)
+        u = _lib.SWEEP_USER
+        tp, fp, fn, tn = [int(v) for v in h[u + 256: u + 260]]
+        fs = h[_lib.SWEEP_FSUM: _lib.SWEEP_FSUM + 4].astype(np.float64) / FSUM_SCALE
+        res.update({
+            "n_images": n_images, "n_records": n, "records_per_rank": ns, "cm": torch.from_numpy(h[u: u + nc * nc].reshape(nc, nc).copy()),
+            "seg_f1": 2 * tp / (2 * tp + fp + fn) if (2 * tp + fp + fn) else 0.0,
+            "seg_precision": tp / (tp + fp) if (tp + fp) else 0.0, "seg_recall": tp / (tp + fn) if (tp + fn) else 0.0,
+            "seg_accuracy": (tp + tn) / max(tp + tn + fp + fn, 1),
+            "seg_dice": float(fs[0]) / ni, "seg_iou": float(fs[1]) / ni, "uni_dice": float(fs[2]) / ni, "uni_iou": float(fs[3]) / ni,
+            "npig": h[_lib.SWEEP_NPIG: _lib.SWEEP_NPIG + 64].reshape(4, 16)[:, :nc].copy(), "precision": pr, "recall": rcl,
         })
         return res

@@ -1,6 +1,9 @@
 // C ABI of libbtpost (declared in include/btpost.h): argument validation + stage dispatch.
 #include <math.h>
 
+#include <mutex>
+#include <new>
+
 #include "common.cuh"
 
 namespace bt {
@@ -22,7 +25,6 @@ int check_params(const BtParams *p, const BtIO *io) {
     if (p->nms_threads != 0 && p->nms_threads != 512 && p->nms_threads != 1024) return BT_ERR_BAD_ARG;
     if (p->proto_dtype != BT_PROTO_F32 && p->proto_dtype != BT_PROTO_BF16) return BT_ERR_BAD_ARG;
     if (p->head_dtype != BT_HEAD_F32 && p->head_dtype != BT_HEAD_BF16) return BT_ERR_BAD_ARG;
-    if (p->head_dtype == BT_HEAD_BF16 && p->layout != BT_LAYOUT_L2) return BT_ERR_UNSUPPORTED;
     if (p->layout == BT_LAYOUT_L1) {
         if (p->reg_max <= 0 || p->reg_max > 32) return BT_ERR_UNSUPPORTED;
         if (p->img_w % 32 != 0 || p->img_h % 32 != 0) return BT_ERR_UNSUPPORTED;
@@ -59,6 +61,8 @@ static int check_stage2(const BtParams *p, const BtIO *io) {
         return BT_ERR_BAD_ARG;
     if (p->layout == BT_LAYOUT_L2 ? !io->head : !io->coeffs) return BT_ERR_BAD_ARG;
     if (io->dt_match && (!io->gt_count || !io->gt_boxes || !io->gt_labels || p->num_iou_thrs <= 0)) return BT_ERR_BAD_ARG;
+    if (io->sweep && !io->dt_match) return BT_ERR_BAD_ARG;   // the records are written by the COCO matching
+    if (io->sweep && (reinterpret_cast<uintptr_t>(io->sweep) & 15)) return BT_ERR_MISALIGNED;
     return BT_OK;
 }
 
@@ -68,32 +72,55 @@ static int check_stage3(const BtParams *p, const BtIO *io) {
         return BT_ERR_BAD_ARG;
     if (!aligned16(io->protos) || !aligned16(io->masks_gt)) return BT_ERR_MISALIGNED;
     if ((io->seg_mask && !aligned16(io->seg_mask)) || (io->uni_mask && !aligned16(io->uni_mask))) return BT_ERR_MISALIGNED;
+    if (io->inst_masks && !io->inst_bits) return BT_ERR_BAD_ARG;   // the bytes are expanded from the bits
+    if ((io->inst_bits && !aligned16(io->inst_bits)) || (io->inst_masks && !aligned16(io->inst_masks))) return BT_ERR_MISALIGNED;
     return BT_OK;
 }
 
-// One helper stream per device for btpost_run: the GT-bit packing (independent of the detections) runs beside the
-// decode / NMS kernels, which leave most SMs idle, and the COCO matching beside the mask kernels.  The helper
-// stream is forked from and joined back into the caller's stream with events, so the whole call is still ordered
-// on the caller's stream and capturable into a CUDA graph.  Calls on the same device are not re-entrant.
+// Helper streams of btpost_run: the GT-bit packing (independent of the detections) runs beside the decode / NMS
+// kernels, which leave most SMs idle, and the COCO matching beside the mask kernels.  A helper stream is forked from
+// and joined back into the caller's stream with events, so the whole call is still ordered on the caller's stream and
+// capturable into a CUDA graph.  Every call borrows a (stream, 5 events) set from a per-device pool under a mutex and
+// returns it when its launches are enqueued: concurrent calls from several host threads get distinct sets (re-entrant),
+// consecutive calls reuse one (a cudaStreamWaitEvent refers to the record that precedes it, so re-recording an
+// event afterwards is harmless).  Host-side objects only; no device memory.
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, pack = nullptr, nms = nullptr, gather = nullptr, join = nullptr;
+    SideStream *next = nullptr;
 };
-static SideStream *side_stream() {
-    static SideStream tab[64];
+static std::mutex g_side_mutex;
+static SideStream *g_side_free[64] = {};
+static SideStream *side_acquire(int *dev_out) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream &t = tab[dev];
-    if (!t.stream) {
-        if (cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking) != cudaSuccess) { t.stream = nullptr; return nullptr; }
-        cudaEvent_t *ev[5] = {&t.fork, &t.pack, &t.nms, &t.gather, &t.join};
-        for (auto e : ev)
-            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    *dev_out = dev;
+    {
+        std::lock_guard<std::mutex> lk(g_side_mutex);
+        if (SideStream *t = g_side_free[dev]) { g_side_free[dev] = t->next; t->next = nullptr; return t; }
     }
-    return &t;
+    SideStream *t = new (std::nothrow) SideStream();
+    if (!t) return nullptr;
+    bool ok = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t *ev[5] = {&t->fork, &t->pack, &t->nms, &t->gather, &t->join};
+    for (auto e : ev) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {   // do not pool a half-built set
+        for (auto e : ev) if (*e) cudaEventDestroy(*e);
+        if (t->stream) cudaStreamDestroy(t->stream);
+        delete t;
+        return nullptr;
+    }
+    return t;
+}
+static void side_release(SideStream *t, int dev) {
+    std::lock_guard<std::mutex> lk(g_side_mutex);
+    t->next = g_side_free[dev];
+    g_side_free[dev] = t;
 }
 
-int g_debug_skip = 0;   // developer tool (scripts/ablate.py): launches left out of btpost_run, see btpost_debug_skip
+#ifdef BT_DEBUG_HOOKS
+int g_debug_skip = 0;   // developer tool (scripts/ablate.py, debug build only): launches left out of btpost_run
+#endif
 
 }  // namespace bt
 
@@ -113,10 +140,13 @@ extern "C" BTPOST_API int btpost_debug_phase_cycles(unsigned long long *out48, i
 
 extern "C" {
 
-// Developer tool, not part of the product ABI (not declared in btpost.h): leave kernels out of the following
-// btpost_run calls to measure what each costs with several batches in flight (results are then stale / invalid).
+#ifdef BT_DEBUG_HOOKS
+// Developer tool of the debug build (libbtpost_dbg.so, `make dbg`); the product library does not contain it.  Leaves
+// kernels out of the following btpost_run calls to measure what each costs with several batches in flight (results
+// are then stale / invalid).
 // bits: 1 gt_pack, 2 decode_filter, 4 nms, 8 plan, 16 gather, 32 match, 64 contract, 128 cells + finalize
 BTPOST_API int btpost_debug_skip(int mask) { bt::g_debug_skip = mask; return BT_OK; }
+#endif
 
 int btpost_version(void) { return BTPOST_VERSION; }
 
@@ -178,12 +208,20 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     if (rc != BT_OK) return rc;
     Workspace w = carve(p, ws);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    SideStream *side = side_stream();
+    int dev = 0;
+    SideStream *side = side_acquire(&dev);
     if (!side) return BT_ERR_CUDA;
     auto ok = [](cudaError_t e) { return e == cudaSuccess; };
-    // fork: GT bits on the helper stream while the caller's stream decodes, filters and runs the NMS
+#ifdef BT_DEBUG_HOOKS
     const int skip = g_debug_skip;
-    if (!ok(cudaEventRecord(side->fork, s)) || !ok(cudaStreamWaitEvent(side->stream, side->fork, 0))) return BT_ERR_CUDA;
+#else
+    constexpr int skip = 0;
+#endif
+    // fork: GT bits on the helper stream while the caller's stream decodes, filters and runs the NMS
+    if (!ok(cudaEventRecord(side->fork, s)) || !ok(cudaStreamWaitEvent(side->stream, side->fork, 0))) {
+        side_release(side, dev);
+        return BT_ERR_CUDA;   // nothing was enqueued on the helper stream yet
+    }
     if (!(skip & 1)) rc = launch_masks(*p, *io, w, side->stream, BT_MASKS_PACK);
     else cudaMemsetAsync(w.work, 0, 32 * 32 * sizeof(int32_t), side->stream);   // ablation: the queue counters gt_pack resets
     if (rc == BT_OK && !ok(cudaEventRecord(side->pack, side->stream))) rc = BT_ERR_CUDA;
@@ -200,12 +238,15 @@ int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, voi
     if (rc == BT_OK && !(skip & 16)) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_GATHER);
     if (rc == BT_OK && !ok(cudaEventRecord(side->gather, side->stream))) rc = BT_ERR_CUDA;
     if (rc == BT_OK && !(skip & 32)) rc = launch_nms_match(*p, *io, w, side->stream, BT_NMS_COCO);
-    if (rc == BT_OK && !ok(cudaEventRecord(side->join, side->stream))) rc = BT_ERR_CUDA;
+    // join point of the helper stream: recorded whatever happened above (after the last launch attempt on it), so that
+    // the wait below never refers to a stale record of an earlier call and a capture never ends with an unjoined stream
+    const bool join_rec = ok(cudaEventRecord(side->join, side->stream));
+    if (rc == BT_OK && !join_rec) rc = BT_ERR_CUDA;
     if (rc == BT_OK && (!ok(cudaStreamWaitEvent(s, side->pack, 0)) || !ok(cudaStreamWaitEvent(s, side->gather, 0)))) rc = BT_ERR_CUDA;
     if (rc == BT_OK && (skip & (64 | 128)) != (64 | 128))
         rc = launch_masks(*p, *io, w, s, ((skip & 64) ? 0 : BT_MASKS_CONTRACT) | ((skip & 128) ? 0 : BT_MASKS_CELLS));
-    // join (always, so that a capture never ends with an unjoined stream)
-    if (!ok(cudaStreamWaitEvent(s, side->join, 0)) && rc == BT_OK) rc = BT_ERR_CUDA;
+    if (join_rec && !ok(cudaStreamWaitEvent(s, side->join, 0)) && rc == BT_OK) rc = BT_ERR_CUDA;
+    side_release(side, dev);
     return rc;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/btpost.h"
 
@@ -29,6 +30,14 @@ extern __device__ unsigned long long g_phase_cycles[3][16];
 
 namespace bt {
 
+// Developer switches (tile buffers, CTAs per SM, ...) exist in the debug build only (`make dbg`: -DBT_DEBUG_HOOKS);
+// the product library reads no environment variables.
+#ifdef BT_DEBUG_HOOKS
+static inline int dbg_env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+static inline int dbg_env_int(const char *, int dflt) { return dflt; }
+#endif
+
 // sigmoid(x) > 0.5 in fp32 (src/running_main_v2.py:702-703, src/test_model.py:85) holds exactly
 // for x > 1.5 * 2^-24 (pinned against torch in tests/golden/make_golden.py).
 __device__ __forceinline__ bool sigmoid_gt_half(float x) { return x > 8.940696716308594e-08f; }
@@ -55,7 +64,6 @@ struct Workspace {
     int32_t *cand_label;  // [B, cap]
     int32_t *cand_anchor; // [B, cap]
     unsigned long long *sort_keys;  // [B, cap_pow2] (only used when the list exceeds the register sort)
-    int32_t *strip_done;  // [B] strips finished per image (mask kernel)
     int32_t *acc;         // [B, 8] per-image int counters: seg inter,P,G ; uni inter,P,G
     short4 *det_region;   // [B, K] crop region of each kept detection at prototype resolution (r_lo, r_hi, c_lo, c_hi)
     int32_t *scr_off;     // [B, K] offset (floats) of the detection's crop-box logits in `pool`; -1: none (invalid / pool full)
@@ -76,7 +84,10 @@ struct Workspace {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static inline int cand_capacity(const BtParams *p) {
+// The candidate list holds every anchor that passes the filter (anchor order); BtParams.max_cand (Ultralytics max_nms)
+// limits how many of them, best score first, enter the NMS sweep.
+static inline int cand_capacity(const BtParams *p) { return p->num_anchors; }
+static inline int cand_limit(const BtParams *p) {
     return (p->max_cand > 0 && p->max_cand < p->num_anchors) ? p->max_cand : p->num_anchors;
 }
 
@@ -130,7 +141,6 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.cand_label = reinterpret_cast<int32_t *>(take(B * cap * sizeof(int32_t)));
     w.cand_anchor = reinterpret_cast<int32_t *>(take(B * cap * sizeof(int32_t)));
     w.sort_keys = reinterpret_cast<unsigned long long *>(take(B * (size_t)next_pow2((int)cap) * 8));
-    w.strip_done = reinterpret_cast<int32_t *>(take(B * sizeof(int32_t)));
     w.acc = reinterpret_cast<int32_t *>(take(B * 8 * sizeof(int32_t)));
     w.det_region = reinterpret_cast<short4 *>(take(B * (size_t)p->max_det * sizeof(short4)));
     const size_t nby = (size_t)mask_blocks(p->proto_h), nbx = (size_t)mask_blocks(p->proto_w);

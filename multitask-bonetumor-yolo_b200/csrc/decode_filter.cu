@@ -30,7 +30,7 @@ constexpr int K1_MAX_GT = 32;
 
 struct K1Params {
     const void *head;    // L2 (fp32 or bf16)
-    const float *maps[3];  // L1
+    const void *maps[3];   // L1 (fp32 or bf16)
     int lvl_off[4];      // anchor offset of each level (L1)
     int lvl_w[3];
     float lvl_stride[3];
@@ -46,7 +46,7 @@ struct K1Params {
     float4 *cand_box;
     float *cand_score;
     int32_t *cand_label, *cand_anchor, *n_cand;
-    int32_t *gt_count;
+    int32_t *gt_count, *gt_rows_total;
     float *gt_boxes, *gt_boxes_raw;
     int32_t *gt_labels;
     unsigned long long *cm;
@@ -118,7 +118,7 @@ struct L2Decoder {
             load_row(4 + c, n, s);
 #pragma unroll
             for (int i = 0; i < VEC; ++i)
-                if (s[i] > best[i]) { best[i] = s[i]; lab[i] = c; }
+                if (s[i] > best[i] || (s[i] != s[i] && best[i] == best[i])) { best[i] = s[i]; lab[i] = c; }   // torch .max: NaN is the maximum, first NaN wins
         }
     }
     __device__ __forceinline__ void boxes(int n, float (&x1)[VEC], float (&y1)[VEC], float (&x2)[VEC],
@@ -155,21 +155,26 @@ __device__ __forceinline__ float bt_expf(float x) {
 
 // ---- L1 decoder: three raw maps [4*R+nc, H, W]; DFL softmax expectation, anchors (x+.5,y+.5),
 // stride = img/W, class score = sigmoid(logit)  (running_main_v2.py:743-775, dist2bbox :97-107).
+template <bool BF16>
 struct L1DecoderBase {
-    const float *map[3];  // already offset to image b
+    const void *map[3];  // already offset to image b (fp32 or bf16 elements; bf16 is widened exactly, = .float())
     int off[4], w[3];
     float stride[3];
     int R, nc, N;
+    __device__ __forceinline__ float ld(int l, size_t i) const {
+        if (BF16) return __uint_as_float((unsigned)__ldg(static_cast<const unsigned short *>(map[l]) + i) << 16);
+        return __ldg(static_cast<const float *>(map[l]) + i);
+    }
     __device__ __forceinline__ int level(int n) const { return n >= off[2] ? 2 : (n >= off[1] ? 1 : 0); }
     __device__ __forceinline__ void scores1(int n, float (&best)[1], int (&lab)[1]) const {
         int l = level(n);
         int HW = off[l + 1] - off[l], pos = n - off[l];
-        const float *p = map[l] + (size_t)(4 * R) * HW + pos;
+        const size_t p = (size_t)(4 * R) * HW + pos;
         float b = -1.0f; int bi = 0;
         for (int c = 0; c < nc; ++c) {
-            float lg = __ldg(p + (size_t)c * HW);
+            float lg = ld(l, p + (size_t)c * HW);
             float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, bt_expf(-lg)));
-            if (c == 0 || s > b) { b = s; bi = c; }
+            if (c == 0 || s > b || (s != s && b == b)) { b = s; bi = c; }   // torch .max: NaN is the maximum, first NaN wins
         }
         best[0] = b; lab[0] = bi;
     }
@@ -182,12 +187,12 @@ struct L1DecoderBase {
         float d[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const float *p = map[l] + (size_t)(s * R) * HW + pos;
-            float m = __ldg(p);
-            for (int k = 1; k < R; ++k) { float v = __ldg(p + (size_t)k * HW); if (v > m) m = v; }
+            const size_t p = (size_t)(s * R) * HW + pos;
+            float m = ld(l, p);
+            for (int k = 1; k < R; ++k) { float v = ld(l, p + (size_t)k * HW); if (v > m) m = v; }
             float sum = 0.0f, acc = 0.0f;
             for (int k = 0; k < R; ++k) {
-                float e = bt_expf(__fsub_rn(__ldg(p + (size_t)k * HW), m));
+                float e = bt_expf(__fsub_rn(ld(l, p + (size_t)k * HW), m));
                 sum = __fadd_rn(sum, e);
                 acc = __fmaf_rn(e, (float)k, acc);
             }
@@ -201,14 +206,15 @@ struct L1DecoderBase {
     }
 };
 
-template <int VEC>
-struct L1Decoder : L1DecoderBase {
+template <int VEC, bool BF16>
+struct L1Decoder : L1DecoderBase<BF16> {
+    using Base = L1DecoderBase<BF16>;
     int astep;    // distance between the VEC anchors of a thread (interleaved mapping: consecutive lanes = consecutive anchors)
     __device__ __forceinline__ void scores(int n, float (&best)[VEC], int (&lab)[VEC]) const {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float b1[1] = {0.0f}; int l1[1] = {0};
-            if (n + i * astep < N) scores1(n + i * astep, b1, l1);
+            if (n + i * astep < Base::N) Base::scores1(n + i * astep, b1, l1);
             best[i] = b1[0]; lab[i] = l1[0];
         }
     }
@@ -216,7 +222,7 @@ struct L1Decoder : L1DecoderBase {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float a[1] = {0.0f}, b[1] = {0.0f}, c[1] = {0.0f}, d[1] = {0.0f};
-            if (n + i * astep < N) boxes1(n + i * astep, a, b, c, d);
+            if (n + i * astep < Base::N) Base::boxes1(n + i * astep, a, b, c, d);
             x1[i] = a[0]; y1[i] = b[0]; x2[i] = c[0]; y2[i] = d[0];
         }
     }
@@ -303,7 +309,10 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
         }
         if (rank == 0) {
             for (int i = tid; i < G; i += nthreads) P.gt_labels[(size_t)b * P.max_gt + i] = s_gl[i];
-            if (tid == 0) P.gt_count[b] = G;
+            if (tid == 0) {
+                P.gt_count[b] = G;
+                if (P.gt_rows_total) P.gt_rows_total[b] = base;   // before the max_gt cut: the host raises when it is larger
+            }
         }
         __syncthreads();
     }
@@ -430,15 +439,15 @@ decode_filter_l2_kernel(const __grid_constant__ K1Params P) {
 // MAXT = 320: four anchors per thread in blocks small enough for 4 CTAs per SM, so the whole batch is one wave
 // and the DFL arithmetic (64 exp per anchor) has ~36 warps per SM to hide behind (r02: one anchor per thread in
 // 1056-thread blocks ran at 1 CTA per SM in 3.5 waves, 180 us).
-template <int VEC, int MAXT>
+template <int VEC, int MAXT, bool BF16 = false>
 __global__ void __cluster_dims__(K1_CLUSTER, 1, 1) __launch_bounds__(MAXT, MAXT <= 320 ? 4 : 1)
 decode_filter_l1_kernel(const __grid_constant__ K1Params P) {
     const int b = blockIdx.y;
-    L1Decoder<VEC> dec;
+    L1Decoder<VEC, BF16> dec;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         int HW = P.lvl_off[l + 1] - P.lvl_off[l];
-        dec.map[l] = P.maps[l] + (size_t)b * P.C * HW;
+        dec.map[l] = static_cast<const char *>(P.maps[l]) + (size_t)b * P.C * HW * (BF16 ? 2 : 4);
         dec.off[l] = P.lvl_off[l];
         dec.w[l] = P.lvl_w[l];
         dec.stride[l] = P.lvl_stride[l];
@@ -466,7 +475,7 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
     P.gt_mode = p.gt_mode; P.max_gt = p.max_gt; P.cm_thr = p.iou_match_thresh;
     P.cand_box = w.cand_box; P.cand_score = w.cand_score; P.cand_label = w.cand_label;
     P.cand_anchor = w.cand_anchor; P.n_cand = io.n_cand;
-    P.gt_count = io.gt_count; P.gt_boxes = io.gt_boxes; P.gt_boxes_raw = io.gt_boxes_raw;
+    P.gt_count = io.gt_count; P.gt_rows_total = io.gt_rows_total; P.gt_boxes = io.gt_boxes; P.gt_boxes_raw = io.gt_boxes_raw;
     P.gt_labels = io.gt_labels;
     P.cm = reinterpret_cast<unsigned long long *>(io.cm); P.cm_pos = io.cm_pos;
     auto block_for = [&](int vecw) {
@@ -503,7 +512,14 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
             off += W * H;
         }
         P.lvl_off[3] = off;
-        if (block_for(4) <= 320) decode_filter_l1_kernel<4, 320><<<grid, dim3(block_for(4)), 0, s>>>(P);
+        const bool bf16 = p.head_dtype == BT_HEAD_BF16;   // raw maps of a bf16-mixed forward (running_main_v2.py:1324)
+        if (bf16) {
+            if (block_for(4) <= 320) decode_filter_l1_kernel<4, 320, true><<<grid, dim3(block_for(4)), 0, s>>>(P);
+            else if (block_for(1) <= K1_MAX_THREADS) decode_filter_l1_kernel<1, K1_MAX_THREADS, true><<<grid, dim3(block_for(1)), 0, s>>>(P);
+            else if (block_for(2) <= K1_MAX_THREADS) decode_filter_l1_kernel<2, K1_MAX_THREADS, true><<<grid, dim3(block_for(2)), 0, s>>>(P);
+            else if (block_for(4) <= K1_MAX_THREADS) decode_filter_l1_kernel<4, K1_MAX_THREADS, true><<<grid, dim3(block_for(4)), 0, s>>>(P);
+            else return BT_ERR_UNSUPPORTED;
+        } else if (block_for(4) <= 320) decode_filter_l1_kernel<4, 320><<<grid, dim3(block_for(4)), 0, s>>>(P);
         else if (block_for(1) <= K1_MAX_THREADS) decode_filter_l1_kernel<1, K1_MAX_THREADS><<<grid, dim3(block_for(1)), 0, s>>>(P);
         else if (block_for(2) <= K1_MAX_THREADS) decode_filter_l1_kernel<2, K1_MAX_THREADS><<<grid, dim3(block_for(2)), 0, s>>>(P);
         else if (block_for(4) <= K1_MAX_THREADS) decode_filter_l1_kernel<4, K1_MAX_THREADS><<<grid, dim3(block_for(4)), 0, s>>>(P);

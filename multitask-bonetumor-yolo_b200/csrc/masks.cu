@@ -65,8 +65,11 @@ struct K3Params {
     long long *seg_cnt4, *uni_cnt4, *seg_img3, *uni_img3;
     float *seg_dice, *seg_iou, *uni_dice, *uni_iou;
     uint8_t *seg_mask, *uni_mask;
+    uint32_t *inst_bits;    // [B, K, S_h, S_w / 32] optional: every instance mask, bit-packed (zeroed before cells_kernel)
+    uint8_t *inst_masks;    // [B, K, S_h, S_w] optional: the same as bytes, expanded from inst_bits
     float *seg_logits;
     double *seg_prob_sum;   // [B] optional: sum of sigmoid(logit) over the projector mask's foreground pixels
+    long long *sweep;       // optional sweep state: per-image Dice / IoU are added to its header (2^-40 fixed point)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -661,6 +664,30 @@ __device__ __forceinline__ void m1_item(const K3Params &P, int b, int q, int lan
     }
 }
 
+// Optional output: the block's 8 x 8 pixels into the detection's bit-packed plane (zeroed beforehand).  A block row is
+// 8 pixels starting at x = 8bx - 2 (6 pixels at x = 0 for bx = 0), so it shares its 32-bit word with the neighbouring
+// blocks: fire-and-forget atomic ORs (RED) into the L2.  Pixels outside the image are already masked out of `bits`.
+__device__ __forceinline__ void scatter_block_bits(const K3Params &P, int bk, int by, int bx, u64 bits) {
+    const int wpr = P.S_w >> 5;
+    uint32_t *plane = P.inst_bits + (size_t)bk * P.S_h * wpr;
+    const int xb = bx ? 8 * bx - 2 : 0, sh = xb & 31;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int ci = 2 * by - 1 + a, ybase = ci < 0 ? 0 : 4 * ci + 2;
+        const unsigned cellA = (unsigned)(bits >> (32 * a)) & 0xffffu, cellB = (unsigned)(bits >> (32 * a + 16)) & 0xffffu;
+        if (!(cellA | cellB)) continue;
+#pragma unroll
+        for (int ry = 0; ry < 4; ++ry) {
+            const unsigned nA = (cellA >> (4 * ry)) & 0xfu, nB = (cellB >> (4 * ry)) & 0xfu;
+            const unsigned row8 = bx ? (nA | (nB << 4)) : (nA | (nB << 2));   // bx = 0: the border cell holds 2 pixels
+            if (!row8) continue;
+            uint32_t *w = plane + (size_t)(ybase + ry) * wpr + (xb >> 5);
+            atomicOr(w, row8 << sh);
+            if (sh > 24 && (row8 >> (32 - sh))) atomicOr(w + 1, row8 >> (32 - sh));   // never past the row: those pixels are masked out
+        }
+    }
+}
+
 // One item of a detection: blocks [chunk * C_CHUNK, (chunk + 1) * C_CHUNK) of its crop box (the plan lists them).
 __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, int lane) {
     const int PH = P.PH, PW = P.PW, K = P.K, NBX = P.NBX, NBY = P.NBY;
@@ -743,6 +770,7 @@ __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, i
         const u64 gtw = __ldg(P.gtc + o);   // with the corner loads, not behind the arithmetic
         if (!act) continue;
         const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, P.S_h, P.S_w);
+        if (bits && P.inst_bits) scatter_block_bits(P, bk, by, bx, bits);
         if (bits) {
             // the OR is serialised per word in the L2: the bits that were not set before are counted exactly once
             // over all detections, so the union's counters need no pass over the union afterwards
@@ -789,8 +817,15 @@ __device__ __forceinline__ void finalize_image(const K3Params &P, int b, int lan
             atomicAdd((unsigned long long *)&cnt4[3], (unsigned long long)(total - pp - gsum + inter));
         }
         const float fi = (float)inter, fu = (float)(pp + gsum - inter);
-        if (iou) iou[b] = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
-        if (dice) dice[b] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gsum), 1e-7f));
+        const float v_iou = __fdiv_rn(__fadd_rn(fi, 1e-7f), __fadd_rn(fu, 1e-7f));
+        const float v_dice = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, fi), 1e-7f), __fadd_rn(__fadd_rn((float)pp, (float)gsum), 1e-7f));
+        if (iou) iou[b] = v_iou;
+        if (dice) dice[b] = v_dice;
+        if (P.sweep) {   // order-independent sums: 2^-40 fixed point (the values are in [0, 1])
+            unsigned long long *fs = reinterpret_cast<unsigned long long *>(P.sweep + BT_SWEEP_FSUM + 2 * lane);
+            atomicAdd(fs, (unsigned long long)__double2ll_rn((double)v_dice * 1099511627776.0));
+            atomicAdd(fs + 1, (unsigned long long)__double2ll_rn((double)v_iou * 1099511627776.0));
+        }
     }
 }
 
@@ -859,6 +894,24 @@ __global__ void __launch_bounds__(C_THREADS) union_dense_kernel(const __grid_con
     }
 }
 
+// optional dense output: bit-packed instance masks -> bytes {0,1}; one 32-pixel word per thread, 32 contiguous bytes out
+__global__ void __launch_bounds__(C_THREADS) inst_dense_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ out,
+                                                               size_t nwords) {
+    for (size_t i = (size_t)blockIdx.x * C_THREADS + threadIdx.x; i < nwords; i += (size_t)gridDim.x * C_THREADS) {
+        const uint32_t w = __ldg(bits + i);
+        uint4 o[2];
+        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t n = (w >> (4 * j)) & 0xfu;   // 4 pixels -> 4 bytes
+            ow[j] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(out + i * 32);
+        __stcs(dst, o[0]);
+        __stcs(dst + 1, o[1]);
+    }
+}
+
 // 3-D tensor map of the prototypes: dims (fastest first) {PW, PH, B*NM}, box {TA_W, TA_H, NM}, 128-byte swizzle.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -878,8 +931,7 @@ static int make_proto_tmap(CUtensorMap *tm, const void *protos, int bf16, int B,
     const cuuint64_t gstride[2] = {(cuuint64_t)PW * esz, (cuuint64_t)PW * PH * esz};
     const cuuint32_t box[3] = {(cuuint32_t)TA_W, (cuuint32_t)TA_H, (cuuint32_t)NM};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    static const char *pe = getenv("BTPOST_A_PROMO");   // developer switch (scripts/): L2 promotion of the prototype loads
-    const int pv = pe ? atoi(pe) : 0;   // measured: no promotion 47.7 us, 128 B 48.0 us, 256 B 50.5 us
+    const int pv = dbg_env_int("BTPOST_A_PROMO", 0);   // debug build: L2 promotion (measured: none 47.7 us, 128 B 48.0, 256 B 50.5)
     const CUtensorMapL2promotion promo = pv == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                        : pv == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(protos),
@@ -903,7 +955,8 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.seg_img3 = (long long *)io.seg_img3; P.uni_img3 = (long long *)io.uni_img3;
     P.seg_dice = io.seg_dice; P.seg_iou = io.seg_iou; P.uni_dice = io.uni_dice; P.uni_iou = io.uni_iou;
     P.seg_mask = io.seg_mask; P.uni_mask = io.uni_mask; P.seg_logits = io.seg_logits;
-    P.seg_prob_sum = io.seg_prob_sum;
+    P.seg_prob_sum = io.seg_prob_sum; P.sweep = static_cast<long long *>(io.sweep);
+    P.inst_bits = reinterpret_cast<uint32_t *>(io.inst_bits); P.inst_masks = io.inst_masks;
     if (p.proto_w % (P.proto_bf16 ? 8 : 4) != 0) return BT_ERR_UNSUPPORTED;   // 16-byte global strides for the tensor map
     P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
     P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
@@ -917,8 +970,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         gt_pack_kernel<<<dim3((P.NBY + G_ROWS - 1) / G_ROWS, p.batch), G_THREADS, smem_g, s>>>(P);
     }
 
-    static const char *nb_env = getenv("BTPOST_A_NBUF");   // developer switch (scripts/): tile buffers per CTA
-    const int nbuf = (nb_env && !P.proto_bf16) ? atoi(nb_env) : 1;
+    const int nbuf = P.proto_bf16 ? 1 : dbg_env_int("BTPOST_A_NBUF", 1);   // debug build: tile buffers per CTA
     const size_t smem_a = (size_t)nbuf * NM * TA_H * TA_W * (P.proto_bf16 ? 2 : 4) + 1024;
     // function attributes are per device: one flag per device ordinal
     static bool attr_done[64] = {};
@@ -933,15 +985,13 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         attr_done[attr_dev] = true;
     }
     {
-        static int sm_count = 0;
-        if (!sm_count) {
-            int dev = 0;
-            if (cudaGetDevice(&dev) != cudaSuccess ||
-                cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
-                return BT_ERR_CUDA;
-        }
-        static const char *ca_env = getenv("BTPOST_A_CTAS"), *cc_env = getenv("BTPOST_C_CTAS");   // developer switches: CTAs per SM
-        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * (ca_env ? atoi(ca_env) : nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
+        static int sm_count_dev[64] = {};   // per device ordinal, like the attribute flags above
+        if (!sm_count_dev[attr_dev] &&
+            (cudaDeviceGetAttribute(&sm_count_dev[attr_dev], cudaDevAttrMultiProcessorCount, attr_dev) != cudaSuccess ||
+             sm_count_dev[attr_dev] <= 0))
+            return BT_ERR_CUDA;
+        const int sm_count = sm_count_dev[attr_dev];
+        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * dbg_env_int("BTPOST_A_CTAS", nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
         const int grid_a = ntiles < cta_a ? ntiles : cta_a;
         if (parts & BT_MASKS_CONTRACT) {
             if (P.proto_bf16) contract_kernel<1, 4, true><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
@@ -950,12 +1000,18 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
         }
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);   // grid sizing only: the kernel reads the real count
-        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * (cc_env ? atoi(cc_env) : 7);
+        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * dbg_env_int("BTPOST_C_CTAS", 7);
         if (parts & BT_MASKS_CELLS) {
             const long long ctas = want < cap ? want : cap;
             P.nq = 1;   // queues: a power of two <= warps in the grid (every queue needs a home warp), at most C_NQ
             while (P.nq * 2 <= C_NQ && P.nq * 2 <= ctas * C_WARPS) P.nq *= 2;
+            const size_t inst_words = (size_t)p.batch * p.max_det * p.img_h * (p.img_w / 32);
+            if (io.inst_bits && cudaMemsetAsync(io.inst_bits, 0, inst_words * 4, s) != cudaSuccess) return BT_ERR_CUDA;
             cells_kernel<<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            if (io.inst_bits && io.inst_masks) {
+                const size_t want_d = (inst_words + C_THREADS - 1) / C_THREADS, cap_d = (size_t)sm_count * 16;
+                inst_dense_kernel<<<(unsigned)(want_d < cap_d ? want_d : cap_d), C_THREADS, 0, s>>>(P.inst_bits, io.inst_masks, inst_words);
+            }
             finalize_kernel<<<(p.batch + C_THREADS / 32 - 1) / (C_THREADS / 32), C_THREADS, 0, s>>>(P);
             if (io.uni_mask) union_dense_kernel<<<p.batch, C_THREADS, 0, s>>>(P);
         }

@@ -101,14 +101,14 @@ __device__ __forceinline__ double bb_iou(const double *d, const double *g) {
 
 
 struct K2Params {
-    int N, nc, nm, C, cap, cap_pow2, max_det, max_gt, class_mode, layout;
+    int N, nc, nm, C, cap, cap_pow2, limit, max_det, max_gt, class_mode, layout;   // limit: BtParams.max_cand (best-scoring candidates that enter the sweep)
     float thr_up;     // smallest float f with (double)f > iou_thres:  (double)ovr > thr  <=>  ovr >= thr_up
     FastDiv fast;     // guarded approximate division (see suppresses)
     int early_out;    // iou_thres >= 0: pairs with zero intersection can never be suppressed
     float max_wh;
     const void *head;     // L2: coefficients are rows 4+nc.. of the head (fp32 or bf16)
     int head_bf16;
-    const float *coeffs;  // L1: [B, nm, N]
+    const void *coeffs;   // L1: [B, nm, N] (fp32, or bf16 with the maps)
     const float4 *cand_box;
     const float *cand_score;
     const int32_t *cand_label, *cand_anchor, *n_cand;
@@ -127,7 +127,7 @@ struct K2Params {
     int32_t *dt_match;
     uint8_t *dt_ignore, *gt_ignore;
     // accumulators of the mask kernel, zeroed here
-    int32_t *strip_done, *acc, *inst_area, *inst_inter;
+    int32_t *acc, *inst_area, *inst_inter;
     double *seg_prob_sum;
     int region0_bytes;    // shared region 0: list of candidate indices in NMS order
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
@@ -137,6 +137,9 @@ struct K2Params {
     int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
     int gx, gy; float inv_cw, inv_ch;   // centre-cell grid
     int coco_smem_doubles;
+    long long *sweep;     // optional sweep state (header + record ring, include/btpost.h)
+    int image_offset, drop_gt_no_cand;
+    const int32_t *image_base;
 };
 
 // =================================================================================================
@@ -257,7 +260,6 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     BT_PHASE_INIT();
     // zero the per-image accumulators the mask kernel adds into
     if (tid < 8) P.acc[b * 8 + tid] = 0;
-    if (tid == 8) P.strip_done[b] = 0;
     if (tid == 10 && b == 0) *P.pool_used = 0ull;
     if (tid == 11 && b == 0) { P.n_items[0] = 0; P.n_items[1] = 0; }
     if (tid == 9 && P.seg_prob_sum) P.seg_prob_sum[b] = 0.0;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     if (tid < MAX_CELLS) { s_cellhead[tid] = -1; s_celltail[tid] = -1; }
     if (tid >= 1 && tid < NMS_CHUNK)
         for (int i = 0; i < tid; ++i) s_pair[tid * (tid - 1) / 2 + i] = (unsigned short)((i << 8) | tid);
-    const int M = P.n_cand[b];
+    const int M_all = P.n_cand[b];
     const float4 *cbox = P.cand_box + (size_t)b * P.cap;
     const float *cscore = P.cand_score + (size_t)b * P.cap;
     const int32_t *clabel = P.cand_label + (size_t)b * P.cap;
@@ -278,22 +280,22 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     const unsigned long long *gkeys = nullptr;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        if (K2_THREADS == 512 && M <= 512) sort_to_smem<1>(cscore, M, 512, s_x, s_sidx);
-        else if (K2_THREADS == 512 && M <= 1024) sort_to_smem<2>(cscore, M, 512, s_x, s_sidx);
-        else if (K2_THREADS == 512 && M <= 2048) sort_to_smem<4>(cscore, M, 512, s_x, s_sidx);
-        else if (K2_THREADS == 512 && M <= SORT_SMALL_MAX) sort_to_smem<8>(cscore, M, 512, s_x, s_sidx);
-        else if (K2_THREADS == 1024 && M <= 1024) sort_to_smem<1>(cscore, M, 1024, s_x, s_sidx);
-        else if (K2_THREADS == 1024 && M <= 2048) sort_to_smem<2>(cscore, M, 1024, s_x, s_sidx);
-        else if (K2_THREADS == 1024 && M <= 4096) sort_to_smem<4>(cscore, M, 1024, s_x, s_sidx);
-        else if (K2_THREADS == 1024 && M <= 8192) sort_to_smem<16>(cscore, M, 512, s_x, s_sidx);
-        else if (K2_THREADS == 1024 && M <= SORT_REG_MAX) sort_to_smem<16>(cscore, M, 1024, s_x, s_sidx);
+        if (K2_THREADS == 512 && M_all <= 512) sort_to_smem<1>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= 1024) sort_to_smem<2>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= 2048) sort_to_smem<4>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= SORT_SMALL_MAX) sort_to_smem<8>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 1024) sort_to_smem<1>(cscore, M_all, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 2048) sort_to_smem<2>(cscore, M_all, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 4096) sort_to_smem<4>(cscore, M_all, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 8192) sort_to_smem<16>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= SORT_REG_MAX) sort_to_smem<16>(cscore, M_all, 1024, s_x, s_sidx);
         else {
             // very long lists (30k-candidate stress case): bitonic network in global memory
             int P2 = 1;
-            while (P2 < M) P2 <<= 1;
+            while (P2 < M_all) P2 <<= 1;
             unsigned long long *keys = P.sort_keys + (size_t)b * P.cap_pow2;
             for (int i = tid; i < P2; i += K2_THREADS)
-                keys[i] = (i < M) ? (((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)i) : ~0ull;
+                keys[i] = (i < M_all) ? (((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)i) : ~0ull;
             __syncthreads();
             for (int k = 2; k <= P2; k <<= 1)
                 for (int j = k >> 1; j > 0; j >>= 1) {
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
         }
     }
     BT_PHASE_MARK(1, 0);   // sort
+    const int M = min(M_all, P.limit);   // Ultralytics max_nms: only the best `limit` candidates enter the sweep
 
     auto cell_x = [&](float x) { return min(max(__float2int_rd(__fmul_rn(x, P.inv_cw)), 0), P.gx - 1); };
     auto cell_y = [&](float y) { return min(max(__float2int_rd(__fmul_rn(y, P.inv_ch)), 0), P.gy - 1); };
@@ -553,12 +556,14 @@ __global__ void __launch_bounds__(GM_THREADS) coeff_gather_kernel(const __grid_c
         const int a = P.det_anchor[(size_t)b * K + k];
         float v = 0.0f;
         if (a >= 0) {
-            if (P.layout == BT_LAYOUT_L2 && P.head_bf16) {
-                const unsigned short *src = static_cast<const unsigned short *>(P.head) + ((size_t)b * P.C + 4 + P.nc) * P.N;
+            if (P.head_bf16) {
+                const unsigned short *src = (P.layout == BT_LAYOUT_L2)
+                                                ? static_cast<const unsigned short *>(P.head) + ((size_t)b * P.C + 4 + P.nc) * P.N
+                                                : static_cast<const unsigned short *>(P.coeffs) + (size_t)b * P.nm * P.N;
                 v = __uint_as_float((unsigned)__ldg(src + (size_t)m * P.N + a) << 16);
             } else {
                 const float *src = (P.layout == BT_LAYOUT_L2) ? static_cast<const float *>(P.head) + ((size_t)b * P.C + 4 + P.nc) * P.N
-                                                              : P.coeffs + (size_t)b * P.nm * P.N;
+                                                              : static_cast<const float *>(P.coeffs) + (size_t)b * P.nm * P.N;
                 v = __ldg(src + (size_t)m * P.N + a);   // nm == 32 (validated by check_params)
             }
         }
@@ -697,12 +702,16 @@ __global__ void __launch_bounds__(GM_THREADS) match_kernel(const __grid_constant
     int *s_dl = reinterpret_cast<int *>(s_db + P.coco_smem_doubles);   // [K] det labels
     int *s_can = s_dl + K;                                              // [K] 1 if the det can match at the loosest threshold
     int *s_list = s_can + K;                                            // [K] compacted list of those dets
+    // [K] match bits per detection (bit a * T + t) and "matched to an ignored GT" bits, for the sweep records
+    unsigned long long *s_mbits = reinterpret_cast<unsigned long long *>(s_list + K + (K & 1));
+    unsigned long long *s_gibits = s_mbits + K;
     __shared__ int s_gl[32];
     __shared__ unsigned s_gign[BT_NUM_AREA];
     __shared__ int s_warpcnt[GM_THREADS / 32];
     __shared__ int s_nlist;
 
     for (int k = tid; k < D; k += GM_THREADS) {
+        s_mbits[k] = 0ull; s_gibits[k] = 0ull;
         const float *o = P.dets + ((size_t)b * K + k) * 6;
         s_db[k * 4 + 0] = (double)o[0];
         s_db[k * 4 + 1] = (double)o[1];
@@ -809,16 +818,69 @@ __global__ void __launch_bounds__(GM_THREADS) match_kernel(const __grid_constant
                 size_t o = (((size_t)b * BT_NUM_AREA + a) * T + t) * K + d;
                 P.dt_match[o] = m + 1;
                 if (P.dt_ignore) P.dt_ignore[o] = (gign >> m) & 1u;
+                if (P.sweep) {
+                    atomicOr(&s_mbits[d], 1ull << tid);
+                    if ((gign >> m) & 1u) atomicOr(&s_gibits[d], 1ull << tid);
+                }
             }
         }
     }
     BT_PHASE_MARK(1, 7);   // COCO matching
+    // ---- sweep records (a9): what torchmetrics keeps per image for COCOeval.accumulate, appended on the device
+    if (P.sweep) {
+        __syncthreads();
+        long long *hdr = P.sweep;
+        BtSweepRecord *ring = reinterpret_cast<BtSweepRecord *>(hdr + BT_SWEEP_HEADER_I64);
+        __shared__ long long s_rbase, s_rcap;
+        if (tid == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(hdr + BT_SWEEP_N_IMAGES), 1ull);
+            s_rbase = D ? (long long)atomicAdd(reinterpret_cast<unsigned long long *>(hdr + BT_SWEEP_N_RECORDS), (unsigned long long)D) : 0;
+            s_rcap = hdr[BT_SWEEP_CAPACITY];
+        }
+        // non-ignored GT per (area range, class); v2 drops the target of an image without candidates (running_main_v2.py:797-814)
+        if (!(P.drop_gt_no_cand && P.n_cand[b] == 0)) {
+            for (int q = tid; q < BT_NUM_AREA * P.nc; q += GM_THREADS) {
+                const int a = q / P.nc, c = q - a * P.nc;
+                int cnt = 0;
+                for (int g = 0; g < G; ++g) cnt += (s_gl[g] == c && !((s_gign[a] >> g) & 1u)) ? 1 : 0;
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long *>(hdr + BT_SWEEP_NPIG + a * BT_MAX_CLASSES + c), (unsigned long long)cnt);
+            }
+        }
+        __syncthreads();
+        const unsigned long long tmask = (T >= 16) ? 0xffffull : ((1ull << T) - 1ull);
+        for (int d = tid; d < D; d += GM_THREADS) {
+            const long long pos = s_rbase + d;
+            if (pos >= s_rcap) continue;   // ring full: reported through the header (N_RECORDS > CAPACITY)
+            const int lab = s_dl[d];
+            int cr = 0;
+            for (int j = 0; j < d; ++j) cr += (s_dl[j] == lab) ? 1 : 0;
+            const double ar = s_db[d * 4 + 2] * s_db[d * 4 + 3];
+            unsigned long long amask = 0ull;   // unmatched detections outside the area range are ignored
+#pragma unroll
+            for (int a = 0; a < BT_NUM_AREA; ++a)
+                if (ar < area_lo[a] || ar > area_hi[a]) amask |= tmask << (a * T);
+            const unsigned long long mb = s_mbits[d];
+            BtSweepRecord r;
+            r.matched = mb;
+            r.ignored = s_gibits[d] | (~mb & amask);
+            r.score_key = desc_key(P.dets[((size_t)b * K + d) * 6 + 4]);
+            r.image = (uint32_t)(P.image_offset + (P.image_base ? __ldg(P.image_base) : 0) + b);
+            r.rank = (uint16_t)d;
+            r.class_rank = (uint16_t)cr;
+            r.label = (uint8_t)lab;
+            r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            uint4 *dst = reinterpret_cast<uint4 *>(ring + pos);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
+    }
 }
 
 int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cudaStream_t s, int parts) {
     K2Params P{};
     P.N = p.num_anchors; P.nc = p.nc; P.nm = p.nm; P.C = 4 + p.nc + p.nm;
-    P.cap = cand_capacity(&p); P.cap_pow2 = next_pow2(P.cap);
+    P.cap = cand_capacity(&p); P.cap_pow2 = next_pow2(P.cap); P.limit = cand_limit(&p);
     P.max_det = p.max_det; P.max_gt = p.max_gt; P.class_mode = p.class_mode; P.layout = p.layout;
     float t = (float)p.iou_thres;
     if (!((double)t > p.iou_thres)) t = nextafterf(t, INFINITY);
@@ -837,8 +899,9 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.T = p.num_iou_thrs;
     for (int i = 0; i < p.num_iou_thrs; ++i) P.thrs[i] = p.iou_thrs[i];
     P.dt_match = io.dt_match; P.dt_ignore = io.dt_ignore; P.gt_ignore = io.gt_ignore;
-    P.strip_done = w.strip_done; P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
+    P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_prob_sum = io.seg_prob_sum;
+    P.sweep = static_cast<long long *>(io.sweep); P.image_offset = p.image_offset; P.drop_gt_no_cand = p.drop_gt_no_cand; P.image_base = io.image_base;
     P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
     P.crop = p.crop; P.PW = p.proto_w; P.PH = p.proto_h;
     P.rx = (float)((double)p.proto_w / (double)p.img_w);
@@ -860,8 +923,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     // the mask kernels of other batches in flight, or for a second image (btpost.Pipeline asks for it: +8 % images/s
     // with six batches in flight, but a single step is 11 us slower).  The 1024-thread variant (default) also sorts
     // long candidate lists in registers; the small one falls back to the global-memory network above 4096 candidates.
-    static const char *nt_env = getenv("BTPOST_NMS_NT");
-    const int nt_req = p.nms_threads ? p.nms_threads : nt_env ? atoi(nt_env) : 1024;
+    const int nt_req = p.nms_threads ? p.nms_threads : dbg_env_int("BTPOST_NMS_NT", 1024);
     const int nt = nt_req == 512 ? 512 : 1024;
     const int sort_max = nt == 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
     const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > sort_max ? sort_max : P.cap_pow2);
@@ -873,7 +935,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     // match_kernel: COCO tables
     const int coco_doubles = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;   // boxes + room for a [K x 4] IoU block
     P.coco_smem_doubles = coco_doubles;
-    const size_t smem_b = (size_t)coco_doubles * 8 + (size_t)p.max_det * 12;
+    const size_t smem_b = (size_t)coco_doubles * 8 + (size_t)p.max_det * 12 + 8 + (size_t)p.max_det * 16;   // + match-bit tables
     if (smem_b > 220 * 1024) return BT_ERR_UNSUPPORTED;
     // function attributes are per device: one flag per device ordinal
     static bool attr_done[64] = {};
@@ -890,12 +952,11 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
         // Developer switch BTPOST_NMS_PRIO=1: launch the NMS kernel (the long pole of a step; needs whole SMs) with the
         // highest launch priority.  Measured: one batch in flight 205.6 -> 198.5 us, four in flight 539 k -> 524 k
         // images/s, so it is off by default.
-        static const char *pe = getenv("BTPOST_NMS_PRIO");
-        static int prio = 0x7fffffff;
-        if (prio == 0x7fffffff) {
+        int prio = 0;
+        if (dbg_env_int("BTPOST_NMS_PRIO", 0) != 0) {   // debug build only
             int lo = 0, hi = 0;
             if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return BT_ERR_CUDA;
-            prio = (pe && atoi(pe) != 0) ? hi : 0;   // hi = numerically lowest = highest priority
+            prio = hi;   // hi = numerically lowest = highest priority
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(p.batch); cfg.blockDim = dim3(nt == 512 ? 512 : 1024); cfg.dynamicSmemBytes = smem_a; cfg.stream = s;

@@ -42,7 +42,8 @@ BTO_API void bto_decode_l2(const float *head, int N, int nc, float *boxes, float
         int32_t bi = 0;
         for (int c = 1; c < nc; ++c) {
             float s = head[(size_t)(4 + c) * N + n];
-            if (s > best) { best = s; bi = c; }
+            /* torch .max(dim): a NaN is the maximum and the first NaN wins (pinned in tests/test_oracle_pinning.py) */
+            if (s > best || (s != s && best == best)) { best = s; bi = c; }
         }
         score[n] = best;
         label[n] = bi;
@@ -163,7 +164,7 @@ static inline float bto_min(float a, float b) { return (b < a) ? b : a; } /* std
  * (== per-class NMS merged by score).  2: Ultralytics offset boxes + label*max_wh
  * in fp32, then agnostic. */
 BTO_API int bto_nms(const float *boxes_in, const float *scores, const int32_t *labels, int n,
-                    double iou_thr, int class_mode, float max_wh, int64_t *keep, int max_keep) {
+                    double iou_thr, int class_mode, float max_wh, int64_t *keep, int max_keep, int max_cand) {
     if (n <= 0 || max_keep <= 0) return 0;
     float *boxes = (float *)malloc(sizeof(float) * 4 * (size_t)n);
     float *area = (float *)malloc(sizeof(float) * (size_t)n);
@@ -177,6 +178,9 @@ BTO_API int bto_nms(const float *boxes_in, const float *scores, const int32_t *l
         ord[i].idx = i;
     }
     qsort(ord, (size_t)n, sizeof(bto_sortrec), bto_cmp);
+    /* Ultralytics non_max_suppression: x = x[x[:, 4].argsort(descending=True)[:max_nms]] before torchvision.ops.nms
+     * (SURVEY.md A.5).  argsort is made stable here (ties -> lower index), as the NMS sort itself is. */
+    if (max_cand > 0 && max_cand < n) n = max_cand;
     int nk = 0;
     for (int _i = 0; _i < n && nk < max_keep; ++_i) {
         int i = ord[_i].idx;

@@ -47,7 +47,7 @@ def lib():
         L.bto_filter.argtypes = [f32p, f32p, i32p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
                                  f32p, f32p, i32p, i32p]
         L.bto_filter.restype = C.c_int
-        L.bto_nms.argtypes = [f32p, f32p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_float, i64p, C.c_int]
+        L.bto_nms.argtypes = [f32p, f32p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_float, i64p, C.c_int, C.c_int]
         L.bto_nms.restype = C.c_int
         L.bto_gt_prep.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, f32p, i32p, C.c_int]
         L.bto_gt_prep.restype = C.c_int
@@ -69,7 +69,7 @@ def lib():
 
 DEFAULTS = dict(conf_thres=0.05, iou_thres=0.6, max_det=300, nc=3, nm=32, img_size=640,
                 class_mode=0, max_wh=7680.0, clamp=1, gt_mode=0, iou_match_thresh=0.5, max_gt=32,
-                crop=1, max_cand=0, with_instances=True, with_masks_out=True)
+                crop=1, max_cand=0, with_instances=True, with_masks_out=True, drop_gt_no_cand=0)
 
 
 def iou_thresholds():
@@ -78,7 +78,7 @@ def iou_thresholds():
     return np.asarray(torch.linspace(0.5, 0.95, 10).tolist(), np.float64)
 
 
-def nms(boxes, scores, iou_thr, labels=None, class_mode=0, max_wh=7680.0, max_keep=None):
+def nms(boxes, scores, iou_thr, labels=None, class_mode=0, max_wh=7680.0, max_keep=None, max_cand=0):
     boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4)
     scores = np.ascontiguousarray(scores, np.float32)
     n = len(scores)
@@ -88,7 +88,7 @@ def nms(boxes, scores, iou_thr, labels=None, class_mode=0, max_wh=7680.0, max_ke
         lab_arr = np.ascontiguousarray(labels, np.int32)
         lab = lab_arr.ctypes.data_as(C.c_void_p)
     k = lib().bto_nms(boxes, scores, lab, n, float(iou_thr), class_mode, max_wh, keep,
-                      n if max_keep is None else max_keep)
+                      n if max_keep is None else max_keep, int(max_cand))
     return keep[:k].copy()
 
 
@@ -196,7 +196,6 @@ def run_pipeline(batch, pool=None, **kw):
     else:
         B, _, N = head.shape
     nc, nm, S, max_det = p["nc"], p["nm"], p["img_size"], p["max_det"]
-    max_cand = p["max_cand"] or N
     out = {
         "n_cand": np.zeros(B, np.int32), "det_count": np.zeros(B, np.int32),
         "dets": np.zeros((B, max_det, 6), np.float32), "det_anchor": np.full((B, max_det), -1, np.int32),
@@ -232,11 +231,10 @@ def run_pipeline(batch, pool=None, **kw):
         cb = np.empty((N, 4), np.float32); cs = np.empty(N, np.float32)
         cl = np.empty(N, np.int32); ca = np.empty(N, np.int32)
         m = lib().bto_filter(boxes, score, label, N, np.float32(p["conf_thres"]), p["clamp"], np.float32(S), np.float32(S), cb, cs, cl, ca)
-        m = min(m, max_cand)
         cb, cs, cl, ca = cb[:m].copy(), cs[:m].copy(), cl[:m].copy(), ca[:m].copy()
         out["n_cand"][b] = m
         out["cand_box"].append(cb); out["cand_score"].append(cs); out["cand_label"].append(cl); out["cand_anchor"].append(ca)
-        keep = nms(cb, cs, p["iou_thres"], cl, p["class_mode"], p["max_wh"], max_det) if m else np.zeros(0, np.int64)
+        keep = nms(cb, cs, p["iou_thres"], cl, p["class_mode"], p["max_wh"], max_det, p["max_cand"]) if m else np.zeros(0, np.int64)
         k = len(keep)
         out["det_count"][b] = k
         out["dets"][b, :k, :4] = cb[keep]; out["dets"][b, :k, 4] = cs[keep]; out["dets"][b, :k, 5] = cl[keep].astype(np.float32)

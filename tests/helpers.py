@@ -26,12 +26,14 @@ def run_cuda(batch, dev="cuda:0", gt_f32=False, l1=False, **kw):
                      iou_match_thresh=kw.get("iou_match_thresh", 0.5),
                      gt_mask_dtype=_lib.MASK_F32 if gt_f32 else _lib.MASK_U8, nms_threads=kw.get("nms_threads", 0),
                      proto_bf16=bool(kw.get("proto_bf16", False)), head_bf16=bool(kw.get("head_bf16", False)),
-                     with_seg_mask=True, with_seg_logits=True, with_uni_mask=True, with_coco=True, with_seg_map=True)
+                     drop_gt_no_cand=bool(kw.get("drop_gt_no_cand", 0)), with_inst_masks=kw.get("with_inst_masks"),
+                     num_anchors=kw.get("num_anchors"), with_seg_mask=True, with_seg_logits=True, with_uni_mask=True, with_coco=True, with_seg_map=True)
     pp = PostProcessor(cfg, dev)
     d = to_dev(batch, dev, gt_f32, bool(kw.get("proto_bf16", False)), bool(kw.get("head_bf16", False)))
     extra = {}
     if l1:
-        extra = dict(maps=[torch.from_numpy(m).to(dev) for m in batch["maps"]], coeffs=torch.from_numpy(batch["coeffs"]).to(dev))
+        cast = (lambda t: t.bfloat16()) if kw.get("head_bf16") else (lambda t: t)
+        extra = dict(maps=[cast(torch.from_numpy(m).to(dev)) for m in batch["maps"]], coeffs=cast(torch.from_numpy(batch["coeffs"]).to(dev)))
     out = pp.run(None if l1 else d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"],
                  **extra)
     torch.cuda.synchronize()
@@ -75,6 +77,48 @@ def assert_same(got, ref, B, max_det, check_masks=True):
         np.testing.assert_allclose(got["uni_iou"], ref["uni_iou"], rtol=1e-5)
         if check_masks:
             np.testing.assert_array_equal(got["uni_mask"], ref["uni_mask"])
+        if "inst_bits" in got:   # every instance bitmap, pixel for pixel (src/test_model.py:80-85 + crop)
+            for b in range(B):
+                k = int(ref["det_count"][b])
+                planes = np.unpackbits(got["inst_bits"][b], axis=-1, bitorder="little")
+                np.testing.assert_array_equal(planes[:k], ref["inst_masks"][b], err_msg=f"instance masks of image {b}")
+                assert not planes[k:].any(), "planes beyond det_count must be zero"
+                if "inst_masks" in got:
+                    np.testing.assert_array_equal(got["inst_masks"][b], planes)
     np.testing.assert_array_equal(got["dt_match"], ref["dt_match"])
     np.testing.assert_array_equal(got["dt_ignore"], ref["dt_ignore"])
     np.testing.assert_array_equal(got["gt_ignore"], ref["gt_ignore"])
+
+
+def oracle_parallel(batch, workers=None, chunk=1, **kw):
+    """oracle.run_pipeline over chunks of images on a thread pool (the C parts release the GIL); outputs are
+    concatenated, the accumulated counters summed.  Same results as one call over the whole batch."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    B = batch["protos"].shape[0]
+    gt = batch["det_boxes_gt"]
+
+    def one(b0):
+        b1 = min(B, b0 + chunk)
+        sub = dict(batch)
+        for k in ("head", "protos", "masks_gt"):
+            sub[k] = batch[k][b0:b1]
+        rows = gt[(gt[:, 0] >= b0) & (gt[:, 0] < b1)].copy() if len(gt) else gt
+        if len(rows):
+            rows[:, 0] -= b0
+        sub["det_boxes_gt"] = rows
+        return oracle.run_pipeline(sub, **kw)
+
+    with ThreadPoolExecutor(workers or os.cpu_count() or 4) as pool:
+        parts = list(pool.map(one, range(0, B, chunk)))
+    out = {}
+    for k, v in parts[0].items():
+        if k in ("cm", "seg_cnt4", "uni_cnt4"):
+            out[k] = sum(p[k] for p in parts)
+        elif isinstance(v, list):
+            out[k] = [x for p in parts for x in p[k]]
+        elif v is None:
+            out[k] = None
+        else:
+            out[k] = np.concatenate([p[k] for p in parts], 0)
+    return out

@@ -32,13 +32,15 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "btpost.h"\nint main(){'
-                   'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(BtParams), offsetof(BtParams, iou_thres),'
-                   'offsetof(BtParams, iou_thrs), offsetof(BtParams, image_offset), sizeof(BtIO), offsetof(BtIO, dt_match));return 0;}')
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(BtParams), offsetof(BtParams, iou_thres),'
+                   'offsetof(BtParams, iou_thrs), offsetof(BtParams, image_offset), sizeof(BtIO), offsetof(BtIO, dt_match),'
+                   'offsetof(BtParams, drop_gt_no_cand), offsetof(BtIO, inst_bits), offsetof(BtIO, sweep));return 0;}')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(_lib.BtParams), _lib.BtParams.iou_thres.offset, _lib.BtParams.iou_thrs.offset,
-            _lib.BtParams.image_offset.offset, C.sizeof(_lib.BtIO), _lib.BtIO.dt_match.offset]
+            _lib.BtParams.image_offset.offset, C.sizeof(_lib.BtIO), _lib.BtIO.dt_match.offset,
+            _lib.BtParams.drop_gt_no_cand.offset, _lib.BtIO.inst_bits.offset, _lib.BtIO.sweep.offset]
     assert got == want
 
 
@@ -66,9 +68,10 @@ def test_argument_validation_without_gpu():
         setattr(p, field, bad)
         assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1, field
         setattr(p, field, 0)
-    p.head_dtype, p.layout = _lib.HEAD_BF16, _lib.LAYOUT_L1
-    assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -2   # bf16 raw maps: not implemented
-    p.head_dtype, p.layout = 0, _lib.LAYOUT_L2
+    io.inst_masks = 4096                                                                   # dense instance masks need the bit planes
+    io.head = io.protos = io.masks_gt = io.proj_weight = io.dets = io.det_count = io.det_coeff = 4096
+    assert L.btpost_masks_parts(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None, 4) == -1
+    io = _lib.BtIO()
     assert L.btpost_masks_parts(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None, 8) == -1   # unknown part bit / null inputs
     assert L.btpost_synth_batch(0, 640, 3, 32, None, None, None, None, None, None, None) == -1
     assert L.btpost_synth_batch(2, 640, 3, 32, None, None, None, C.c_void_p(256), None, None, None) == -1   # head without keys / objects

@@ -160,3 +160,114 @@ def test_full_size_batch_is_consistent_with_small_batches():
             np.testing.assert_array_equal(got64[k], 8 * v, err_msg=k)
         else:
             assert got64[k].tobytes() == rep(v).tobytes(), k
+
+
+@pytest.mark.parametrize("kw", [dict(with_inst_masks="dense"), dict(with_inst_masks="bits", crop=0, max_det=24),
+                                dict(with_inst_masks="dense", max_det=40, proto_bf16=True)])
+def test_instance_masks_pixel_for_pixel(kw):
+    """g1: every instance bitmap `[B,K,S,S]` (bit-packed, and expanded to bytes) against oracle.instance_mask
+    (`/root/reference/src/test_model.py:80-85`: einsum -> bilinear -> sigmoid > 0.5, with / without the Ultralytics crop):
+    a detection whose pixels are wrong inside another instance's footprint cannot hide behind equal popcounts."""
+    import torch
+    batch = helpers.make(batch=2, img_size=640, seed=20271)
+    if kw.get("proto_bf16"):
+        batch["protos"] = torch.from_numpy(batch["protos"]).bfloat16().float().numpy()
+    okw = {k: v for k, v in kw.items() if k not in ("with_inst_masks", "proto_bf16")}
+    ref = helpers.oracle_parallel(batch, **okw)
+    got, _ = helpers.run_cuda(batch, **kw)
+    assert "inst_bits" in got and sum(len(m) for m in ref["inst_masks"]) == int(ref["det_count"].sum()) > 0
+    helpers.assert_same(got, ref, 2, kw.get("max_det", 300))
+
+
+def test_pipeline_1024_batch8_full():
+    """BASELINE config 3 shapes at batch 8: 1024^2 (21504 anchors, 256^2 prototypes), max_det 300, instance masks on and
+    compared bitmap by bitmap."""
+    batch = helpers.make(batch=8, img_size=1024, seed=20273)
+    ref = helpers.oracle_parallel(batch, img_size=1024)
+    got, _ = helpers.run_cuda(batch, with_inst_masks="bits")
+    assert int(ref["det_count"].max()) > 200
+    helpers.assert_same(got, ref, 8, 300)
+
+
+def test_config4_dense_at_stated_size():
+    """BASELINE config 4 as stated: batch 128 x 1024^2, conf 0.001 -> every one of the 21504 anchors is a candidate
+    (above the 16384-key register sort: the global-memory sort network of nms_kernel), max_det 300.  Inputs come from the
+    device generator (bit-identical to the numpy one, tests/test_gpu_synth.py); the oracle checks every detection-side
+    and projector-side output of all 128 images (its instance masks at this size would take half an hour: those are
+    compared at batch 8 above)."""
+    import torch
+    from btpost import PostConfig, PostProcessor, synth
+    B, S = 128, 1024
+    scfg = synth.SynthConfig(batch=B, img_size=S, seed=20274)
+    d = synth.make_batch_device(scfg, "cuda:0")
+    torch.cuda.synchronize()
+    batch = {k: d[k].cpu().numpy() for k in ("head", "protos", "masks_gt", "det_boxes_gt", "proj_weight")}
+    batch["proj_bias"] = d["proj_bias"]
+    kw = dict(conf_thres=0.001, max_det=300)
+    ref = helpers.oracle_parallel(batch, img_size=S, with_instances=False, with_masks_out=False, **kw)
+    assert int(ref["n_cand"].min()) == 21504
+    cfg = PostConfig(batch=B, img_size=S, conf_thres=0.001, iou_thres=0.6, max_det=300, with_coco=True, with_seg_map=True)
+    pp = PostProcessor(cfg, "cuda:0")
+    out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    helpers.assert_same(got, ref, B, 300, check_masks=False)
+
+
+def test_dense_30000_candidates_padded():
+    """The `up to 30k boxes / image` end of config 4: the head is padded to N = 30000 anchors that all pass conf 0.001
+    (32768-key global-memory sort)."""
+    batch = helpers.make(batch=2, img_size=1024, seed=20275)
+    rng = np.random.default_rng(5)
+    B, C, N0 = batch["head"].shape
+    extra = 30000 - N0
+    pad = np.zeros((B, C, extra), np.float32)
+    pad[:, 0:2] = rng.uniform(0, 1024, (B, 2, extra))
+    pad[:, 2:4] = rng.uniform(4, 200, (B, 2, extra))
+    pad[:, 4:7] = rng.uniform(0.002, 0.5, (B, 3, extra))
+    pad[:, 7:] = rng.normal(0, 1, (B, C - 7, extra))
+    batch["head"] = np.ascontiguousarray(np.concatenate([batch["head"], pad.astype(np.float32)], 2))
+    kw = dict(conf_thres=0.001, max_det=300)
+    ref = helpers.oracle_parallel(batch, img_size=1024, with_instances=False, **kw)
+    assert int(ref["n_cand"].min()) == 30000
+    got, _ = helpers.run_cuda(batch, num_anchors=30000, **kw)
+    helpers.assert_same(got, ref, 2, 300)
+
+
+def test_bf16_l1_maps():
+    """f1: the reference's three raw maps as bfloat16 (bf16-mixed validation, `/root/reference/src/running_main_v2.py:1324`):
+    widened exactly on load, so every output equals the oracle's on the rounded maps."""
+    import torch
+    batch = helpers.make(batch=2, img_size=640, seed=43, l1=True)
+    rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    batch["maps"] = [rnd(m) for m in batch["maps"]]
+    batch["coeffs"] = rnd(batch["coeffs"])
+    kw = dict(max_det=40)
+    ref = oracle.run_pipeline(batch, layout="l1", **kw)
+    got, _ = helpers.run_cuda(batch, l1=True, head_bf16=True, **kw)
+    helpers.assert_same(got, ref, 2, 40)
+
+
+def test_drop_gt_no_cand_and_gt_overflow():
+    """(i) v2 drops the target of an image without any candidate above CONF_TH (`running_main_v2.py:797-814`),
+    v3 keeps it (`running_main_v3.py:541-571`): an explicit flag, not tied to gt_mode; (ii) more GT rows than max_gt
+    is reported, not silent."""
+    import torch
+    from btpost import PostConfig, PostProcessor
+    batch = helpers.make(batch=2, img_size=640, seed=44)
+    batch["head"][1, 4:7] = 0.0                                   # image 1: nothing passes the filter
+    d = helpers.to_dev(batch, "cuda:0")
+    args = (d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    for drop in (False, True):
+        pp = PostProcessor(PostConfig(batch=2, img_size=640, drop_gt_no_cand=drop, gt_mode=0), "cuda:0")
+        pp.run(*args)
+        preds, targets, _, _ = pp.to_reference_lists()
+        assert len(preds[1]["boxes"]) == 0 and int(pp.out["gt_count"][1]) > 0
+        assert len(targets[1]["boxes"]) == (0 if drop else int(pp.out["gt_count"][1]))
+        assert len(targets[0]["boxes"]) == int(pp.out["gt_count"][0])
+    rows = np.tile(batch["det_boxes_gt"][:1], (40, 1)).astype(np.float32)      # 40 rows for one image, max_gt = 32
+    pp = PostProcessor(PostConfig(batch=2, img_size=640), "cuda:0")
+    pp.run(d["head"], d["protos"], torch.from_numpy(rows).cuda(), d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    assert pp.out["gt_rows_total"].cpu().tolist()[int(rows[0, 0])] == 40
+    with pytest.raises(ValueError, match="max_gt"):
+        pp.to_reference_lists()

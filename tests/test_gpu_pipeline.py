@@ -35,24 +35,49 @@ def test_stage_by_stage_equals_run():
         assert ra[k].cpu().numpy().tobytes() == rb[k].cpu().numpy().tobytes(), k
 
 
-def test_pipeline_three_batches_in_flight_bit_identical():
+def test_pipeline_six_different_batches_in_flight():
+    """Six DIFFERENT batches in flight, each in its own slot (own static inputs, workspace, outputs, stream), two rounds:
+    every slot's outputs must equal a serial PostProcessor's on the same batch bit for bit, and the shared counters must
+    be the sum over all twelve steps.  The second round feeds the slots in a different order through `submit`."""
     dev = torch.device("cuda:0")
-    batch = helpers.make(batch=8, img_size=640, seed=32)
-    args = _args(batch, dev)
-    ref_pp = PostProcessor(_cfg(8), dev)
-    ref = {k: v.clone() for k, v in ref_pp.run(*args).items()}
-    pipe = Pipeline(_cfg(8), dev, depth=3).capture(*args)
-    pipe.reset_metrics()
-    n = 12
+    B, depth = 4, 6
+    batches = [helpers.make(batch=B, img_size=640, seed=600 + i, image_offset=100 * i) for i in range(depth)]
+    serial = PostProcessor(_cfg(B), dev)
+    refs = []
+    for bt in batches:
+        serial.reset_metrics()
+        refs.append({k: v.clone() for k, v in serial.run(*_args(bt, dev)).items()})
+    torch.cuda.synchronize()
+    w, bias = _args(batches[0], dev)[4:6]
+    pipe = Pipeline(_cfg(B), dev, depth=depth, proj_weight=w, proj_bias=bias)
+    # round 1: zero-copy style -- inputs are written into the slots' buffers, then the steps are replayed round robin
+    for i, bt in enumerate(batches):
+        a = _args(bt, dev)
+        pipe.load(i, a[0], a[1], a[2], a[3])
     pipe.fork()
-    for _ in range(n):
+    for i in range(depth):
         pipe.replay()
     pipe.join()
     torch.cuda.synchronize()
-    for p in pipe.procs:
-        for k, v in p.out.items():
+    for i in range(depth):
+        for k, v in pipe.procs[i].out.items():
             if k in KEYS_ACC:
                 continue
-            assert v.cpu().numpy().tobytes() == ref[k].cpu().numpy().tobytes(), k
-    for k in KEYS_ACC:   # every step added its counters exactly once
-        np.testing.assert_array_equal(pipe.counters(k).cpu().numpy(), n * ref[k].cpu().numpy())
+            assert v.cpu().numpy().tobytes() == refs[i][k].cpu().numpy().tobytes(), (i, k)
+    # round 2: submit() from pinned host tensors, shifted by one slot; wait(slot) hands the outputs back
+    order = [(i + 1) % depth for i in range(depth)]
+    tickets = []
+    for j in order:
+        bt = batches[j]
+        host = [torch.from_numpy(np.ascontiguousarray(bt[k])).pin_memory() for k in ("head", "protos", "det_boxes_gt", "masks_gt")]
+        tickets.append((pipe.submit(*host), j))
+    for slot, j in tickets:
+        out = pipe.wait(slot)
+        for k, v in out.items():
+            if k in KEYS_ACC:
+                continue
+            assert v.cpu().numpy().tobytes() == refs[j][k].cpu().numpy().tobytes(), (slot, j, k)
+    torch.cuda.synchronize()
+    for k in KEYS_ACC:   # every step added its counters exactly once into the shared accumulators
+        want = 2 * sum(r[k].cpu().numpy() for r in refs)
+        np.testing.assert_array_equal(pipe.counters(k).cpu().numpy(), want)

@@ -5,7 +5,8 @@ import pytest
 import torch
 
 import helpers
-from btpost.sweep import SweepState
+from btpost import Pipeline, PostConfig, PostProcessor
+from btpost.sweep import DeviceSweep, SweepState, decode_records
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -30,3 +31,112 @@ def test_device_sweep_matches_cpu_sweep_of_oracle_outputs():
         assert float(a[k]) == pytest.approx(float(b[k]), rel=1e-6, abs=1e-9), k
     np.testing.assert_array_equal(a["cm"].cpu().numpy(), b["cm"].numpy())
     np.testing.assert_allclose(a["precision"].cpu().numpy(), b["precision"].numpy(), rtol=1e-12)
+
+
+def _oracle_ap(outs, offsets, max_dets=(1, 10, 100), drop=False):
+    """oracle.accumulate_ap over a list of oracle batch outputs (images in global order)."""
+    thrs = oracle.iou_thresholds()
+    recs, npig = [], np.zeros((4, 3), np.int64)
+    order = np.argsort(offsets)
+    for i in order:
+        out = outs[i]
+        for b in range(len(out["det_count"])):
+            k, g = int(out["det_count"][b]), int(out["gt_count"][b])
+            recs.append(dict(labels=out["dets"][b, :k, 5].astype(np.int64), scores=out["dets"][b, :k, 4],
+                             matched=out["dt_match"][b][:, :, :k] > 0, ignored=out["dt_ignore"][b][:, :, :k] > 0))
+            if drop and int(out["n_cand"][b]) == 0:
+                continue
+            for a in range(4):
+                for gi in range(g):
+                    if not out["gt_ignore"][b, a, gi]:
+                        npig[a, out["gt_labels"][b, gi]] += 1
+    return oracle.accumulate_ap(recs, npig, thrs, max_dets, 3), npig
+
+
+@pytest.mark.parametrize("quantise", [False, True])
+def test_device_sweep_records_and_accumulate_kernel(quantise):
+    """a9 on the device: the records the library appends per batch (zero torch ops) decode to the oracle's per-detection
+    match bits, and btpost_sweep_accumulate (radix sort + scans + 101-point lookup) reproduces the oracle's numpy
+    restatement of COCOeval.accumulate BIT FOR BIT (doubles), also when scores tie across images (quantised scores: the
+    global order then hangs on the (image, rank) tie-break) and when batches arrive out of order."""
+    kw = dict(max_det=100, gt_mode=1)
+    B, S, nb = 4, 160, 5
+    sweep = DeviceSweep(3, oracle.iou_thresholds(), (1, 10, 100), capacity=4096, max_det_per_image=100, device="cuda:0")
+    cfg = PostConfig(batch=B, img_size=S, max_det=100, gt_mode=1, with_coco=True)
+    pp = PostProcessor(cfg, "cuda:0", sweep=sweep)
+    outs, offs = [], []
+    for i in (3, 0, 4, 1, 2):                             # batches in scrambled order: the result must not depend on it
+        batch = helpers.make(batch=B, img_size=S, seed=31, image_offset=B * i)
+        if quantise:
+            batch["head"][:, 4:7] = np.round(batch["head"][:, 4:7] * 16) / 16
+        if i == 1:
+            batch["head"][2, 4:7] = 0.0                   # an image without candidates
+        ref = oracle.run_pipeline(batch, img_size=S, **kw)
+        d = helpers.to_dev(batch, "cuda:0")
+        out = pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"], image_offset=B * i)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out["dt_match"].cpu().numpy(), ref["dt_match"])
+        outs.append(ref); offs.append(B * i)
+    # ---- records
+    n = int(sweep.hdr[0])
+    assert n == sum(int(o["det_count"].sum()) for o in outs)
+    rec = decode_records(sweep.records[:n], 10)
+    for ref, off in zip(outs, offs):
+        for b in range(B):
+            k = int(ref["det_count"][b])
+            sel = np.nonzero(rec["image"] == off + b)[0]
+            assert len(sel) == k
+            sel = sel[np.argsort(rec["rank"][sel])]
+            np.testing.assert_array_equal(rec["rank"][sel], np.arange(k))
+            assert rec["score"][sel].tobytes() == ref["dets"][b, :k, 4].tobytes()
+            lab = ref["dets"][b, :k, 5].astype(np.int64)
+            np.testing.assert_array_equal(rec["label"][sel], lab)
+            np.testing.assert_array_equal(rec["class_rank"][sel], [int((lab[:j] == lab[j]).sum()) for j in range(k)])
+            np.testing.assert_array_equal(rec["matched"][sel], np.moveaxis(ref["dt_match"][b][:, :, :k] > 0, 2, 0))
+            np.testing.assert_array_equal(rec["ignored"][sel], np.moveaxis(ref["dt_ignore"][b][:, :, :k] > 0, 2, 0))
+    # ---- header + accumulate
+    want, npig = _oracle_ap(outs, offs)
+    res = sweep.finish()
+    assert res["n_images"] == nb * B and res["n_records"] == n
+    np.testing.assert_array_equal(res["npig"], npig)
+    np.testing.assert_array_equal(res["precision"], want["precision"])      # float64, bit for bit
+    np.testing.assert_array_equal(res["recall"], want["recall"])
+    for k in ("map", "map_50", "map_75", "mar_1", "mar_10", "mar_100", "map_small", "map_medium", "map_large"):
+        assert res[k] == want[k], k
+    assert want["map_50"] > 0.05
+    np.testing.assert_array_equal(res["cm"].numpy(), sum(o["cm"] for o in outs))
+    assert res["seg_dice"] == pytest.approx(float(np.mean([o["seg_dice"] for o in outs])), rel=1e-6)
+    assert res["uni_iou"] == pytest.approx(float(np.mean([o["uni_iou"] for o in outs])), rel=1e-6)
+    # second finish() on the untouched ring gives the same tables (the sort works on a copy)
+    np.testing.assert_array_equal(sweep.finish()["precision"], want["precision"])
+
+
+def test_device_sweep_through_pipeline_drop_flag_and_overflow():
+    """Sweep records from captured steps replayed with several batches in flight (image index through the device-side
+    `image_base`), the v2 `drop_gt_no_cand` rule in the GT counts, and the ring-overflow report."""
+    B, S, depth = 4, 160, 3
+    for drop in (False, True):
+        sweep = DeviceSweep(3, oracle.iou_thresholds(), (1, 10, 100), capacity=8192, max_det_per_image=100, device="cuda:0")
+        cfg = PostConfig(batch=B, img_size=S, max_det=100, gt_mode=1, with_coco=True, drop_gt_no_cand=drop)
+        batches = [helpers.make(batch=B, img_size=S, seed=91, image_offset=B * i) for i in range(6)]
+        batches[2]["head"][1, 4:7] = 0.0
+        w, bias = helpers.to_dev(batches[0], "cuda:0")["proj_weight"], float(batches[0]["proj_bias"])
+        pipe = Pipeline(cfg, "cuda:0", depth=depth, proj_weight=w, proj_bias=bias, sweep=sweep)
+        outs, offs = [], []
+        for i, bt in enumerate(batches):
+            d = helpers.to_dev(bt, "cuda:0")
+            pipe.submit(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], image_offset=B * i)
+            outs.append(oracle.run_pipeline(bt, img_size=S, max_det=100, gt_mode=1)); offs.append(B * i)
+        pipe.join()
+        torch.cuda.synchronize()
+        want, npig = _oracle_ap(outs, offs, drop=drop)
+        res = sweep.finish()
+        np.testing.assert_array_equal(res["npig"], npig)
+        np.testing.assert_array_equal(res["precision"], want["precision"])
+        assert res["n_images"] == 6 * B
+    small = DeviceSweep(3, oracle.iou_thresholds(), (1, 10, 100), capacity=16, max_det_per_image=100, device="cuda:0")
+    pp = PostProcessor(cfg, "cuda:0", sweep=small)
+    d = helpers.to_dev(batches[0], "cuda:0")
+    pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
+    with pytest.raises(RuntimeError, match="ring too small"):
+        small.finish()
