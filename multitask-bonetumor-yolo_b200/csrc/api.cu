@@ -126,18 +126,6 @@ int g_debug_skip = 0;   // developer tool (scripts/ablate.py, debug build only):
 
 using namespace bt;
 
-#ifdef BT_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[3][16];
-extern "C" BTPOST_API int btpost_debug_phase_cycles(unsigned long long *out48, int reset) {
-    if (cudaMemcpyFromSymbol(out48, g_phase_cycles, sizeof(unsigned long long) * 48) != cudaSuccess) return BT_ERR_CUDA;
-    if (reset) {
-        static unsigned long long zeros[48];
-        if (cudaMemcpyToSymbol(g_phase_cycles, zeros, sizeof(zeros)) != cudaSuccess) return BT_ERR_CUDA;
-    }
-    return BT_OK;
-}
-#endif
-
 extern "C" {
 
 #ifdef BT_DEBUG_HOOKS

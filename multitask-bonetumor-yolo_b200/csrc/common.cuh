@@ -13,7 +13,7 @@
 // Optional per-phase cycle accounting (debug builds only: make dbg).  Thread 0 of every CTA adds the
 // cycles it spent between marks into a global table read back by btpost_debug_phase_cycles().
 #ifdef BT_PHASE_TIMING
-extern __device__ unsigned long long g_phase_cycles[3][16];
+// (defined in nms_match.cu, the only file with marks: no relocatable device code needed)
 #define BT_PHASE_INIT() long long _pt = clock64()
 #define BT_PHASE_MARK(kern, idx)                                                           \
     do {                                                                                   \

@@ -308,6 +308,12 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
             }
         }
         if (rank == 0) {
+            // padding beyond the image's boxes is zero-filled: the outputs do not depend on what a previous batch left
+            for (int i = 4 * G + tid; i < 4 * P.max_gt; i += nthreads) {
+                P.gt_boxes_raw[(size_t)b * P.max_gt * 4 + i] = 0.0f;
+                P.gt_boxes[(size_t)b * P.max_gt * 4 + i] = 0.0f;
+            }
+            for (int i = G + tid; i < P.max_gt; i += nthreads) P.gt_labels[(size_t)b * P.max_gt + i] = 0;
             for (int i = tid; i < G; i += nthreads) P.gt_labels[(size_t)b * P.max_gt + i] = s_gl[i];
             if (tid == 0) {
                 P.gt_count[b] = G;

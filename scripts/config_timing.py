@@ -45,9 +45,11 @@ print(f"whole step us: {us:.1f}  -> {B / us * 1e6:.0f} images/s")
 for st in ("decode_filter", "nms_match", "masks", "masks_contract"):
     print(f"  {st:14s} us: {timeit(pp.capture(*args, stage=st, **extra)):.1f}")
 
-# the same step with four batches in flight (own workspace each)
-if len(sys.argv) > 2 and sys.argv[2] == "pipe":
-    pipe = Pipeline(PostConfig(batch=B, img_size=S, **kw), dev, depth=4).capture(*args, **extra)
+# the same step with four batches in flight (own inputs, workspace and outputs each)
+if len(sys.argv) > 2 and sys.argv[2] == "pipe" and not l1:
+    pipe = Pipeline(PostConfig(batch=B, img_size=S, **kw), dev, depth=4, proj_weight=args[4], proj_bias=args[5], gt_rows_cap=len(gt))
+    for i in range(4):
+        pipe.load(i, args[0], args[1], args[2], args[3])
     pipe.fork()
     for _ in range(12): pipe.replay()
     pipe.join(); torch.cuda.synchronize()

@@ -12,7 +12,7 @@ cfg = synth.SynthConfig(batch=B, img_size=S, seed=20262)
 b = synth.make_batch(cfg)
 dev = torch.device("cuda:0")
 d = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("head", "protos", "det_boxes_gt", "masks_gt", "proj_weight")}
-pp = PostProcessor(PostConfig(batch=B, img_size=S), dev)
+pp = PostProcessor(PostConfig(batch=B, img_size=S, nms_threads=int(sys.argv[3]) if len(sys.argv) > 3 else 0), dev)
 args = (d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], float(b["proj_bias"]))
 L = _lib.load()
 buf = (C.c_ulonglong * 48)()
@@ -21,11 +21,10 @@ torch.cuda.synchronize(); L.btpost_debug_phase_cycles(buf, 1)
 n = 10
 for _ in range(n): pp.run(*args)
 torch.cuda.synchronize(); L.btpost_debug_phase_cycles(buf, 1)
-names = {1: {0: "sort", 1: "stage window", 3: "chunks (tail mark)", 8: "chunk A", 12: "A: sum of per-warp max (warps 0-7)", 13: "A: warp-chunks counted", 14: "A: sum per-warp max (idle warps)", 11: "chunk B", 9: "chunk C", 10: "chunk insert", 6: "package", 7: "COCO match (other kernel)"},
-         }
+names = {1: {0: "sort", 1: "stage window", 2: "carry (kept of earlier windows)", 3: "diagonal blocks", 4: "blocks: resolve + rows", 5: "insert", 6: "package", 7: "COCO match (other kernel)"}}
 for k, nb in ((1, B),):   # the mask stage is four plain kernels now: time them with bench.py / ncu
     tot = sum(buf[k * 16 + i] for i in range(16))
-    print(f"kernel {k}: total cycles/launch {tot / n:.0f}")
+    print(f"kernel {k}: total cycles/launch {tot / n:.0f}  ({tot / n / nb:.0f} per image, thread 0 of every CTA)")
     for i in range(16):
         v = buf[k * 16 + i]
         if v: print(f"   {names[k].get(i, i)!s:28s} {v / n:14.0f} cycles/launch  {100 * v / tot:5.1f}%")
