@@ -54,7 +54,11 @@ extern "C" __attribute__((visibility("default"))) int btpost_debug_phase_cycles(
 
 namespace bt {
 
+constexpr int NMS_CHUNK = 64;
+constexpr int SORT_REG_MAX = 16384;  // keys sorted in registers (16 per thread) up to this many
+constexpr int SORT_SMALL_MAX = 4096; // same for the 512-thread variant (8 per thread): its shared memory stays below 80 KB
 constexpr int GM_THREADS = 256;      // match_kernel block
+constexpr int MAX_CELLS = 256;
 
 __device__ __forceinline__ uint32_t desc_key(float s) {
     uint32_t u = __float_as_uint(s);
@@ -66,10 +70,17 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
 
 // i = earlier (kept) box, j = later candidate; operand order of std::max/std::min as in
 // torchvision's nms_kernel_impl so NaN coordinates behave identically.
+//
+// centre_cull: IoU > 0.5 means the intersection covers more than half of EACH box, hence contains
+// each box's centre.  With iou_thres >= 0.55 (margin >> fp32 rounding of the IoU) a pair whose
+// later centre (cxj, cyj) is outside the earlier box can be skipped without evaluating the IoU;
+// every pair that is evaluated uses the exact expression, so the keep set does not change.
 struct FastDiv { int on; float lo, hi; };
 __device__ __forceinline__ bool suppresses(const float4 &bi, float ai, int li, const float4 &bj, float aj, int lj,
-                                           float thr_up, int early_out, int class_mode, const FastDiv &g_fast) {
+                                           float thr_up, int early_out, int class_mode, int centre_cull, float cxj,
+                                           float cyj, const FastDiv &g_fast) {
     if (class_mode == BT_CLASS_AWARE && li != lj) return false;
+    if (centre_cull && !(cxj >= bi.x && cxj <= bi.z && cyj >= bi.y && cyj <= bi.w)) return false;
     float xx1 = (bi.x < bj.x) ? bj.x : bi.x;
     float yy1 = (bi.y < bj.y) ? bj.y : bi.y;
     float xx2 = (bj.z < bi.z) ? bj.z : bi.z;
@@ -137,9 +148,9 @@ struct K2Params {
     int32_t *scr_off; unsigned long long *pool_used; long long pool_cap;   // logit-pool plan of the mask stage
     int2 *items; int32_t *n_items; int item_cap;                            // work items of cells_kernel
     int32_t *tile_cnt; unsigned short *tile_list; int ntiles, ntx;         // tile lists of contract_kernel
+    int centre_cull; // iou_thres >= 0.55: a suppressing pair has each centre inside the other box
+    int gx, gy; float inv_cw, inv_ch;   // centre-cell grid
     int coco_smem_doubles;
-    int centre_cull;      // iou_thres >= 0.55: a suppressed box has its centre inside the box that suppresses it
-    float inv_cw, inv_ch; // centre-cell grid of the NMS kernel (NMS_G x NMS_G cells over the image)
     long long *sweep;     // optional sweep state (header + record ring, include/btpost.h)
     int image_offset, drop_gt_no_cand;
     const int32_t *image_base;
@@ -206,11 +217,9 @@ __device__ __forceinline__ void bitonic_regs(unsigned long long (&v)[E], unsigne
     }
 }
 
-// Sorts the image's candidates; on return the i-th candidate in NMS order is s_sidx[i] (gout == nullptr) or the low
-// word of gout[i] (long lists: the sorted keys go to the workspace, the shared-memory list is capped at SIDX_MAX).
+// Sorts the image's candidates; on return s_sidx[i] (i < M) = index of the i-th candidate in NMS order.
 template <int E>
-__device__ __forceinline__ void sort_keys_regs(const float *cscore, int M, int nthr, unsigned long long *s_x, uint32_t *s_sidx,
-                                               unsigned long long *gout) {
+__device__ __forceinline__ void sort_to_smem(const float *cscore, int M, int nthr, unsigned long long *s_x, uint32_t *s_sidx) {
     const int tid = threadIdx.x;
     unsigned long long v[E];
 #pragma unroll
@@ -222,10 +231,7 @@ __device__ __forceinline__ void sort_keys_regs(const float *cscore, int M, int n
     __syncthreads();   // s_x (aliases s_sidx) is no longer read
     if (tid < nthr) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (gout) gout[tid * E + e] = v[e];
-            else s_sidx[tid * E + e] = (uint32_t)v[e];
-        }
+        for (int e = 0; e < E; ++e) s_sidx[tid * E + e] = (uint32_t)v[e];
     }
     __syncthreads();
 }
@@ -233,84 +239,37 @@ __device__ __forceinline__ void sort_keys_regs(const float *cscore, int M, int n
 // =================================================================================================
 // fused NMS kernel
 // =================================================================================================
-// Greedy sweep over windows of W = NT sorted candidates (one per thread).  Only KEPT boxes ever suppress anybody, and
-// a box can only suppress candidates near it, so the kernel never builds an all-pairs matrix:
-//   (a) stage   boxes / areas / labels of the window in NMS order; candidates are binned by the cell (16 x 16 grid)
-//               of their centre: counts (shared-memory atomics) -> scan -> cell-sorted candidate list;
-//   (b) carry   every box kept in an earlier window marks the window candidates it suppresses (see `sweep_row`);
-//   (c) diag    for every block of 32 consecutive candidates the 32 x 32 "i suppresses j > i" bits, all blocks at once
-//               (one warp per row: column = lane, one ballot);
-//   (d) blocks  in order, two barriers each: one warp resolves the block from its diagonal bits and the removed
-//               bitmap (no bit among alive rows: everybody alive is kept; else a 32-step chain on registers), then
-//               every kept candidate of the block gets a warp that walks the cells under its box and marks the later
-//               candidates it suppresses (atomic OR into the removed bitmap);
-//   (e) insert  kept candidates are appended to the kept arrays (keep order).
-// Which cells a kept box must look at: for iou_thres >= 0.55 a suppressed box has its centre inside the kept box (the
-// intersection covers more than half of it; margin 5 % of its size >> fp32 rounding), so the cells under the kept box;
-// below that, the box grown by the largest half-extent in the window (two boxes that intersect have centres closer
-// than the sum of their half-extents); for iou_thres < 0 (everything suppresses) all cells.  Every pair that is tested
-// uses the exact expression (suppresses()), so the keep set equals torchvision's.  `[:TOP_K]` is an early exit.
-constexpr int SIDX_MAX = 4096;   // sorted index list kept in shared memory up to this many candidates
-constexpr int NMS_G = 16;        // centre cells per dimension
-
-struct CellGrid {
-    float inv_cw, inv_ch;
-    __device__ __forceinline__ int cx(float x) const { return min(max(__float2int_rd(__fmul_rn(x, inv_cw)), 0), NMS_G - 1); }
-    __device__ __forceinline__ int cy(float y) const { return min(max(__float2int_rd(__fmul_rn(y, inv_ch)), 0), NMS_G - 1); }
-};
-
-// One warp: the kept box (bi, ai, li) against the window candidates whose centre cell lies under it (grown by `grow`),
-// restricted to sorted indices > after; suppressed candidates are ORed into s_removed.
-__device__ __forceinline__ void sweep_row(const K2Params &P, const CellGrid &G, const float4 &bi, float ai, int li, int after,
-                                          float grow, const int *s_cellstart, const unsigned short *s_cellcand,
-                                          const float4 *s_sbox, const float *s_sarea, const int *s_slabel, unsigned *s_removed,
-                                          int lane) {
-    int x0 = 0, x1 = NMS_G - 1, y0 = 0, y1 = NMS_G - 1;
-    if (P.early_out) {
-        x0 = G.cx(__fsub_rn(bi.x, grow)); x1 = G.cx(__fadd_rn(bi.z, grow));
-        y0 = G.cy(__fsub_rn(bi.y, grow)); y1 = G.cy(__fadd_rn(bi.w, grow));
-        if (!(bi.x <= bi.z && bi.y <= bi.w)) return;   // inverted / NaN box: never intersects anything
-    }
-    for (int y = y0; y <= y1; ++y) {
-        const int beg = s_cellstart[y * NMS_G + x0], end = s_cellstart[y * NMS_G + x1 + 1];   // cells of a row are consecutive
-        for (int q = beg + lane; q < end; q += 32) {
-            const int j = s_cellcand[q];
-            if (j <= after || ((s_removed[j >> 5] >> (j & 31)) & 1u)) continue;
-            if (suppresses(bi, ai, li, s_sbox[j], s_sarea[j], s_slabel[j], P.thr_up, P.early_out, P.class_mode, P.fast))
-                atomicOr(&s_removed[j >> 5], 1u << (j & 31));
-        }
-    }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT) nms_kernel(const __grid_constant__ K2Params P) {
+template <int K2_THREADS>
+__global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int W = NT, NWARPS = NT / 32;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = P.max_det;
+    constexpr int WIN = K2_TAIL_WIN;
 
-    // ---- shared-memory carve-up (the sort's exchange buffer overlays it)
+    // ---- shared-memory carve-up (the sort's exchange buffer / sorted-index list overlays it)
     uint32_t *s_sidx = reinterpret_cast<uint32_t *>(smem_raw);
-    float4 *s_sbox = reinterpret_cast<float4 *>(smem_raw + P.region0_bytes);                 // [W] window, NMS coordinates
-    float4 *s_kbox = s_sbox + W;                                                             // [K] kept boxes
-    float *s_sarea = reinterpret_cast<float *>(s_kbox + K);                                  // [W]
-    float *s_sscore = s_sarea + W;                                                           // [W]
-    int *s_slabel = reinterpret_cast<int *>(s_sscore + W);                                   // [W]
-    int *s_sanchor = s_slabel + W;                                                           // [W]
-    int *s_sorig = s_sanchor + W;                                                            // [W] index into the filtered list
-    float *s_karea = reinterpret_cast<float *>(s_sorig + W);                                 // [K]
+    float4 *s_sbox = reinterpret_cast<float4 *>(smem_raw + P.region0_bytes);                 // [WIN] window, NMS coordinates
+    float4 *s_kbox = s_sbox + WIN;                                                           // [K] kept boxes
+    float2 *s_sctr = reinterpret_cast<float2 *>(s_kbox + K);                                 // [WIN] centres
+    float2 *s_kctr = s_sctr + WIN;                                                           // [K] kept centres
+    float *s_sarea = reinterpret_cast<float *>(s_kctr + K);                                  // [WIN]
+    float *s_sscore = s_sarea + WIN;                                                         // [WIN]
+    int *s_slabel = reinterpret_cast<int *>(s_sscore + WIN);                                 // [WIN]
+    int *s_sanchor = s_slabel + WIN;                                                         // [WIN]
+    int *s_sorig = s_sanchor + WIN;                                                          // [WIN] index into the filtered list
+    float *s_karea = reinterpret_cast<float *>(s_sorig + WIN);                               // [K]
     float *s_kscore = s_karea + K;                                                           // [K]
     int *s_klabel = reinterpret_cast<int *>(s_kscore + K);                                   // [K]
     int *s_kanchor = s_klabel + K;                                                           // [K]
     int *s_korig = s_kanchor + K;                                                            // [K]
-    uint32_t *s_diag = reinterpret_cast<uint32_t *>(s_korig + K);                            // [W] diagonal-block row words
-    unsigned short *s_cellcand = reinterpret_cast<unsigned short *>(s_diag + W);             // [W] candidates sorted by centre cell
-    __shared__ int s_cellcnt[NMS_G * NMS_G], s_cellstart[NMS_G * NMS_G + 1];
-    __shared__ unsigned s_removed[32];  // window bitmap: suppressed by a kept box / past the end
-    __shared__ unsigned s_keptw[32];    // window bitmap: kept
-    __shared__ int s_kbase[32];         // kept slots handed out before each block of 32
-    __shared__ int s_nkept;
-    __shared__ unsigned s_grow;         // largest half-extent in the window (float bits)
+    int *s_knext = s_korig + K;                                                              // [K] next kept box of the same cell
+    int *s_scell = s_knext + K;                                                              // [WIN] packed cell range under the box
+    __shared__ unsigned int s_row32[NMS_CHUNK * 2];
+    __shared__ int s_cellhead[MAX_CELLS], s_celltail[MAX_CELLS];
+    __shared__ unsigned int s_supA[2];
+    __shared__ int s_anyrow;
+    __shared__ unsigned short s_pair[NMS_CHUNK * (NMS_CHUNK - 1) / 2];   // (i << 8) | j for every pair i < j of a chunk
+    __shared__ unsigned long long s_keepm;
 
     BT_PHASE_INIT();
     // zero the per-image accumulators the mask kernel adds into
@@ -318,38 +277,43 @@ __global__ void __launch_bounds__(NT, 1024 / NT) nms_kernel(const __grid_constan
     if (tid == 10 && b == 0) *P.pool_used = 0ull;
     if (tid == 11 && b == 0) { P.n_items[0] = 0; P.n_items[1] = 0; }
     if (tid == 9 && P.seg_prob_sum) P.seg_prob_sum[b] = 0.0;
-    for (int i = tid; i < K; i += NT) {
+    for (int i = tid; i < K; i += K2_THREADS) {
         if (P.inst_area) P.inst_area[(size_t)b * K + i] = 0;
         if (P.inst_inter) P.inst_inter[(size_t)b * K + i] = 0;
     }
+    if (tid < MAX_CELLS) { s_cellhead[tid] = -1; s_celltail[tid] = -1; }
+    if (tid >= 1 && tid < NMS_CHUNK)
+        for (int i = 0; i < tid; ++i) s_pair[tid * (tid - 1) / 2 + i] = (unsigned short)((i << 8) | tid);
     const int M_all = P.n_cand[b];
     const float4 *cbox = P.cand_box + (size_t)b * P.cap;
     const float *cscore = P.cand_score + (size_t)b * P.cap;
     const int32_t *clabel = P.cand_label + (size_t)b * P.cap;
     const int32_t *canchor = P.cand_anchor + (size_t)b * P.cap;
-    const CellGrid G{P.inv_cw, P.inv_ch};
 
-    // ---- 1. stable descending sort: key = (descending score key << 32) | candidate index.  Up to SIDX_MAX candidates the
-    // widest strides of the network are exchanged through shared memory; longer lists use the workspace for that (and
-    // keep their sorted keys there), so the kernel's shared memory does not grow with the candidate capacity.
+    // ---- 1. stable descending sort: key = (descending score key << 32) | candidate index
     const unsigned long long *gkeys = nullptr;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        unsigned long long *keys = P.sort_keys + (size_t)b * P.cap_pow2;
-        if (M_all <= NT) sort_keys_regs<1>(cscore, M_all, NT, s_x, s_sidx, nullptr);
-        else if (M_all <= 2 * NT) sort_keys_regs<2>(cscore, M_all, NT, s_x, s_sidx, nullptr);
-        else if (M_all <= SIDX_MAX) sort_keys_regs<SIDX_MAX / NT>(cscore, M_all, NT, s_x, s_sidx, nullptr);
-        else if (M_all <= 16 * NT) { sort_keys_regs<16>(cscore, M_all, NT, keys, s_sidx, keys); gkeys = keys; }
+        if (K2_THREADS == 512 && M_all <= 512) sort_to_smem<1>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= 1024) sort_to_smem<2>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= 2048) sort_to_smem<4>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= SORT_SMALL_MAX) sort_to_smem<8>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 1024) sort_to_smem<1>(cscore, M_all, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 2048) sort_to_smem<2>(cscore, M_all, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 4096) sort_to_smem<4>(cscore, M_all, 1024, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= 8192) sort_to_smem<16>(cscore, M_all, 512, s_x, s_sidx);
+        else if (K2_THREADS == 1024 && M_all <= SORT_REG_MAX) sort_to_smem<16>(cscore, M_all, 1024, s_x, s_sidx);
         else {
             // very long lists (30k-candidate stress case): bitonic network in global memory
             int P2 = 1;
             while (P2 < M_all) P2 <<= 1;
-            for (int i = tid; i < P2; i += NT)
+            unsigned long long *keys = P.sort_keys + (size_t)b * P.cap_pow2;
+            for (int i = tid; i < P2; i += K2_THREADS)
                 keys[i] = (i < M_all) ? (((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)i) : ~0ull;
             __syncthreads();
             for (int k = 2; k <= P2; k <<= 1)
                 for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int t = tid; t < (P2 >> 1); t += NT) {
+                    for (int t = tid; t < (P2 >> 1); t += K2_THREADS) {
                         int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                         int l = i | j;
                         unsigned long long a = keys[i], c = keys[l];
@@ -364,141 +328,201 @@ __global__ void __launch_bounds__(NT, 1024 / NT) nms_kernel(const __grid_constan
     BT_PHASE_MARK(1, 0);   // sort
     const int M = min(M_all, P.limit);   // Ultralytics max_nms: only the best `limit` candidates enter the sweep
 
-    // ---- 2. greedy sweep, one window of W sorted candidates at a time
+    auto cell_x = [&](float x) { return min(max(__float2int_rd(__fmul_rn(x, P.inv_cw)), 0), P.gx - 1); };
+    auto cell_y = [&](float y) { return min(max(__float2int_rd(__fmul_rn(y, P.inv_ch)), 0), P.gy - 1); };
+
+    // ---- 2. greedy sweep over windows of 1024 sorted candidates, 64 at a time
     int nkept = 0;
-    for (int w0 = 0; w0 < M && nkept < K; w0 += W) {
-        const int wn = min(W, M - w0), RWn = (wn + 31) >> 5;
-        // (a) stage the window in NMS order and bin it by centre cell
-        if (tid < NMS_G * NMS_G) s_cellcnt[tid] = 0;
-        if (tid < 32) s_keptw[tid] = 0;
-        if (tid == 32) s_grow = 0u;
-        __syncthreads();
-        int my_cell = 0, my_pos = 0;
-        if (tid < wn) {
-            const int idx = gkeys ? (int)(unsigned)gkeys[w0 + tid] : (int)s_sidx[w0 + tid];
+    for (int w0 = 0; w0 < M && nkept < K; w0 += WIN) {
+        const int wn = min(WIN, M - w0);
+        // (a) stage the window in NMS order; bucket its candidates by the cell of their centre
+        for (int t = tid; t < wn; t += K2_THREADS) {
+            const int idx = gkeys ? (int)(unsigned)gkeys[w0 + t] : (int)s_sidx[w0 + t];
             float4 bx = __ldg(cbox + idx);
             const int lb = __ldg(clabel + idx);
-            s_sscore[tid] = __ldg(cscore + idx);
-            s_sanchor[tid] = __ldg(canchor + idx);
-            s_sorig[tid] = idx;
+            s_sscore[t] = __ldg(cscore + idx);
+            s_sanchor[t] = __ldg(canchor + idx);
+            s_sorig[t] = idx;
             if (P.class_mode == BT_CLASS_OFFSET) {
                 const float off = __fmul_rn((float)lb, P.max_wh);
                 bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
                 bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
             }
-            s_sbox[tid] = bx;
-            s_sarea[tid] = box_area(bx);
-            s_slabel[tid] = lb;
-            my_cell = G.cy(__fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f)) * NMS_G + G.cx(__fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f));
-            my_pos = atomicAdd(&s_cellcnt[my_cell], 1);
-            if (!P.centre_cull) {   // largest half-extent (non-negative floats order like their bit patterns; NaN / negative: ignored)
-                const float he = __fmul_rn(fmaxf(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y)), 0.5f);
-                if (he > 0.0f) atomicMax(&s_grow, __float_as_uint(he));
+            s_sbox[t] = bx;
+            s_sctr[t] = make_float2(__fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f), __fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f));
+            {   // cells under the box: x0 | y0 << 4 | nx << 8 | ny << 13 (nx = 1, ny = 0 for an inverted box)
+                const int gx0 = cell_x(bx.x), gy0 = cell_y(bx.y);
+                const int ncx = max(cell_x(bx.z) - gx0 + 1, 1), ncy = max(cell_y(bx.w) - gy0 + 1, 0);
+                s_scell[t] = gx0 | (gy0 << 4) | (ncx << 8) | (ncy << 13);
             }
+            s_sarea[t] = box_area(bx);
+            s_slabel[t] = lb;
         }
         __syncthreads();
-        if (wid == 0) {   // exclusive scan of the 256 cell counts: 8 per lane
-            int v[8], sum = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { v[q] = s_cellcnt[lane * 8 + q]; sum += v[q]; }
-            int incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += u;
-            }
-            int run = incl - sum;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { s_cellstart[lane * 8 + q] = run; run += v[q]; }
-            if (lane == 31) s_cellstart[NMS_G * NMS_G] = run;
-        }
-        {   // candidates past the end of the list count as removed
-            const unsigned m = __ballot_sync(0xffffffffu, tid >= wn);
-            if (lane == 0) s_removed[wid] = m;
-        }
-        __syncthreads();
-        if (tid < wn) s_cellcand[s_cellstart[my_cell] + my_pos] = (unsigned short)tid;
-        __syncthreads();
-        const float grow = P.centre_cull ? 0.0f : __uint_as_float(s_grow);
         BT_PHASE_MARK(1, 1);   // stage window
-        // (b) boxes kept in earlier windows against this window
-        for (int k = wid; k < nkept; k += NWARPS)
-            sweep_row(P, G, s_kbox[k], s_karea[k], s_klabel[k], -1, grow, s_cellstart, s_cellcand, s_sbox, s_sarea, s_slabel, s_removed, lane);
-        __syncthreads();
-        BT_PHASE_MARK(1, 2);   // carry
-        // (c) diagonal blocks: row i against the 32 candidates of its own block
-        for (int i = wid; i < wn; i += NWARPS) {
-            if ((s_removed[i >> 5] >> (i & 31)) & 1u) continue;   // warp-uniform
-            const int c = (i & ~31) + lane;
-            const bool p = c > i && c < wn &&
-                           suppresses(s_sbox[i], s_sarea[i], s_slabel[i], s_sbox[c], s_sarea[c], s_slabel[c], P.thr_up, P.early_out,
-                                      P.class_mode, P.fast);
-            const unsigned bal = __ballot_sync(0xffffffffu, p);
-            if (lane == 0) s_diag[i] = bal;
-        }
-        __syncthreads();
-        BT_PHASE_MARK(1, 3);   // diag
-        // (d) the blocks, in order
-        int nk = nkept;
-        for (int blk = 0; blk < RWn && nk < K; ++blk) {
-            if (wid == 0) {
-                const unsigned cur = s_removed[blk];
-                const unsigned alive = ~cur;
-                const unsigned diag = ((alive >> lane) & 1u) ? s_diag[blk * 32 + lane] : 0u;   // rows of removed candidates are not used
-                unsigned kept;
-                if (!__any_sync(0xffffffffu, diag != 0u)) {
-                    kept = alive;      // nobody alive suppresses anybody in the block
-                } else {
-                    unsigned c = cur;
-                    kept = 0u;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const unsigned dj = __shfl_sync(0xffffffffu, diag, j);
-                        if (!((c >> j) & 1u)) { kept |= 1u << j; c |= dj; }
+        // (c) the chunks, in order
+        for (int c0 = 0; c0 < wn && nkept < K; c0 += NMS_CHUNK) {
+            const int n_in = min(NMS_CHUNK, wn - c0);
+            if (tid < 2 * NMS_CHUNK) s_row32[tid] = 0;
+            if (tid < 2) s_supA[tid] = 0;
+            if (tid == 2) s_anyrow = 0;
+            __syncthreads();
+            // (A) chunk vs kept boxes.  Centre-cull mode: only kept boxes whose centre lies in a cell under
+            // the candidate's box can suppress it; 4 threads per candidate walk those cells (8 warps: the
+            // phase is issue-bound, r01k).  Otherwise 16 threads per candidate stride over all kept boxes.
+#ifdef BT_PHASE_TIMING
+            const long long _a0 = clock64();
+#endif
+            if (P.centre_cull) {
+                if (tid < 4 * NMS_CHUNK) {
+                    const int ci = tid >> 2, sub = tid & 3;
+                    bool f = false;
+                    if (ci < n_in) {
+                        const float4 bj = s_sbox[c0 + ci];
+                        const float2 cj = s_sctr[c0 + ci];
+                        const float aj = s_sarea[c0 + ci];
+                        const int lj = s_slabel[c0 + ci];
+                        const int pc = s_scell[c0 + ci];
+                        const int gx0 = pc & 15, gy0 = (pc >> 4) & 15, ncx = (pc >> 8) & 31, ncy = (pc >> 13) & 31;
+                        int qx = sub, qy = 0;   // cells sub, sub + 4, ... in row-major order (ncx >= 1)
+                        while (qx >= ncx) { qx -= ncx; ++qy; }
+                        while (qy < ncy && !f) {
+                            // lists are in keep order: the strongest box of a cluster comes first and usually settles it
+                            for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0 && !f; k = s_knext[k]) {
+                                const float2 ck = s_kctr[k];
+                                if (!(ck.x >= bj.x && ck.x <= bj.z && ck.y >= bj.y && ck.y <= bj.w)) continue;
+                                f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                               P.class_mode, 1, cj.x, cj.y, P.fast);
+                            }
+                            qx += 4;
+                            while (qx >= ncx) { qx -= ncx; ++qy; }
+                        }
                     }
+                    const unsigned m = __ballot_sync(0xffffffffu, f);
+                    if ((lane & 3) == 0 && ((m >> lane) & 0xfu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
                 }
-                const int room = K - nk;   // [:TOP_K]: only the first `room` keeps survive (room >= 1 here)
-                if (__popc(kept) > room) kept &= (2u << __fns(kept, 0, room)) - 1u;
-                if (lane == 0) { s_keptw[blk] = kept; s_kbase[blk] = nk; s_nkept = nk + __popc(kept); }
+            } else {
+                for (int ci = tid >> 4; ci < NMS_CHUNK; ci += K2_THREADS >> 4) {   // warp-uniform trip count
+                    const int sub = tid & 15;
+                    bool f = false;
+                    if (ci < n_in) {
+                        const float4 bj = s_sbox[c0 + ci];
+                        const float aj = s_sarea[c0 + ci];
+                        const int lj = s_slabel[c0 + ci];
+                        for (int k = sub; k < nkept && !f; k += 16)
+                            f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
+                                           P.class_mode, 0, 0.0f, 0.0f, P.fast);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, f);
+                    if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
+                }
+            }
+#ifdef BT_PHASE_TIMING
+            {
+                const unsigned dt = (unsigned)(clock64() - _a0);
+                const unsigned mx = __reduce_max_sync(0xffffffffu, dt);
+                if (lane == 0 && wid < 8) { atomicAdd(&g_phase_cycles[1][12], (unsigned long long)mx); atomicAdd(&g_phase_cycles[1][13], 1ull); }
+                if (lane == 0 && wid >= 8) { atomicAdd(&g_phase_cycles[1][14], (unsigned long long)mx); }
+            }
+#endif
+            __syncthreads();
+            BT_PHASE_MARK(1, 8);   // chunk: A
+            // (B) "who suppresses me" rows of the candidates A left undecided, against the undecided
+            // earlier candidates of the chunk only (a cluster of hundreds of candidates on one object is
+            // settled by A as soon as its leader is kept).  One thread per pair (i < j) of the chunk, from a
+            // table of the 2016 pairs; the exact IoU runs only for pairs that pass the cheap necessary test.
+            const unsigned long long valid = (n_in == 64) ? ~0ull : ((1ull << n_in) - 1ull);
+            const unsigned long long und0 = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
+            for (int pq = tid; pq < NMS_CHUNK * (NMS_CHUNK - 1) / 2; pq += K2_THREADS) {
+                const int pr = s_pair[pq], io = pr >> 8, jo = pr & 255;
+                if (!((und0 >> io) & (und0 >> jo) & 1ull)) continue;
+                const int i = c0 + io, j = c0 + jo;
+                const float4 bi = s_sbox[i], bj = s_sbox[j];
+                const float2 cj = s_sctr[j];
+                if (P.centre_cull) {
+                    const float2 ci = s_sctr[i];
+                    if (!(ci.x >= bj.x && ci.x <= bj.z && ci.y >= bj.y && ci.y <= bj.w && cj.x >= bi.x && cj.x <= bi.z &&
+                          cj.y >= bi.y && cj.y <= bi.w))
+                        continue;
+                } else if (P.early_out) {
+                    if (!(fminf(bi.z, bj.z) > fmaxf(bi.x, bj.x) && fminf(bi.w, bj.w) > fmaxf(bi.y, bj.y))) continue;
+                }
+                if (suppresses(bi, s_sarea[i], s_slabel[i], bj, s_sarea[j], s_slabel[j], P.thr_up, P.early_out, P.class_mode,
+                               P.centre_cull, cj.x, cj.y, P.fast)) {
+                    atomicOr(&s_row32[jo * 2 + (io >> 5)], 1u << (io & 31));
+                    s_anyrow = 1;
+                }
             }
             __syncthreads();
-            const unsigned kept = s_keptw[blk];
-            nk = s_nkept;
-            if (nk >= K) break;            // nothing after the K-th keep matters
-            if (blk + 1 < RWn) {
-                // every kept candidate of the block marks the later candidates it suppresses
-                for (int q = wid; q < 32; q += NWARPS) {
-                    if (!((kept >> q) & 1u)) continue;   // warp-uniform
-                    const int i = blk * 32 + q;
-                    sweep_row(P, G, s_sbox[i], s_sarea[i], s_slabel[i], blk * 32 + 31, grow, s_cellstart, s_cellcand, s_sbox, s_sarea,
-                              s_slabel, s_removed, lane);
+            BT_PHASE_MARK(1, 11);  // chunk: B
+            unsigned long long keepm;
+            if (s_anyrow) {
+                // (C) one warp resolves the chunk as a fixpoint over the rows (lane: rows lane, lane + 32)
+                if (wid == 0) {
+                    const unsigned long long row_a = ((unsigned long long)s_row32[lane * 2 + 1] << 32) | s_row32[lane * 2];
+                    const unsigned long long row_b = ((unsigned long long)s_row32[(lane + 32) * 2 + 1] << 32) | s_row32[(lane + 32) * 2];
+                    unsigned long long und = und0, km = 0ull;
+                    while (und) {
+                        // kept: no undecided and no kept suppressor left; removed: a kept suppressor exists
+                        const bool ua = (und >> lane) & 1ull, ub = (und >> (lane + 32)) & 1ull;
+                        const unsigned long long live = und | km;
+                        const unsigned long long newk =
+                            ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & live) == 0ull) << 32) |
+                            __ballot_sync(0xffffffffu, ua && (row_a & live) == 0ull);
+                        km |= newk;
+                        und &= ~newk;
+                        const unsigned long long rem =
+                            ((unsigned long long)__ballot_sync(0xffffffffu, ub && (row_b & km) != 0ull) << 32) |
+                            __ballot_sync(0xffffffffu, ua && (row_a & km) != 0ull);
+                        und &= ~rem;
+                    }
+                    if (lane == 0) s_keepm = km;
+                }
+                __syncthreads();
+                keepm = s_keepm;
+            } else {
+                keepm = und0;   // nobody in the chunk suppresses anybody: every undecided candidate is kept
+            }
+            {
+                // [:TOP_K]: only the first `room` keeps survive (later ones cannot affect earlier ones)
+                const int room = K - nkept;
+                if (__popcll(keepm) > room) {   // room < 64 here: cut after the room-th set bit
+                    const unsigned lo = (unsigned)keepm, hi = (unsigned)(keepm >> 32);
+                    const int nlo = __popc(lo);
+                    if (room == 0) keepm = 0ull;
+                    else if (room <= nlo) keepm &= (2ull << __fns(lo, 0, room)) - 1ull;
+                    else keepm &= (2ull << (32 + __fns(hi, 0, room - nlo))) - 1ull;
                 }
             }
-            __syncthreads();
-        }
-        __syncthreads();   // a break above leaves the loop between the barriers: this one is reached by every thread
-        BT_PHASE_MARK(1, 4);   // blocks
-        // (e) append the kept candidates of the window (keep order)
-        {
-            const unsigned kw = s_keptw[wid];
-            if (tid < wn && ((kw >> lane) & 1u)) {
-                const int slot = s_kbase[wid] + __popc(kw & ((1u << lane) - 1u));
-                s_kbox[slot] = s_sbox[tid];
-                s_karea[slot] = s_sarea[tid];
-                s_klabel[slot] = s_slabel[tid];
-                s_kscore[slot] = s_sscore[tid];
-                s_kanchor[slot] = s_sanchor[tid];
-                s_korig[slot] = s_sorig[tid];
+            BT_PHASE_MARK(1, 9);   // chunk: C
+            if (tid < NMS_CHUNK && ((keepm >> tid) & 1ull)) {
+                const int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
+                const float2 ctr = s_sctr[c0 + tid];
+                s_kbox[slot] = s_sbox[c0 + tid];
+                s_kctr[slot] = ctr;
+                s_karea[slot] = s_sarea[c0 + tid];
+                s_klabel[slot] = s_slabel[c0 + tid];
+                s_kscore[slot] = s_sscore[c0 + tid];
+                s_kanchor[slot] = s_sanchor[c0 + tid];
+                s_korig[slot] = s_sorig[c0 + tid];
+                if (P.centre_cull) {
+                    // append to the cell's list (keep order: earlier, stronger boxes first)
+                    const int cell = cell_y(ctr.y) * P.gx + cell_x(ctr.x);
+                    s_knext[slot] = -1;
+                    const int prev = atomicExch(&s_celltail[cell], slot);
+                    if (prev < 0) s_cellhead[cell] = slot; else s_knext[prev] = slot;
+                }
             }
-            nkept = s_nkept;
+            nkept += __popcll(keepm);
+            BT_PHASE_MARK(1, 10);  // chunk: insert
         }
-        __syncthreads();   // the window is re-staged next; the kept arrays are read by every thread
-        BT_PHASE_MARK(1, 5);   // insert
+        __syncthreads();   // the window is re-staged next
+        BT_PHASE_MARK(1, 3);   // chunks
     }
 
     // ---- 3. package kept detections (running_main_v2.py:818-839); zero-fill the padding
     if (tid == 0) P.det_count[b] = nkept;
-    for (int k = tid; k < K; k += NT) {
+    for (int k = tid; k < K; k += K2_THREADS) {
         float *o = P.dets + ((size_t)b * K + k) * 6;
         if (k < nkept) {
             const int idx = s_korig[k];
@@ -527,9 +551,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) nms_kernel(const __grid_constan
         int32_t *dm = P.dt_match + (size_t)b * per_img;
         if ((per_img & 3) == 0) {
             int4 *d4 = reinterpret_cast<int4 *>(dm);   // per-image base is 16-byte aligned when per_img % 4 == 0
-            for (int q = tid; q < (int)(per_img >> 2); q += NT) d4[q] = make_int4(0, 0, 0, 0);
+            for (int q = tid; q < (int)(per_img >> 2); q += K2_THREADS) d4[q] = make_int4(0, 0, 0, 0);
         } else {
-            for (int q = tid; q < (int)per_img; q += NT) dm[q] = 0;
+            for (int q = tid; q < (int)per_img; q += K2_THREADS) dm[q] = 0;
         }
     }
     BT_PHASE_MARK(1, 6);   // package
@@ -892,6 +916,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.acc = w.acc; P.inst_area = io.inst_area; P.inst_inter = io.inst_inter;
     P.seg_prob_sum = io.seg_prob_sum;
     P.sweep = static_cast<long long *>(io.sweep); P.image_offset = p.image_offset; P.drop_gt_no_cand = p.drop_gt_no_cand; P.image_base = io.image_base;
+    P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
     P.crop = p.crop; P.PW = p.proto_w; P.PH = p.proto_h;
     P.rx = (float)((double)p.proto_w / (double)p.img_w);
     P.ry = (float)((double)p.proto_h / (double)p.img_h);
@@ -900,23 +925,27 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.items = w.items; P.n_items = w.n_items; P.item_cap = (int)w.item_cap;
     P.tile_cnt = w.tile_cnt; P.tile_list = w.tile_list; P.ntiles = mask_tiles(&p); P.ntx = (p.proto_w + TA_W - 1) / TA_W;
     if (P.ntiles > PLAN_MAX_TILES) return BT_ERR_UNSUPPORTED;
-    // shared memory of nms_kernel<NT>: [sorted-index list (<= SIDX_MAX entries; longer lists live in the workspace) |
-    // window arrays (36 B/candidate, W = NT) + kept arrays (36 B/slot) | diagonal words + cell-sorted list (6 B/candidate)];
-    // the sort's exchange buffer (8 B per key, up to SIDX_MAX keys) overlays it.  ~70 KB for NT = 1024, ~45 KB for 512.
-    // BtParams.nms_threads = 512: windows of 512 candidates and 32 k registers per image leave more room on the SM for
-    // CTAs of the mask kernels of other batches in flight; 1024 (default): one window covers the ~600-900 candidates of
-    // a 640^2 image at conf 0.05.
+    // centre-cell grid: cells of >= 64 px, at most 16 x 16
+    P.gx = p.img_w / 64 < 1 ? 1 : (p.img_w / 64 > 16 ? 16 : p.img_w / 64);
+    P.gy = p.img_h / 64 < 1 ? 1 : (p.img_h / 64 > 16 ? 16 : p.img_h / 64);
+    P.inv_cw = (float)P.gx / (float)p.img_w;
+    P.inv_ch = (float)P.gy / (float)p.img_h;
+
+    // shared memory of nms_kernel: [sorted-index list | window (48 B/candidate) + kept arrays (48 B/slot)];
+    // the sort's exchange buffer overlays everything.
+    // BtParams.nms_threads = 512: 32 k registers and < 80 KB of shared memory per image leave room on the SM for CTAs of
+    // the mask kernels of other batches in flight, or for a second image (btpost.Pipeline asks for it: +8 % images/s
+    // with six batches in flight, but a single step is 11 us slower).  The 1024-thread variant (default) also sorts
+    // long candidate lists in registers; the small one falls back to the global-memory network above 4096 candidates.
     const int nt_req = p.nms_threads ? p.nms_threads : dbg_env_int("BTPOST_NMS_NT", 1024);
     const int nt = nt_req == 512 ? 512 : 1024;
-    const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > SIDX_MAX ? SIDX_MAX : P.cap_pow2);
+    const int sort_max = nt == 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
+    const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > sort_max ? sort_max : P.cap_pow2);
     const size_t region0 = align_up((size_t)sort_slots * 4, 16);
     P.region0_bytes = (int)region0;
-    size_t smem_a = region0 + (size_t)nt * 36 + (size_t)p.max_det * 36 + (size_t)nt * 6 + 64;
+    size_t smem_a = region0 + (size_t)K2_TAIL_WIN * 48 + (size_t)p.max_det * 48 + 64;
     if (smem_a < (size_t)sort_slots * 8) smem_a = (size_t)sort_slots * 8;
     if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
-    P.centre_cull = (p.iou_thres >= 0.55) ? 1 : 0;
-    P.inv_cw = (float)NMS_G / (float)p.img_w;
-    P.inv_ch = (float)NMS_G / (float)p.img_h;
     // match_kernel: COCO tables
     const int coco_doubles = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;   // boxes + room for a [K x 4] IoU block
     P.coco_smem_doubles = coco_doubles;
