@@ -70,6 +70,8 @@ struct K3Params {
     float *seg_logits;
     double *seg_prob_sum;   // [B] optional: sum of sigmoid(logit) over the projector mask's foreground pixels
     long long *sweep;       // optional sweep state: per-image Dice / IoU are added to its header (2^-40 fixed point)
+    u64 valid_tab[9];       // valid-pixel mask of a block by (row class, column class): first / interior / last
+    float inv_NBX;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,10 +166,10 @@ __device__ __forceinline__ unsigned cell_bits_log(float v00, float v01, float v1
 
 // Valid-pixel mask of a cell: border cells (-1) own output rows/cols {0,1}; the last cell row/col
 // owns only the two pixels left before the image edge; cells past the last one do not exist.
-__device__ __forceinline__ unsigned cell_valid(int ci, int cj, int PH, int PW, int S_h, int S_w) {
+__host__ __device__ __forceinline__ unsigned cell_valid(int ci, int cj, int PH, int PW, int S_h, int S_w) {
     if (ci > PH - 1 || cj > PW - 1) return 0u;
-    const int nry = (ci < 0) ? 2 : min(4, S_h - (4 * ci + 2));
-    const int nrx = (cj < 0) ? 2 : min(4, S_w - (4 * cj + 2));
+    const int nry = (ci < 0) ? 2 : (S_h - (4 * ci + 2) < 4 ? S_h - (4 * ci + 2) : 4);
+    const int nrx = (cj < 0) ? 2 : (S_w - (4 * cj + 2) < 4 ? S_w - (4 * cj + 2) : 4);
     const unsigned rowm = (1u << nrx) - 1u;
     unsigned m = 0;
     for (int r = 0; r < nry; ++r) m |= rowm << (4 * r);
@@ -193,12 +195,18 @@ __device__ __forceinline__ BlockGeo block_geo(int by, int bx, int PH, int PW) {
     return g;
 }
 
-__device__ __forceinline__ u64 block_valid(int by, int bx, int PH, int PW, int S_h, int S_w) {
+// Valid-pixel mask of a block.  Only the first and the last block row / column differ from all-ones, so the host
+// computes the nine masks once (`valid_tab`, launch_masks) and the kernels look them up.
+__host__ __device__ __forceinline__ u64 block_valid_slow(int by, int bx, int PH, int PW, int S_h, int S_w) {
     const int ciA = 2 * by - 1, cjA = 2 * bx - 1;
-    if (by > 0 && bx > 0 && ciA + 1 < PH - 1 && cjA + 1 < PW - 1) return ~0ull;
     const u64 vAA = cell_valid(ciA, cjA, PH, PW, S_h, S_w), vAB = cell_valid(ciA, cjA + 1, PH, PW, S_h, S_w);
     const u64 vBA = cell_valid(ciA + 1, cjA, PH, PW, S_h, S_w), vBB = cell_valid(ciA + 1, cjA + 1, PH, PW, S_h, S_w);
     return vAA | (vAB << 16) | (vBA << 32) | (vBB << 48);
+}
+__device__ __forceinline__ u64 block_valid(const K3Params &P, int by, int bx) {
+    if (by > 0 && bx > 0 && by < P.NBY - 1 && bx < P.NBX - 1) return ~0ull;   // interior: the common case, no table access
+    const int rc = by == 0 ? 0 : (by == P.NBY - 1 ? 2 : 1), cc = bx == 0 ? 0 : (bx == P.NBX - 1 ? 2 : 1);
+    return P.valid_tab[rc * 3 + cc];
 }
 
 // Thresholded pixels of a 2x2 cell block from its 3x3 corner logits v[row][col] (unmasked).  BY0 / BX0: the block
@@ -273,11 +281,11 @@ __device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
     uint32_t wv[4] = {v.x, v.y, v.z, v.w}, bits = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t x = wv[j];   // byte != 0 -> bit: fold each byte to its low bit, then gather the four low bits
-        x = (x | (x >> 4)) & 0x0f0f0f0fu;
-        x = (x | (x >> 2)) & 0x03030303u;
-        x = (x | (x >> 1)) & 0x01010101u;
-        bits |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (16 * half + 4 * j);
+        // byte != 0 -> bit.  High bit of every non-zero byte (the classic "haszero" carry trick), then the four high bits
+        // are gathered into one nibble by a multiplication whose partial products land on distinct bit positions.
+        const uint32_t x = wv[j];
+        const uint32_t y = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+        bits |= (((y >> 7) * 0x01020408u) >> 24) << (16 * half + 4 * j);   // the product's top byte holds only the nibble
     }
     return bits;
 }
@@ -595,7 +603,8 @@ __device__ __forceinline__ void m1_item(const K3Params &P, int b, int q, int lan
     int inter = 0, area = 0;
     double psum = 0.0;
     if (q < NBY * NBX) {
-        const int by = q / NBX, bx = q - by * NBX;
+        int by = __float2int_rz(((float)q + 0.5f) * P.inv_NBX), bx = q - by * NBX;   // q / NBX without the integer division
+        if (bx < 0) { --by; bx += NBX; } else if (bx >= NBX) { ++by; bx -= NBX; }
         const BlockGeo g = block_geo(by, bx, PH, PW);
         const float *lm = P.lm + (size_t)b * PH * PW;
         float v[3][3];
@@ -606,7 +615,7 @@ __device__ __forceinline__ void m1_item(const K3Params &P, int b, int q, int lan
             for (int j = 0; j < 3; ++j) v[i][j] = __ldg(lm + rr[i] + cc[j]);
         const u64 gtw = __ldg(P.gtc + ((size_t)b * NBY + by) * NBX + bx);
         if (!(P.seg_logits || P.seg_mask || P.seg_prob_sum)) {
-            const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, S_h, S_w);
+            const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(P, by, bx);
             area = __popcll(bits); inter = __popcll(bits & gtw);
         } else {
             // dense outputs / v3 score: scalar path that keeps the logits
@@ -648,11 +657,8 @@ __device__ __forceinline__ void m1_item(const K3Params &P, int b, int q, int lan
                 }
         }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        inter += __shfl_down_sync(0xffffffffu, inter, d);
-        area += __shfl_down_sync(0xffffffffu, area, d);
-    }
+    inter = __reduce_add_sync(0xffffffffu, inter);
+    area = __reduce_add_sync(0xffffffffu, area);
     if (lane == 0) {
         if (inter) atomicAdd(&P.acc[b * 8 + 0], inter);
         if (area) atomicAdd(&P.acc[b * 8 + 1], area);
@@ -769,7 +775,7 @@ __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, i
         const size_t o = ((size_t)b * NBY + by) * NBX + bx;
         const u64 gtw = __ldg(P.gtc + o);   // with the corner loads, not behind the arithmetic
         if (!act) continue;
-        const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(by, bx, PH, PW, P.S_h, P.S_w);
+        const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(P, by, bx);
         if (bits && P.inst_bits) scatter_block_bits(P, bk, by, bx, bits);
         if (bits) {
             // the OR is serialised per word in the L2: the bits that were not set before are counted exactly once
@@ -781,13 +787,10 @@ __device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, i
             uinter += __popcll(fresh & gtw);
         }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        inter += __shfl_down_sync(0xffffffffu, inter, d);
-        area += __shfl_down_sync(0xffffffffu, area, d);
-        uinter += __shfl_down_sync(0xffffffffu, uinter, d);
-        uarea += __shfl_down_sync(0xffffffffu, uarea, d);
-    }
+    inter = __reduce_add_sync(0xffffffffu, inter);   // one REDUX instruction each
+    area = __reduce_add_sync(0xffffffffu, area);
+    uinter = __reduce_add_sync(0xffffffffu, uinter);
+    uarea = __reduce_add_sync(0xffffffffu, uarea);
     if (lane == 0) {
         // zeroed by the NMS kernel; a detection of several chunks adds up
         if (P.inst_area && area) atomicAdd(&P.inst_area[bk], area);
@@ -961,7 +964,12 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
     P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
     P.m1_items = (P.NBY * P.NBX + 31) / 32;
-    P.inv_K = 1.0f / (float)p.max_det; P.inv_m1 = 1.0f / (float)P.m1_items;
+    P.inv_K = 1.0f / (float)p.max_det; P.inv_m1 = 1.0f / (float)P.m1_items; P.inv_NBX = 1.0f / (float)P.NBX;
+    {
+        const int rows[3] = {0, P.NBY > 2 ? 1 : 0, P.NBY - 1}, cols[3] = {0, P.NBX > 2 ? 1 : 0, P.NBX - 1};
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) P.valid_tab[r * 3 + c] = block_valid_slow(rows[r], cols[c], p.proto_h, p.proto_w, p.img_h, p.img_w);
+    }
     CUtensorMap tm;
     if (make_proto_tmap(&tm, io.protos, P.proto_bf16, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 

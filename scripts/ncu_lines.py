@@ -1,9 +1,10 @@
 """Developer tool: per-CUDA-source-line instruction counts / stall samples of one kernel from an .ncu-rep
 (`ncu --set full --import-source on`), read here without a GPU.
-usage: python scripts/ncu_lines.py gpurun_out/x.ncu-rep [top N]"""
+usage: python scripts/ncu_lines.py gpurun_out/x.ncu-rep [top N] [kernel regex]"""
 import csv, subprocess, sys
 rep, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+kern = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 fname, hdr, agg = None, None, {}
 for r in rows:
