@@ -163,13 +163,15 @@ def main():
     ap.add_argument("--max-det", dest="max_det", type=int, default=300)
     ap.add_argument("--cpu-sample", type=int, default=4, help="images the cpu_baseline leg times (0 = skip)")
     ap.add_argument("--pipeline", type=int, default=0,
-                    help="batches in flight = slots with their own input set (0 = default: 6, or 2 for c2; 1 = strictly serial steps)")
+                    help="batches in flight = slots with their own input set (0 = auto: 6, 5 or 4, whichever divides --steps; 2 for c2; 1 = strictly serial steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period during the timed region (0 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.pipeline <= 0:
-        args.pipeline = 2 if args.workload == "c2" else 6
+        # a slot runs its steps one after the other, so a ragged last round (steps not a multiple of the depth) leaves
+        # most slots idle at the end: take the deepest of 6, 5, 4 that divides the number of steps
+        args.pipeline = 2 if args.workload == "c2" else next((d for d in (6, 5, 4) if args.steps % d == 0), 6)
 
     if args.impl == "reference":
         run_reference(args)

@@ -248,15 +248,10 @@ def make_batch(cfg: SynthConfig, l1: bool = False) -> dict:
     return out
 
 
-def make_batch_device(cfg: SynthConfig, device="cuda:0", stream=None) -> dict:
-    """Same batch as ``make_batch`` (L2 layout), generated on the GPU by ``btpost_synth_batch``: only the stream
-    keys, the object table (3 rows per image) and the GT rows are made on the host.  Returns torch tensors on
-    ``device`` (``head``, ``protos``, ``masks_gt``, ``det_boxes_gt``, ``proj_weight``) and ``proj_bias``."""
-    import ctypes as C
-
+def prepare_batch_device(cfg: SynthConfig, device="cuda:0") -> dict:
+    """Host part of the device generator: stream keys, object table (3 rows per image) and GT rows, uploaded once.
+    `generate_into` then needs no host work, so a sweep can prepare all its batches up front."""
     import torch
-
-    from . import _lib
     dev = torch.device(device)
     tab = object_table(cfg)
     inv = np.float32(1.0) / np.float32(cfg.img_size)
@@ -266,22 +261,50 @@ def make_batch_device(cfg: SynthConfig, device="cuda:0", stream=None) -> dict:
     keys = np.array([[stream_key(cfg.seed, TID_HEAD, cfg.image_offset + b), stream_key(cfg.seed, TID_PROTO, cfg.image_offset + b)]
                      for b in range(cfg.batch)], dtype=np.uint64)
     # uint64 has no torch dtype everywhere: ship the keys as int64 bit patterns
-    kh = torch.from_numpy(np.ascontiguousarray(keys[:, 0]).view(np.int64)).to(dev)
-    kp = torch.from_numpy(np.ascontiguousarray(keys[:, 1]).view(np.int64)).to(dev)
-    objs = torch.from_numpy(tab).to(dev)
-    P = cfg.proto_hw
-    head = torch.empty(cfg.batch, 4 + cfg.nc + cfg.nm, cfg.num_anchors, dtype=torch.float32, device=dev)
-    protos = torch.empty(cfg.batch, cfg.nm, P, P, dtype=torch.float32, device=dev)
-    masks = torch.empty(cfg.batch, 1, cfg.img_size, cfg.img_size, dtype=torch.uint8, device=dev)
+    return {"cfg": cfg, "objects": tab,
+            "kh": torch.from_numpy(np.ascontiguousarray(keys[:, 0]).view(np.int64)).to(dev),
+            "kp": torch.from_numpy(np.ascontiguousarray(keys[:, 1]).view(np.int64)).to(dev),
+            "objs": torch.from_numpy(tab).to(dev), "det_boxes_gt": torch.from_numpy(gt).to(dev)}
+
+
+def generate_into(prep: dict, head, protos, masks, stream=None):
+    """Device part: fills caller-owned `head` [B,4+nc+nm,N] f32, `protos` [B,nm,S/4,S/4] f32, `masks` [B,1,S,S] u8."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    cfg = prep["cfg"]
+    dev = head.device
+    assert head.dtype == torch.float32 and protos.dtype == torch.float32 and masks.dtype == torch.uint8
+    assert tuple(head.shape) == (cfg.batch, 4 + cfg.nc + cfg.nm, cfg.num_anchors) and head.is_contiguous()
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
-        rc = _lib.load().btpost_synth_batch(cfg.batch, cfg.img_size, cfg.nc, cfg.nm, C.c_void_p(kh.data_ptr()), C.c_void_p(kp.data_ptr()),
-                                           C.c_void_p(objs.data_ptr()), C.c_void_p(head.data_ptr()), C.c_void_p(protos.data_ptr()),
-                                           C.c_void_p(masks.data_ptr()), C.c_void_p(st.cuda_stream))
+        rc = _lib.load().btpost_synth_batch(cfg.batch, cfg.img_size, cfg.nc, cfg.nm, C.c_void_p(prep["kh"].data_ptr()),
+                                           C.c_void_p(prep["kp"].data_ptr()), C.c_void_p(prep["objs"].data_ptr()),
+                                           C.c_void_p(head.data_ptr()), C.c_void_p(protos.data_ptr()), C.c_void_p(masks.data_ptr()),
+                                           C.c_void_p(st.cuda_stream))
     _lib.check(rc, "btpost_synth_batch")
+
+
+def make_batch_device(cfg: SynthConfig, device="cuda:0", stream=None, out: dict | None = None) -> dict:
+    """Same batch as ``make_batch`` (L2 layout), generated on the GPU by ``btpost_synth_batch``: only the stream
+    keys, the object table (3 rows per image) and the GT rows are made on the host.  Returns torch tensors on
+    ``device`` (``head``, ``protos``, ``masks_gt``, ``det_boxes_gt``, ``proj_weight``) and ``proj_bias``; with ``out``
+    the three big tensors are generated straight into caller-owned buffers."""
+    import torch
+    dev = torch.device(device)
+    prep = prepare_batch_device(cfg, dev)
+    P = cfg.proto_hw
+    if out is not None:
+        head, protos, masks = out["head"], out["protos"], out["masks_gt"]
+    else:
+        head = torch.empty(cfg.batch, 4 + cfg.nc + cfg.nm, cfg.num_anchors, dtype=torch.float32, device=dev)
+        protos = torch.empty(cfg.batch, cfg.nm, P, P, dtype=torch.float32, device=dev)
+        masks = torch.empty(cfg.batch, 1, cfg.img_size, cfg.img_size, dtype=torch.uint8, device=dev)
+    generate_into(prep, head, protos, masks, stream)
     key = stream_key(cfg.seed, 99, 0)
     h = hash_elems(key, np.arange(cfg.nm + 1))
-    out = {"objects": tab, "head": head, "protos": protos, "masks_gt": masks, "det_boxes_gt": torch.from_numpy(gt).to(dev),
-           "proj_weight": torch.from_numpy(gauss16(h[:cfg.nm]) * np.float32(0.25)).to(dev),
-           "proj_bias": float(gauss16(h[cfg.nm:])[0] * np.float32(0.1)), "_keepalive": (kh, kp, objs)}
-    return out
+    return {"objects": prep["objects"], "head": head, "protos": protos, "masks_gt": masks, "det_boxes_gt": prep["det_boxes_gt"],
+            "proj_weight": torch.from_numpy(gauss16(h[:cfg.nm]) * np.float32(0.25)).to(dev),
+            "proj_bias": float(gauss16(h[cfg.nm:])[0] * np.float32(0.1)), "_keepalive": prep}
