@@ -357,7 +357,9 @@ class DeviceSweep:
         hdr = self.hdr.clone()
         ns, rec = merge_shards(hdr, self.records, group)
         n = int(sum(ns))
-        rec = rec.contiguous().clone() if n else rec      # the sort reorders in place: keep the ring as it was
+        if n and rec.data_ptr() == self.records.data_ptr():
+            rec = rec.clone()                              # the sort reorders in place: keep the ring as it was
+        rec = rec.contiguous()
         n_images = int(hdr[_lib.SWEEP_N_IMAGES])
         T, A, M, nc = self.T, 4, len(self.max_dets), self.nc
         precision = torch.empty(T, 101, nc, A, M, dtype=torch.float64, device=self.device)

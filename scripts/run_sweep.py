@@ -32,6 +32,9 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
     dist.all_reduce(torch.zeros(1, device=dev))   # connect the peers now: communicator set-up is not part of the sweep
     dist.all_gather_into_tensor(torch.zeros(world, device=dev), torch.zeros(1, device=dev))
+    _n = (args.images // args.batch // world + 1) * args.batch * args.max_det * 32   # a record all-gather of the real size
+    dist.all_gather_into_tensor(torch.empty(world * _n, dtype=torch.uint8, device=dev), torch.empty(_n, dtype=torch.uint8, device=dev))
+    dist.all_reduce(torch.zeros(512, dtype=torch.int64, device=dev))
 B, K = args.batch, args.max_det
 nbatches = args.images // B
 mine = [i for i in range(nbatches) if i % world == rank]          # whole batches b = r (mod G)

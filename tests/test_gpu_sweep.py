@@ -140,3 +140,50 @@ def test_device_sweep_through_pipeline_drop_flag_and_overflow():
     pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], d["proj_bias"])
     with pytest.raises(RuntimeError, match="ring too small"):
         small.finish()
+
+
+@pytest.mark.parametrize("case", [dict(n_img=40, K=12, nc=3, T=10, max_dets=(1, 10, 100), q=8),
+                                  dict(n_img=700, K=40, nc=5, T=10, max_dets=(1, 5, 20), q=4),       # image index needs two radix passes
+                                  dict(n_img=9, K=300, nc=2, T=3, max_dets=(3, 100, 300), q=64),     # rank needs two radix passes
+                                  dict(n_img=64, K=30, nc=1, T=16, max_dets=(100,), q=2)])           # one class, 16 thresholds, masses of ties
+def test_accumulate_kernel_fuzz_against_oracle(case):
+    """btpost_sweep_accumulate on RANDOM records (random match / ignore bits, heavily tied scores, classes without GT or
+    without detections, more images than one radix digit, more detections per image than one radix digit) against the
+    oracle's numpy restatement of COCOeval.accumulate: the float64 tables must be identical."""
+    from test_sweep import encode_records
+    from btpost import _lib
+    n_img, K, nc, T, max_dets, q = (case[k] for k in ("n_img", "K", "nc", "T", "max_dets", "q"))
+    rng = np.random.default_rng(n_img * 1000 + K)
+    thrs = np.linspace(0.5, 0.95, T) if T > 1 else np.array([0.5])
+    dets = np.zeros((n_img, K, 6), np.float32)
+    cnt = rng.integers(0, K + 1, n_img).astype(np.int32)
+    dt_match = np.zeros((n_img, 4, T, K), np.int32)
+    dt_ignore = np.zeros((n_img, 4, T, K), np.uint8)
+    recs = []
+    for b in range(n_img):
+        k = int(cnt[b])
+        sc = np.sort((rng.integers(1, q + 1, k) / q).astype(np.float32))[::-1]
+        dets[b, :k, 4] = sc
+        dets[b, :k, 5] = rng.integers(0, nc, k)
+        dt_match[b, :, :, :k] = rng.integers(0, 2, (4, T, k)) * rng.integers(1, 4, (4, T, k))
+        dt_ignore[b, :, :, :k] = rng.integers(0, 4, (4, T, k)) == 0
+        recs.append(dict(labels=dets[b, :k, 5].astype(np.int64), scores=dets[b, :k, 4], matched=dt_match[b][:, :, :k] > 0,
+                         ignored=dt_ignore[b][:, :, :k] > 0))
+    npig = rng.integers(0, 50, (4, nc)).astype(np.int64)
+    npig[:, rng.integers(0, nc)] *= rng.integers(0, 2)                      # sometimes a class without any GT
+    want = oracle.accumulate_ap(recs, npig, thrs, max_dets, nc)
+    out = dict(det_count=cnt, dets=dets, dt_match=dt_match, dt_ignore=dt_ignore)
+    raw = encode_records(out, 0, T)
+    perm = rng.permutation(len(raw))                                        # the ring order is whatever the atomics made it
+    raw = raw[perm]
+    sweep = DeviceSweep(nc, thrs, max_dets, capacity=len(raw) + 5, max_det_per_image=K, device="cuda:0")
+    sweep.records[:len(raw)].copy_(torch.from_numpy(raw.view(np.uint8).reshape(-1, 32)))
+    hdr = np.zeros(sweep.hdr.numel(), np.int64)
+    hdr[_lib.SWEEP_N_RECORDS], hdr[_lib.SWEEP_N_IMAGES], hdr[_lib.SWEEP_CAPACITY] = len(raw), n_img, len(raw) + 5
+    hdr[_lib.SWEEP_NPIG: _lib.SWEEP_NPIG + 64].reshape(4, 16)[:, :nc] = npig
+    sweep.hdr.copy_(torch.from_numpy(hdr))
+    res = sweep.finish()
+    np.testing.assert_array_equal(res["precision"], want["precision"])
+    np.testing.assert_array_equal(res["recall"], want["recall"])
+    for k in ("map", "map_50", "map_75", "map_small", "map_medium", "map_large"):
+        assert res[k] == want[k], k

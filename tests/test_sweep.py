@@ -130,8 +130,8 @@ def encode_records(out, image_offset, T=10):
         k = int(out["det_count"][b])
         lab = out["dets"][b, :k, 5].astype(np.int64)
         r = np.zeros(k, REC_DTYPE)
-        mt = np.moveaxis(out["dt_match"][b][:, :, :k] > 0, 2, 0).reshape(k, -1)
-        ig = np.moveaxis(out["dt_ignore"][b][:, :, :k] > 0, 2, 0).reshape(k, -1)
+        mt = np.moveaxis(out["dt_match"][b][:, :, :k] > 0, 2, 0).reshape(k, 4 * T)
+        ig = np.moveaxis(out["dt_ignore"][b][:, :, :k] > 0, 2, 0).reshape(k, 4 * T)
         r["matched"] = (mt * bits).sum(1).astype(np.uint64)
         r["ignored"] = (ig * bits).sum(1).astype(np.uint64)
         u = out["dets"][b, :k, 4].astype(np.float32).view(np.uint32)
