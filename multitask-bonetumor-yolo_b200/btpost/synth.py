@@ -182,6 +182,7 @@ def _anchor_fields(cfg: SynthConfig, b: int, tab: np.ndarray, tensor_id: int):
         for c in range(nc):
             scores[c] = np.where(inside, s_obj if c == int(cls) else s_oth[c], scores[c])
         assigned |= inside
+    _anchor_fields.last_assigned = assigned   # (used by the peaked L1 variant; plain attribute to keep the 4-tuple API)
     return key, n_idx, (cx, cy, w, h), scores
 
 
@@ -209,23 +210,40 @@ def make_protos(cfg: SynthConfig) -> np.ndarray:
     return out
 
 
-def make_maps_l1(cfg: SynthConfig, tab: np.ndarray | None = None):
+def make_maps_l1(cfg: SynthConfig, tab: np.ndarray | None = None, peaked: bool = False):
     """Raw per-level maps: box-bin logits 2*gauss over 4*reg_max channels, class logits chosen so
     that sigmoid(logit) follows the same recipe as the L2 scores (logit = log(s/(1-s)) in fp64,
-    rounded once to fp32; host-only, the CUDA generator does not produce L1)."""
+    rounded once to fp32; host-only, the CUDA generator does not produce L1).
+
+    ``peaked=True``: anchors that belong to an object get near-one-hot DFL logits (+12 on the bin nearest to the
+    distance between the anchor and the edge of their jittered object box, -12 elsewhere), so the DECODED boxes sit
+    on the objects: clusters for the NMS and many anchor<->GT confusion-matrix pairs, which random DFL logits
+    almost never produce."""
     tab = object_table(cfg) if tab is None else tab
     nc, R = cfg.nc, cfg.reg_max
     maps, off = [], 0
-    per_image = []
+    per_image, per_box, per_asg = [], [], []
     for b in range(cfg.batch):
-        _, _, _, scores = _anchor_fields(cfg, b, tab, TID_HEAD)
-        per_image.append(scores)
+        _, _, box, scores = _anchor_fields(cfg, b, tab, TID_HEAD)
+        per_image.append(scores); per_box.append(box); per_asg.append(_anchor_fields.last_assigned.copy())
+    ax, ay, _ = anchor_grid(cfg)
     for (h, w, s) in cfg.levels:
         m = np.empty((cfg.batch, 4 * R + nc, h, w), np.float32)
         idx = np.arange(4 * R * h * w, dtype=np.uint64)
         for b in range(cfg.batch):
             key = stream_key(cfg.seed, TID_L1 + int(s), cfg.image_offset + b)
             m[b, :4 * R] = (np.float32(2.0) * gauss16(hash_elems(key, idx))).reshape(4 * R, h, w)
+            if peaked:
+                cx, cy, bw, bh = (v[off:off + h * w] for v in per_box[b])
+                asg = per_asg[b][off:off + h * w]
+                axl, ayl = ax[off:off + h * w], ay[off:off + h * w]
+                dist = np.stack([axl - (cx - bw * np.float32(0.5)), ayl - (cy - bh * np.float32(0.5)),
+                                 (cx + bw * np.float32(0.5)) - axl, (cy + bh * np.float32(0.5)) - ayl]) / np.float32(s)
+                k = np.clip(np.rint(dist), 0, R - 1).astype(np.int64)                      # [4, hw]
+                dfl = m[b, :4 * R].reshape(4, R, h * w)
+                onehot = np.full((4, R, h * w), np.float32(-12.0))
+                np.put_along_axis(onehot, k[:, None, :], np.float32(12.0), axis=1)
+                dfl[:, :, asg] = onehot[:, :, asg]
             sc = per_image[b][:, off:off + h * w].astype(np.float64)
             m[b, 4 * R:] = np.log(sc / (1.0 - sc)).astype(np.float32).reshape(nc, h, w)
         maps.append(m)
@@ -233,13 +251,13 @@ def make_maps_l1(cfg: SynthConfig, tab: np.ndarray | None = None):
     return maps
 
 
-def make_batch(cfg: SynthConfig, l1: bool = False) -> dict:
+def make_batch(cfg: SynthConfig, l1: bool = False, l1_peaked: bool = False) -> dict:
     tab = object_table(cfg)
     gt, masks = gt_from_objects(cfg, tab)
     out = {"objects": tab, "head": make_head_l2(cfg, tab), "protos": make_protos(cfg),
            "det_boxes_gt": gt, "masks_gt": masks}
     if l1:
-        out["maps"] = make_maps_l1(cfg, tab)
+        out["maps"] = make_maps_l1(cfg, tab, peaked=l1_peaked)
         out["coeffs"] = np.ascontiguousarray(out["head"][:, 4 + cfg.nc:, :])   # Segment `mc` [B, nm, N]
     key = stream_key(cfg.seed, 99, 0)
     h = hash_elems(key, np.arange(cfg.nm + 1))

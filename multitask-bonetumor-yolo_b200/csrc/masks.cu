@@ -204,7 +204,7 @@ __host__ __device__ __forceinline__ u64 block_valid_slow(int by, int bx, int PH,
     return vAA | (vAB << 16) | (vBA << 32) | (vBB << 48);
 }
 __device__ __forceinline__ u64 block_valid(const K3Params &P, int by, int bx) {
-    if (by > 0 && bx > 0 && by < P.NBY - 1 && bx < P.NBX - 1) return ~0ull;   // interior: the common case, no table access
+    if ((unsigned)(by - 1) < (unsigned)(P.NBY - 2) && (unsigned)(bx - 1) < (unsigned)(P.NBX - 2)) return ~0ull;   // interior: the common case
     const int rc = by == 0 ? 0 : (by == P.NBY - 1 ? 2 : 1), cc = bx == 0 ? 0 : (bx == P.NBX - 1 ? 2 : 1);
     return P.valid_tab[rc * 3 + cc];
 }

@@ -28,12 +28,17 @@ CASES = [
     ("ref_v2_s160", "v2", 3, 160, 4243, None, None, None),     # v2 defaults: TOP_K 300
     ("ref_v3_s160_loose", "v3", 2, 160, 4244, 0.01, 0.45, 20),
     ("ref_v3_s640", "v3", 1, 640, 4245, None, None, None),
+    # peaked DFL logits: decoded boxes sit on the objects -> NMS clusters and many anchor<->GT confusion-matrix pairs
+    ("ref_v3_s160_peaked", "v3", 6, 160, 4246, None, None, None),
+    ("ref_v2_s160_peaked", "v2", 6, 160, 4247, None, None, None),
+    ("ref_v3_s640_peaked", "v3", 2, 640, 4248, None, None, None),
 ]
 
 
 def run_case(name, version, B, S, seed, conf, iou, top_k):
     cfg = synth.SynthConfig(batch=B, img_size=S, seed=seed)
-    batch = synth.make_batch(cfg, l1=True)
+    peaked = name.endswith("_peaked")
+    batch = synth.make_batch(cfg, l1=True, l1_peaked=peaked)
     t = torch.from_numpy
     maps = [t(m) for m in batch["maps"]]
     res = ref_shim.run_validation_step(
@@ -42,7 +47,7 @@ def run_case(name, version, B, S, seed, conf, iou, top_k):
         conf_th=conf, nms_iou=iou, top_k=top_k)
     mod = res["module"]
     preds, targets = res["map_update"]
-    out = {"version": version, "batch": B, "img_size": S, "seed": seed,
+    out = {"version": version, "batch": B, "img_size": S, "seed": seed, "l1_peaked": int(peaked),
            "conf_th": conf if conf is not None else mod.CONF_TH, "nms_iou": iou if iou is not None else mod.NMS_IOU,
            "top_k": top_k if top_k is not None else mod.TOP_K, "n_images": len(preds)}
     for i, (p, g) in enumerate(zip(preds, targets)):

@@ -10,13 +10,14 @@ from btpost import synth
 from oracle import oracle
 
 GOLD = Path(__file__).resolve().parent / "golden"
-CASES = ["ref_v3_s160", "ref_v2_s160", "ref_v3_s160_loose", "ref_v3_s640"]
+CASES = ["ref_v3_s160", "ref_v2_s160", "ref_v3_s160_loose", "ref_v3_s640", "ref_v3_s160_peaked", "ref_v2_s160_peaked",
+         "ref_v3_s640_peaked"]
 
 
 def load(name):
     f = np.load(GOLD / f"{name}.npz")
     cfg = synth.SynthConfig(batch=int(f["batch"]), img_size=int(f["img_size"]), seed=int(f["seed"]))
-    batch = synth.make_batch(cfg, l1=True)
+    batch = synth.make_batch(cfg, l1=True, l1_peaked=bool(int(f["l1_peaked"])) if "l1_peaked" in f else False)
     kw = dict(layout="l1", img_size=cfg.img_size, conf_thres=float(f["conf_th"]), iou_thres=float(f["nms_iou"]),
               max_det=int(f["top_k"]), gt_mode=0, with_instances=False)
     return f, cfg, batch, kw
