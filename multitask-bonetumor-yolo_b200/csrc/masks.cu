@@ -273,109 +273,114 @@ __device__ __forceinline__ u64 block_bits(const float (&v)[3][3], bool by0, bool
 }
 
 // =================================================================================================
-// GT mask -> cell-block bits.  One CTA per (image, block row): the row's <= 8 output rows are packed to
-// row bits with coalesced 32-byte reads, then one thread per block assembles its word.  Also clears
-// the union words of the row, the per-image accumulators and the completion counter.
+// GT mask -> cell-block bits.  One CTA per (image, G_ROWS rows of blocks): the <= 8 * G_ROWS + 2 output rows it needs
+// are one contiguous byte range; 32 pixels per job become one word of row bits (coalesced 32-byte reads, dot-product
+// packing), then one thread per FOUR neighbouring blocks assembles their words with byte permutes.  Also clears the
+// union words of the rows, the per-image accumulators and the work-queue counters.
 // =================================================================================================
-__device__ __forceinline__ uint32_t pack_u8(const uint4 &v, int half) {
-    uint32_t wv[4] = {v.x, v.y, v.z, v.w}, bits = 0;
+// 8 bytes -> 128 * (bit j = byte j != 0).  The carry trick leaves 0x80 in every non-zero byte; the 4-way byte dot
+// product with the weights 1, 2, 4, ... then gathers the eight flags (no partial product overlaps another).
+__device__ __forceinline__ uint32_t nz8_x128(uint32_t x0, uint32_t x1) {
+    const uint32_t y0 = (((x0 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x0) & 0x80808080u;
+    const uint32_t y1 = (((x1 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x1) & 0x80808080u;
+    return __dp4a(y1, 0x80402010u, __dp4a(y0, 0x08040201u, 0u));
+}
+__device__ __forceinline__ uint32_t pack_u8x32(const uint4 &lo, const uint4 &hi) {
+    const uint32_t g0 = nz8_x128(lo.x, lo.y), g1 = nz8_x128(lo.z, lo.w), g2 = nz8_x128(hi.x, hi.y), g3 = nz8_x128(hi.z, hi.w);
+    return (g0 >> 7) | (g1 << 1) | (g2 << 9) | (g3 << 17);   // every g is a multiple of 128 below 2^15
+}
+__device__ __forceinline__ uint32_t pack_f32x32(const float4 *gp) {
+    uint32_t bits = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        // byte != 0 -> bit.  High bit of every non-zero byte (the classic "haszero" carry trick), then the four high bits
-        // are gathered into one nibble by a multiplication whose partial products land on distinct bit positions.
-        const uint32_t x = wv[j];
-        const uint32_t y = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
-        bits |= (((y >> 7) * 0x01020408u) >> 24) << (16 * half + 4 * j);   // the product's top byte holds only the nibble
+    for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(gp + i);
+        bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
+                ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
     }
     return bits;
 }
+// Low nibbles of the four bytes of r -> 16 contiguous bits (byte k -> bits 4k .. 4k+3).
+__device__ __forceinline__ uint32_t squeeze_nibbles(uint32_t r) {
+    r = (r | (r >> 4)) & 0x00ff00ffu;
+    return (r | (r >> 8)) & 0xffffu;
+}
 
 __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constant__ K3Params P) {
-    // one CTA packs G_ROWS rows of blocks of one image: their 8 * G_ROWS (+2 above) output rows -> row bits -> words
-    extern __shared__ uint32_t s_rows[];   // [8 * G_ROWS + 2][wpr + 1]
+    // row bits of the CTA's output rows, flat: word q = pixels 32 (q % wpr) .. + 31 of row y_lo + q / wpr
+    extern __shared__ uint32_t s_rows[];   // [(8 * G_ROWS + 2) * wpr]
     __shared__ int s_cnt[G_ROWS];
     const int by_lo = blockIdx.x * G_ROWS, b = blockIdx.y, tid = threadIdx.x;
     const int nby = min(G_ROWS, P.NBY - by_lo);
-    const int S_h = P.S_h, S_w = P.S_w, wpr = S_w >> 5, tp = wpr + 1;
+    const int S_h = P.S_h, S_w = P.S_w, wpr = S_w >> 5;
     const int y_lo = by_lo ? 8 * by_lo - 2 : 0, y_hi = min(8 * (by_lo + nby) - 2, S_h);   // output rows of these block rows
-    const int nyr = y_hi - y_lo;
+    const int nw = (y_hi - y_lo) * wpr;
     if (blockIdx.x == 0) {
         if (tid < 8) P.acc[b * 8 + tid] = 0;
         if (b == 0 && tid >= 32 && tid < 32 + C_NQ) P.work[(tid - 32) * C_QSTRIDE] = 0;
     }
     if (tid < G_ROWS) s_cnt[tid] = 0;
-    // ---- bytes -> row bits: 32 pixels per job, (row, word) advanced without divisions
-    {
-        int yr = tid / wpr, w = tid - yr * wpr;
-        const int dyr = G_THREADS / wpr, dw = G_THREADS - dyr * wpr;
-        for (; yr < nyr; yr += dyr, w += dw) {
-            if (w >= wpr) { w -= wpr; ++yr; if (yr >= nyr) break; }
-            uint32_t bits = 0;
-            if (!P.gt_f32) {
-                const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) +
-                                                                  ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
-                bits = pack_u8(__ldg(gp), 0) | pack_u8(__ldg(gp + 1), 1);
-            } else {
-                const float4 *gp = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) +
-                                                                    ((size_t)b * S_h + (y_lo + yr)) * S_w + (size_t)w * 32);
+    // ---- bytes -> row bits: the rows are contiguous in memory, job q = the q-th run of 32 pixels
+    if (!P.gt_f32) {
+        const uint4 *gp = reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(P.masks_gt) + ((size_t)b * S_h + y_lo) * S_w);
+        constexpr int U = 3;   // jobs in flight per thread
+        for (int q0 = tid; q0 < nw; q0 += U * G_THREADS) {
+            uint4 v[U][2];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 v = __ldg(gp + i);
-                    bits |= ((int)v.x != 0 ? 1u : 0u) << (4 * i) | ((int)v.y != 0 ? 1u : 0u) << (4 * i + 1) |
-                            ((int)v.z != 0 ? 1u : 0u) << (4 * i + 2) | ((int)v.w != 0 ? 1u : 0u) << (4 * i + 3);
-                }
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * G_THREADS;
+                if (q < nw) { v[u][0] = __ldg(gp + 2 * q); v[u][1] = __ldg(gp + 2 * q + 1); }
             }
-            s_rows[yr * tp + w] = bits;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * G_THREADS;
+                if (q < nw) s_rows[q] = pack_u8x32(v[u][0], v[u][1]);
+            }
         }
-        for (int q = tid; q < nyr; q += G_THREADS) s_rows[q * tp + wpr] = 0;   // pad word: the funnel shifts read one past
+    } else {
+        const float4 *gp = reinterpret_cast<const float4 *>(static_cast<const float *>(P.masks_gt) + ((size_t)b * S_h + y_lo) * S_w);
+        for (int q = tid; q < nw; q += G_THREADS) s_rows[q] = pack_f32x32(gp + 8 * q);
     }
     __syncthreads();
-    // ---- row bits -> block words.  Interior blocks first (uniform: one funnel shift per row), then the border ones.
-    const int NBX = P.NBX;
-    for (int q = tid; q < nby * NBX; q += G_THREADS) {
-        // blocks of a row in the order 1 .. NBX-2, 0, NBX-1: the two border columns share the last lanes
-        const int a_row = q / NBX, qq = q - a_row * NBX;
-        const int bx = (qq < NBX - 2) ? qq + 1 : (qq == NBX - 2 ? 0 : NBX - 1);
-        const int by = by_lo + a_row;
-        u64 word = 0;
-        if (by > 0 && bx > 0 && 2 * by < P.PH - 1 && 2 * bx < P.PW - 1) {
-            // interior block: 8 output rows x 8 pixels starting at (8by-2, 8bx-2)
-            const int xb = 8 * bx - 2;
-            const uint32_t *row = s_rows + (8 * by - 2 - y_lo) * tp + (xb >> 5);
-            uint32_t lo = 0, hi = 0;
+    // ---- row bits -> block words.  Block (by, bx) is the 8 x 8 pixels at (8by - 2, 8bx - 2) of the zero-padded image:
+    // shifted left by two pixels, a row of bits holds one BYTE per block, so a thread takes the 32-bit word of four
+    // neighbouring blocks from each of the eight rows and transposes bytes into words with permutes.
+    const int NBX = P.NBX, tpr = (NBX + 3) >> 2;   // threads per row of blocks
+    for (int t = tid; t < nby * tpr; t += G_THREADS) {
+        const int a_row = t / tpr, w = t - a_row * tpr, by = by_lo + a_row;
+        uint32_t rw[8];
 #pragma unroll
-            for (int rr = 0; rr < 8; ++rr) {
-                const unsigned g8 = __funnelshift_r(row[rr * tp], row[rr * tp + 1], xb & 31) & 0xffu;
-                // pixels 0-3 -> cell column A, 4-7 -> cell column B; rows 0-3 -> cell row A, 4-7 -> cell row B
-                const unsigned two = (g8 & 0xfu) | ((g8 & 0xf0u) << 12);
-                if (rr < 4) lo |= two << (4 * rr); else hi |= two << (4 * (rr - 4));
+        for (int rr = 0; rr < 8; ++rr) {
+            const int y = 8 * by - 2 + rr;
+            uint32_t prev = 0, cur = 0;
+            if (y >= 0 && y < S_h) {
+                const uint32_t *row = s_rows + (y - y_lo) * wpr;
+                if (w > 0) prev = row[w - 1];
+                if (w < wpr) cur = row[w];
             }
-            word = ((u64)hi << 32) | lo;
-        } else {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int ci = 2 * by - 1 + a;
-                if (ci > P.PH - 1) continue;
-                const int ybase = (ci < 0) ? 0 : 4 * ci + 2, nry = (ci < 0) ? 2 : min(4, S_h - ybase);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int cj = 2 * bx - 1 + c;
-                    if (cj > P.PW - 1) continue;
-                    const int xbase = (cj < 0) ? 0 : 4 * cj + 2, nrx = (cj < 0) ? 2 : min(4, S_w - xbase);
-                    unsigned bits = 0;
-                    for (int ry = 0; ry < nry; ++ry) {
-                        const uint32_t *row = s_rows + (ybase + ry - y_lo) * tp + (xbase >> 5);
-                        const unsigned gb = __funnelshift_r(row[0], row[1], xbase & 31) & ((1u << nrx) - 1u);
-                        bits |= gb << (4 * ry);
-                    }
-                    word |= (u64)bits << (16 * (2 * a + c));
-                }
-            }
+            rw[rr] = __funnelshift_r(prev, cur, 30);   // pixels 32w - 2 .. 32w + 29
         }
-        const size_t o = ((size_t)b * P.NBY + by) * NBX + bx;
-        P.gtc[o] = word;
-        P.unc[o] = 0ull;
-        const int cnt = __popcll(word);
+        const size_t o = ((size_t)b * P.NBY + by) * NBX + 4 * w;
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (4 * w + j >= NBX) break;
+            // byte j of rows 0-3 / 4-7: pixels 0-3 of a row -> cell column A, 4-7 -> B; rows 0-3 -> cell row A, 4-7 -> B
+            const uint32_t sel = (uint32_t)j | ((uint32_t)(4 + j) << 4);
+            const uint32_t r03 = __byte_perm(__byte_perm(rw[0], rw[1], sel), __byte_perm(rw[2], rw[3], sel), 0x5410u);
+            const uint32_t r47 = __byte_perm(__byte_perm(rw[4], rw[5], sel), __byte_perm(rw[6], rw[7], sel), 0x5410u);
+            uint32_t lo = squeeze_nibbles(r03 & 0x0f0f0f0fu) | (squeeze_nibbles((r03 >> 4) & 0x0f0f0f0fu) << 16);
+            uint32_t hi = squeeze_nibbles(r47 & 0x0f0f0f0fu) | (squeeze_nibbles((r47 >> 4) & 0x0f0f0f0fu) << 16);
+            if (j == 0 && w == 0) {
+                // block column 0: the border cell -1 owns the pixels x = 0, 1 as its columns 0, 1 (they sit at 2, 3 here)
+                lo = (lo & 0xffff0000u) | ((lo >> 2) & 0x3333u);
+                hi = (hi & 0xffff0000u) | ((hi >> 2) & 0x3333u);
+            }
+            if (by == 0) lo = (lo >> 8) & 0x00ff00ffu;   // block row 0: the border cell row owns y = 0, 1 as its rows 0, 1
+            const u64 word = ((u64)hi << 32) | lo;
+            P.gtc[o + j] = word;
+            P.unc[o + j] = 0ull;
+            cnt += __popc(lo) + __popc(hi);
+        }
         if (cnt) atomicAdd(&s_cnt[a_row], cnt);
     }
     __syncthreads();
@@ -842,7 +847,8 @@ __device__ __forceinline__ int atom_inc(int *p) {
 // serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).  A warp serves its home queue
 // until it is drained and then leaves: every queue holds the same mix of items and has the same number of warps, so
 // they drain together (stealing from the other queues cost a scan of 31 counters per warp at the end).
-__global__ void __launch_bounds__(C_WARPS * 32, 7) cells_kernel(const __grid_constant__ K3Params P) {
+template <int MINB>
+__global__ void __launch_bounds__(C_WARPS * 32, MINB) cells_kernel(const __grid_constant__ K3Params P) {
     const int lane = threadIdx.x & 31;
     const int ndet = min(__ldg(P.n_items), P.item_cap), total = ndet + P.B * P.m1_items;
     const int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (P.nq - 1);
@@ -974,7 +980,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     if (make_proto_tmap(&tm, io.protos, P.proto_bf16, p.batch, p.proto_h, p.proto_w) != BT_OK) return BT_ERR_CUDA;
 
     if (parts & BT_MASKS_PACK) {
-        const size_t smem_g = (size_t)(8 * G_ROWS + 2) * (p.img_w / 32 + 1) * sizeof(uint32_t);
+        const size_t smem_g = (size_t)(8 * G_ROWS + 2) * (p.img_w / 32) * sizeof(uint32_t);
         gt_pack_kernel<<<dim3((P.NBY + G_ROWS - 1) / G_ROWS, p.batch), G_THREADS, smem_g, s>>>(P);
     }
 
@@ -990,6 +996,9 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             cudaFuncSetAttribute(contract_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(contract_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
+#ifdef BT_DEBUG_HOOKS
+        if (cudaFuncSetAttribute(contract_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return BT_ERR_CUDA;
+#endif
         attr_done[attr_dev] = true;
     }
     {
@@ -1003,6 +1012,9 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
         const int grid_a = ntiles < cta_a ? ntiles : cta_a;
         if (parts & BT_MASKS_CONTRACT) {
             if (P.proto_bf16) contract_kernel<1, 4, true><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+#ifdef BT_DEBUG_HOOKS
+            else if (nbuf == 2 && dbg_env_int("BTPOST_A_MINB", 3) == 4) contract_kernel<2, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
+#endif
             else if (nbuf == 2) contract_kernel<2, 3><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
             else if (nbuf == 3) contract_kernel<3, 2><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
             else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
@@ -1015,7 +1027,11 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             while (P.nq * 2 <= C_NQ && P.nq * 2 <= ctas * C_WARPS) P.nq *= 2;
             const size_t inst_words = (size_t)p.batch * p.max_det * p.img_h * (p.img_w / 32);
             if (io.inst_bits && cudaMemsetAsync(io.inst_bits, 0, inst_words * 4, s) != cudaSuccess) return BT_ERR_CUDA;
-            cells_kernel<<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+#ifdef BT_DEBUG_HOOKS
+            if (dbg_env_int("BTPOST_C_MINB", 7) == 8) cells_kernel<8><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            else
+#endif
+            cells_kernel<7><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
             if (io.inst_bits && io.inst_masks) {
                 const size_t want_d = (inst_words + C_THREADS - 1) / C_THREADS, cap_d = (size_t)sm_count * 16;
                 inst_dense_kernel<<<(unsigned)(want_d < cap_d ? want_d : cap_d), C_THREADS, 0, s>>>(P.inst_bits, io.inst_masks, inst_words);

@@ -294,7 +294,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     const unsigned long long *gkeys = nullptr;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        if (K2_THREADS == 512 && M_all <= 512) sort_to_smem<1>(cscore, M_all, 512, s_x, s_sidx);
+        if (K2_THREADS == 256 && M_all <= 256) sort_to_smem<1>(cscore, M_all, 256, s_x, s_sidx);
+        else if (K2_THREADS == 256 && M_all <= 512) sort_to_smem<2>(cscore, M_all, 256, s_x, s_sidx);
+        else if (K2_THREADS == 256 && M_all <= 1024) sort_to_smem<4>(cscore, M_all, 256, s_x, s_sidx);
+        else if (K2_THREADS == 256 && M_all <= 2048) sort_to_smem<8>(cscore, M_all, 256, s_x, s_sidx);
+        else if (K2_THREADS == 256 && M_all <= SORT_SMALL_MAX) sort_to_smem<16>(cscore, M_all, 256, s_x, s_sidx);
+        else if (K2_THREADS == 512 && M_all <= 512) sort_to_smem<1>(cscore, M_all, 512, s_x, s_sidx);
         else if (K2_THREADS == 512 && M_all <= 1024) sort_to_smem<2>(cscore, M_all, 512, s_x, s_sidx);
         else if (K2_THREADS == 512 && M_all <= 2048) sort_to_smem<4>(cscore, M_all, 512, s_x, s_sidx);
         else if (K2_THREADS == 512 && M_all <= SORT_SMALL_MAX) sort_to_smem<8>(cscore, M_all, 512, s_x, s_sidx);
@@ -938,8 +943,8 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     // with six batches in flight, but a single step is 11 us slower).  The 1024-thread variant (default) also sorts
     // long candidate lists in registers; the small one falls back to the global-memory network above 4096 candidates.
     const int nt_req = p.nms_threads ? p.nms_threads : dbg_env_int("BTPOST_NMS_NT", 1024);
-    const int nt = nt_req == 512 ? 512 : 1024;
-    const int sort_max = nt == 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
+    const int nt = nt_req == 512 ? 512 : (nt_req == 256 ? 256 : 1024);
+    const int sort_max = nt <= 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
     const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > sort_max ? sort_max : P.cap_pow2);
     const size_t region0 = align_up((size_t)sort_slots * 4, 16);
     P.region0_bytes = (int)region0;
@@ -958,6 +963,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     if (!attr_done[attr_dev]) {
         if (cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(nms_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(nms_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
         attr_done[attr_dev] = true;
@@ -973,12 +979,14 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
             prio = hi;   // hi = numerically lowest = highest priority
         }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(p.batch); cfg.blockDim = dim3(nt == 512 ? 512 : 1024); cfg.dynamicSmemBytes = smem_a; cfg.stream = s;
+        cfg.gridDim = dim3(p.batch); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem_a; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributePriority;
         at[0].val.priority = prio;
         cfg.attrs = at; cfg.numAttrs = prio != 0 ? 1 : 0;
-        if ((nt == 512 ? cudaLaunchKernelEx(&cfg, nms_kernel<512>, P) : cudaLaunchKernelEx(&cfg, nms_kernel<1024>, P)) != cudaSuccess)
+        if ((nt == 256   ? cudaLaunchKernelEx(&cfg, nms_kernel<256>, P)
+             : nt == 512 ? cudaLaunchKernelEx(&cfg, nms_kernel<512>, P)
+                         : cudaLaunchKernelEx(&cfg, nms_kernel<1024>, P)) != cudaSuccess)
             return BT_ERR_CUDA;
     }
     if (parts & BT_NMS_GATHER) coeff_gather_kernel<<<dim3((p.max_det + 7) / 8, p.batch), GM_THREADS, 0, s>>>(P);

@@ -12,7 +12,7 @@ cfg = synth.SynthConfig(batch=B, img_size=S, seed=20262)
 b = synth.make_batch(cfg)
 dev = torch.device("cuda:0")
 d = {k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("head", "protos", "det_boxes_gt", "masks_gt", "proj_weight")}
-pp = PostProcessor(PostConfig(batch=B, img_size=S), dev)
+pp = PostProcessor(PostConfig(batch=B, img_size=S, nms_threads=int(sys.argv[4]) if len(sys.argv) > 4 else 0), dev)
 for _ in range(n):
     pp.run(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], d["proj_weight"], float(b["proj_bias"]))
 torch.cuda.synchronize()

@@ -64,7 +64,7 @@ def test_argument_validation_without_gpu():
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(260), n.value, None) == -4   # misaligned workspace
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), 16, None) == -3        # workspace too small
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1   # null head
-    for field, bad in (("nms_threads", 256), ("proto_dtype", 2), ("head_dtype", 7)):          # scheduling / dtype knobs
+    for field, bad in (("nms_threads", 384), ("proto_dtype", 2), ("head_dtype", 7)):          # scheduling / dtype knobs
         setattr(p, field, bad)
         assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1, field
         setattr(p, field, 0)

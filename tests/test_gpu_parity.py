@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
     dict(max_cand=500),
     dict(crop=0, max_det=100),                      # every detection on every strip: several rounds / scratch batches
     dict(max_det=400),                              # more detections than fit one round of the contract kernel's tables
-    dict(nms_threads=1024), dict(nms_threads=512, class_mode=1),   # both NMS kernel variants whatever the heuristic picks
+    dict(nms_threads=1024), dict(nms_threads=512, class_mode=1), dict(nms_threads=256), dict(nms_threads=256, iou_thres=0.5),   # every NMS kernel variant whatever the heuristic picks
 ])
 def test_pipeline_matches_oracle_640(kw):
     batch = helpers.make(batch=2, img_size=640)
@@ -30,7 +30,7 @@ def test_pipeline_matches_oracle_640(kw):
     helpers.assert_same(got, ref, 2, kw.get("max_det", 300))
 
 
-@pytest.mark.parametrize("nms_threads", [0, 512, 1024])
+@pytest.mark.parametrize("nms_threads", [0, 256, 512, 1024])
 def test_pipeline_dense_candidates(nms_threads):
     """conf 0.001: every anchor is a candidate (8400 per image) -> the 16-keys-per-thread register sort of the
     1024-thread NMS kernel (auto / 1024) and the global-memory sort of the 512-thread one."""
