@@ -49,6 +49,8 @@ typedef unsigned long long u64;
 
 struct K3Params {
     int B, S_h, S_w, PH, PW, K, gt_f32, proto_bf16, NBY, NBX, ntx, nty, m1_items, nq;
+    int pref;               // contract_kernel: tiles prefetched into the L2 ahead of the tile being loaded
+    int interleave;         // contract_kernel: tiles dealt round-robin to the CTAs instead of in contiguous ranges
     float bias, inv_K, inv_m1;
     const int2 *items;      // plan of the cells kernel: (image * K + detection, chunk)
     const int32_t *n_items;
@@ -96,6 +98,13 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *tm, i
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(chan0), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
+}
+// The same box, DRAM -> L2 only: issued a tile (or two) ahead of the load, it costs no shared memory or registers and
+// turns the load's DRAM latency into an L2 hit.
+__device__ __forceinline__ void tma_tile_prefetch_l2(const CUtensorMap *tm, int col, int row, int chan0) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(col),
+                 "r"(row), "r"(chan0)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(G_THREADS) gt_pack_kernel(const __grid_constan
     const int nw = (y_hi - y_lo) * wpr;
     if (blockIdx.x == 0) {
         if (tid < 8) P.acc[b * 8 + tid] = 0;
-        if (b == 0 && tid >= 32 && tid < 32 + C_NQ) P.work[(tid - 32) * C_QSTRIDE] = 0;
+        if (b == 0 && tid >= 32 && tid < 32 + 2 * C_NQ) P.work[((tid - 32) >> 1) * C_QSTRIDE + ((tid - 32) & 1)] = 0;   // detection / projector counters
     }
     if (tid < G_ROWS) s_cnt[tid] = 0;
     // ---- bytes -> row bits: the rows are contiguous in memory, job q = the q-th run of 32 pixels
@@ -410,7 +419,12 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     const int tiles = P.ntx * P.nty, total = tiles * P.B;
     const int PH = P.PH, PW = P.PW, K = P.K;
     // this CTA's contiguous range of tiles
-    const int t_begin = (int)(((long long)blockIdx.x * total) / gridDim.x), t_end = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+    // Tiles of a CTA.  Interleaved (P.interleave): CTA i takes tiles i, i + grid, i + 2 grid, ...: at any moment the CTAs of
+    // the grid read a window of neighbouring tiles, i.e. whole rows of every channel plane (DRAM pages are consumed while
+    // they are open).  Contiguous: a range of total / grid tiles per CTA.
+    const int ts = P.interleave ? (int)gridDim.x : 1;
+    const int t_begin = P.interleave ? (int)blockIdx.x : (int)(((long long)blockIdx.x * total) / gridDim.x);
+    const int t_end = P.interleave ? total : (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
     if (t_begin >= t_end) return;
 
     // The tile buffer is dead as soon as every thread holds its pixels in registers: the next tile's TMA is issued
@@ -425,19 +439,29 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         a.ty = t / P.ntx; a.tx = t - a.ty * P.ntx;
         return a;
     };
+    // one step of `ts` tiles, decomposed once into (images, tile rows, tiles)
+    const int ts_b = ts / tiles, ts_y = (ts - ts_b * tiles) / P.ntx, ts_x = ts - ts_b * tiles - ts_y * P.ntx;
     auto step = [&](TileAt &a) {
-        if (++a.tx == P.ntx) { a.tx = 0; if (++a.ty == P.nty) { a.ty = 0; ++a.b; } }
+        a.tx += ts_x;
+        if (a.tx >= P.ntx) { a.tx -= P.ntx; ++a.ty; }
+        a.ty += ts_y;
+        if (a.ty >= P.nty) { a.ty -= P.nty; ++a.b; }
+        a.b += ts_b;
     };
     auto issue = [&](const TileAt &a, int buf) {   // thread 0
         mbar_expect_tx(&s_bar[buf], (uint32_t)(TILE_FLOATS * sizeof(float)));
         tma_tile_g2s(s_tiles + buf * TILE_FLOATS, &tmap, a.tx * TA_W, a.ty * TA_H, a.b * NM, &s_bar[buf], keep_protos);
     };
-    TileAt at = tile_at(t_begin), at_issue = at;   // current tile; next tile to load (thread 0)
+    TileAt at = tile_at(t_begin), at_issue = at, at_pref = at;   // current tile; next tile to load / to prefetch (thread 0)
+    const int pref = P.pref;
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) mbar_init(&s_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < NBUF; ++i)
-            if (t_begin + i < t_end) { issue(at_issue, i); step(at_issue); }
+            if (t_begin + i * ts < t_end) { issue(at_issue, i); step(at_issue); }
+        at_pref = at_issue;
+        for (int i = 0; i < pref; ++i)
+            if (t_begin + (NBUF + i) * ts < t_end) { tma_tile_prefetch_l2(&tmap, at_pref.tx * TA_W, at_pref.ty * TA_H, at_pref.b * NM); step(at_pref); }
     }
     if (tid < NM) s_w[tid] = __ldg(P.proj_weight + tid);
     __syncthreads();
@@ -466,7 +490,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     };
     Meta cur = fetch_meta(t_begin);
 
-    for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it, step(at)) {
+    for (int tile = t_begin, it = 0; tile < t_end; tile += ts, ++it, step(at)) {
         const int b = at.b;
         const int R0 = at.ty * TA_H, C0 = at.tx * TA_W;
         const int r = R0 + row, c = C0 + colp;
@@ -484,7 +508,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
             rg0 = __ldg(P.det_region + (size_t)b * K + cur.k0);
             off0 = __ldg(P.scr_off + (size_t)b * K + cur.k0);
         }
-        if (tile + 1 < t_end) cur = fetch_meta(tile + 1);
+        if (tile + ts < t_end) cur = fetch_meta(tile + ts);
 
         // ---- the tile: shared memory -> registers, then the buffer is free for the next tile
         const int buf = it % NBUF;
@@ -504,7 +528,10 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
             }
         }
         __syncthreads();
-        if (tid == 0 && tile + NBUF < t_end) { issue(at_issue, buf); step(at_issue); }
+        if (tid == 0 && tile + NBUF * ts < t_end) {
+            issue(at_issue, buf); step(at_issue);
+            if (pref > 0 && tile + (NBUF + pref) * ts < t_end) { tma_tile_prefetch_l2(&tmap, at_pref.tx * TA_W, at_pref.ty * TA_H, at_pref.b * NM); step(at_pref); }
+        }
 
         // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
         {
@@ -699,109 +726,125 @@ __device__ __forceinline__ void scatter_block_bits(const K3Params &P, int bk, in
     }
 }
 
-// One item of a detection: blocks [chunk * C_CHUNK, (chunk + 1) * C_CHUNK) of its crop box (the plan lists them).
-__device__ __forceinline__ void det_item(const K3Params &P, int bk, int chunk, int lane) {
-    const int PH = P.PH, PW = P.PW, K = P.K, NBX = P.NBX, NBY = P.NBY;
+// One item of a detection = blocks [chunk * C_CHUNK, (chunk + 1) * C_CHUNK) of its crop box (the plan lists them).
+// An item is worked on by a GROUP of GS lanes, GS blocks per pass: the crop boxes of the benchmark's detections hold
+// 28 blocks on average (median 24), so whole-warp passes ran at 65 % lane utilisation; groups of 8 lanes reach 94 %.
+// The groups of a warp hold different detections; everything per item lives in the lanes' own registers.
+struct DetWork {
+    int bk, b, i, i_end, off, nbx;
+    short4 rg;       // crop region at prototype resolution (r_lo, r_hi, c_lo, c_hi)
+    float inv;       // 1 / nbx
+};
+__device__ __forceinline__ void det_begin(const K3Params &P, int bk, int chunk, DetWork &w) {
+    const int K = P.K;
     int b = __float2int_rz(((float)bk + 0.5f) * P.inv_K), k = bk - b * K;
-    if (k < 0) { --b; k += K; } else if (k >= K) { ++b; k -= K; }
+    if (k < 0) --b; else if (k >= K) ++b;
     const short4 rg = __ldg(P.det_region + bk);
-    const int r_lo = rg.x, r_hi = rg.y, c_lo = rg.z, c_hi = rg.w, bw = c_hi - c_lo + 1;
-    const int by0 = r_lo >> 1, bx0 = c_lo >> 1, nbx = ((c_hi + 1) >> 1) - bx0 + 1, nby = ((r_hi + 1) >> 1) - by0 + 1;
-    const int nblk = nbx * nby, i_end = min(nblk, (chunk + 1) * C_CHUNK);
-    const int off = __ldg(P.scr_off + bk);
-    const float inv = 1.0f / (float)nbx;
-    int area = 0, inter = 0, uarea = 0, uinter = 0;   // uarea / uinter: pixels this detection ADDS to the image's union
-    for (int i0 = chunk * C_CHUNK; i0 < i_end; i0 += 32) {
-        const int i = i0 + lane;
-        const bool act = i < i_end;
-        int yy = __float2int_rz(((float)i + 0.5f) * inv);
-        int xx = i - yy * nbx;
-        if (xx < 0) { --yy; xx += nbx; } else if (xx >= nbx) { ++yy; xx -= nbx; }
-        const int by = act ? by0 + yy : by0, bx = act ? bx0 + xx : bx0;
-        const BlockGeo g = block_geo(by, bx, PH, PW);
-        const int rr[3] = {g.r0, g.r1, g.r2}, cc[3] = {g.c0, g.c1, g.c2};
-        bool rin[3], cin[3];
+    const int nbx = ((rg.w + 1) >> 1) - (rg.z >> 1) + 1, nby = ((rg.y + 1) >> 1) - (rg.x >> 1) + 1;
+    w.bk = bk; w.b = b; w.rg = rg; w.nbx = nbx;
+    w.i = chunk * C_CHUNK;
+    w.i_end = min(nbx * nby, (chunk + 1) * C_CHUNK);
+    w.off = __ldg(P.scr_off + bk);
+    w.inv = 1.0f / (float)nbx;
+}
+// one pass: block w.i + gl of the item (gl = lane within the group)
+__device__ __forceinline__ void det_pass(const K3Params &P, const DetWork &w, int gl, int &area, int &inter, int &uarea, int &uinter) {
+    const int PH = P.PH, PW = P.PW, NBX = P.NBX, NBY = P.NBY;
+    const int r_lo = w.rg.x, r_hi = w.rg.y, c_lo = w.rg.z, c_hi = w.rg.w, bw = c_hi - c_lo + 1;
+    const int by0 = r_lo >> 1, bx0 = c_lo >> 1, nbx = w.nbx, b = w.b;
+    const int i = w.i + gl;
+    const bool act = i < w.i_end;
+    int yy = __float2int_rz(((float)i + 0.5f) * w.inv);
+    int xx = i - yy * nbx;
+    if (xx < 0) { --yy; xx += nbx; } else if (xx >= nbx) { ++yy; xx -= nbx; }
+    const int by = act ? by0 + yy : by0, bx = act ? bx0 + xx : bx0;
+    const BlockGeo g = block_geo(by, bx, PH, PW);
+    const int rr[3] = {g.r0, g.r1, g.r2}, cc[3] = {g.c0, g.c1, g.c2};
+    bool rin[3], cin[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rin[a] = act && rr[a] >= r_lo && rr[a] <= r_hi;
+        cin[a] = cc[a] >= c_lo && cc[a] <= c_hi;
+    }
+    float v[3][3];
+    if (w.off >= 0) {
+        // the crop box's logits; corners outside the box are zero (clamped address, value discarded)
+        const float *scr = P.pool + w.off;
+        int ro[3], co[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            rin[a] = act && rr[a] >= r_lo && rr[a] <= r_hi;
-            cin[a] = cc[a] >= c_lo && cc[a] <= c_hi;
+            ro[a] = (min(max(rr[a], r_lo), r_hi) - r_lo) * bw;
+            co[a] = min(max(cc[a], c_lo), c_hi) - c_lo;
         }
-        float v[3][3];
-        if (off >= 0) {
-            // the crop box's logits; corners outside the box are zero (clamped address, value discarded)
-            const float *scr = P.pool + off;
-            int ro[3], co[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                ro[a] = (min(max(rr[a], r_lo), r_hi) - r_lo) * bw;
-                co[a] = min(max(cc[a], c_lo), c_hi) - c_lo;
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float x = __ldg(scr + ro[a] + co[c]);
+                v[a][c] = (rin[a] && cin[c]) ? x : 0.0f;
             }
+    } else {
+        // no room in the logit pool (huge crop boxes / crop off): contract the 9 corners here, same sequential order;
+        // the coefficients are broadcast loads (the lanes of a group read the same address)
+        const float *cf = P.det_coeff + (size_t)w.bk * NM;
+        const size_t pr0 = (size_t)b * NM * PH * PW;
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float x = __ldg(scr + ro[a] + co[c]);
-                    v[a][c] = (rin[a] && cin[c]) ? x : 0.0f;
-                }
+            for (int c = 0; c < 3; ++c) v[a][c] = 0.0f;
+        if (!P.proto_bf16) {
+            const float *pr = static_cast<const float *>(P.protos) + pr0;
+            for (int ch = 0; ch < NM; ++ch) {
+                const float wt = __ldg(cf + ch);
+                const float *pc = pr + (size_t)ch * PH * PW;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(wt, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
+            }
         } else {
-            // no room in the logit pool (huge crop boxes / crop off): contract the 9 corners here,
-            // same sequential order
-            const size_t pr0 = (size_t)b * NM * PH * PW;
-            const float mycf = __ldg(P.det_coeff + ((size_t)b * K + k) * NM + lane);
+            const unsigned short *pr = static_cast<const unsigned short *>(P.protos) + pr0;
+            for (int ch = 0; ch < NM; ++ch) {
+                const float wt = __ldg(cf + ch);
+                const unsigned short *pc = pr + (size_t)ch * PH * PW;
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[a][c] = 0.0f;
-            if (!P.proto_bf16) {
-                const float *pr = static_cast<const float *>(P.protos) + pr0;
-                for (int ch = 0; ch < NM; ++ch) {
-                    const float w = __shfl_sync(0xffffffffu, mycf, ch);
-                    const float *pc = pr + (size_t)ch * PH * PW;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(w, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
-                }
-            } else {
-                const unsigned short *pr = static_cast<const unsigned short *>(P.protos) + pr0;
-                for (int ch = 0; ch < NM; ++ch) {
-                    const float w = __shfl_sync(0xffffffffu, mycf, ch);
-                    const unsigned short *pc = pr + (size_t)ch * PH * PW;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            if (rin[a] && cin[c])
-                                v[a][c] = __fmaf_rn(w, __uint_as_float((uint32_t)__ldg(pc + rr[a] * PW + cc[c]) << 16), v[a][c]);
-                }
+                    for (int c = 0; c < 3; ++c)
+                        if (rin[a] && cin[c])
+                            v[a][c] = __fmaf_rn(wt, __uint_as_float((uint32_t)__ldg(pc + rr[a] * PW + cc[c]) << 16), v[a][c]);
             }
-        }
-        const size_t o = ((size_t)b * NBY + by) * NBX + bx;
-        const u64 gtw = __ldg(P.gtc + o);   // with the corner loads, not behind the arithmetic
-        if (!act) continue;
-        const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(P, by, bx);
-        if (bits && P.inst_bits) scatter_block_bits(P, bk, by, bx, bits);
-        if (bits) {
-            // the OR is serialised per word in the L2: the bits that were not set before are counted exactly once
-            // over all detections, so the union's counters need no pass over the union afterwards
-            const u64 fresh = bits & ~atomicOr(P.unc + o, bits);
-            area += __popcll(bits);
-            inter += __popcll(bits & gtw);
-            uarea += __popcll(fresh);
-            uinter += __popcll(fresh & gtw);
         }
     }
-    inter = __reduce_add_sync(0xffffffffu, inter);   // one REDUX instruction each
-    area = __reduce_add_sync(0xffffffffu, area);
-    uinter = __reduce_add_sync(0xffffffffu, uinter);
-    uarea = __reduce_add_sync(0xffffffffu, uarea);
-    if (lane == 0) {
+    const size_t o = ((size_t)b * NBY + by) * NBX + bx;
+    const u64 gtw = __ldg(P.gtc + o);   // with the corner loads, not behind the arithmetic
+    if (!act) return;
+    const u64 bits = block_bits(v, by == 0, bx == 0) & block_valid(P, by, bx);
+    if (bits && P.inst_bits) scatter_block_bits(P, w.bk, by, bx, bits);
+    if (bits) {
+        // the OR is serialised per word in the L2: the bits that were not set before are counted exactly once
+        // over all detections, so the union's counters need no pass over the union afterwards
+        const u64 fresh = bits & ~atomicOr(P.unc + o, bits);
+        area += __popcll(bits);
+        inter += __popcll(bits & gtw);
+        uarea += __popcll(fresh);
+        uinter += __popcll(fresh & gtw);
+    }
+}
+// item done: the group's sums (one REDUX each) -> the detection's / the image's counters
+__device__ __forceinline__ void det_end(const K3Params &P, const DetWork &w, unsigned gmask, int gl, int area, int inter, int uarea,
+                                        int uinter) {
+    inter = __reduce_add_sync(gmask, inter);
+    area = __reduce_add_sync(gmask, area);
+    uinter = __reduce_add_sync(gmask, uinter);
+    uarea = __reduce_add_sync(gmask, uarea);
+    if (gl == 0) {
         // zeroed by the NMS kernel; a detection of several chunks adds up
-        if (P.inst_area && area) atomicAdd(&P.inst_area[bk], area);
-        if (P.inst_inter && inter) atomicAdd(&P.inst_inter[bk], inter);
-        if (uinter) atomicAdd(&P.acc[b * 8 + 3], uinter);
-        if (uarea) atomicAdd(&P.acc[b * 8 + 4], uarea);
+        if (P.inst_area && area) atomicAdd(&P.inst_area[w.bk], area);
+        if (P.inst_inter && inter) atomicAdd(&P.inst_inter[w.bk], inter);
+        if (uinter) atomicAdd(&P.acc[w.b * 8 + 3], uinter);
+        if (uarea) atomicAdd(&P.acc[w.b * 8 + 4], uarea);
     }
 }
 
@@ -843,27 +886,58 @@ __device__ __forceinline__ int atom_inc(int *p) {
     return v;
 }
 
-// Work queues: item i lives in queue i % nq; one counter per queue, 128 bytes apart (atomics on one address
-// serialise in the L2: a single counter took 2 ns per item, the whole kernel's time).  A warp serves its home queue
-// until it is drained and then leaves: every queue holds the same mix of items and has the same number of warps, so
-// they drain together (stealing from the other queues cost a scan of 31 counters per warp at the end).
-template <int MINB>
+// Work queues: item i lives in queue i % nq; one counter per queue and kind of item (detections / projector runs), a
+// queue's counters in one 128-byte line of their own (atomics on one address serialise in the L2: a single counter took
+// 2 ns per item, the whole kernel's time).  A warp serves its home queue until it is drained and then leaves: every queue
+// holds the same mix of items and has the same number of warps, so they drain together (stealing from the other queues
+// cost a scan of 31 counters per warp at the end).  Detection items are taken by lane GROUPS (see DetWork), the projector
+// mask's runs of 32 blocks by whole warps once the queue's detections are out.
+template <int MINB, int GS>
 __global__ void __launch_bounds__(C_WARPS * 32, MINB) cells_kernel(const __grid_constant__ K3Params P) {
-    const int lane = threadIdx.x & 31;
-    const int ndet = min(__ldg(P.n_items), P.item_cap), total = ndet + P.B * P.m1_items;
+    const int lane = threadIdx.x & 31, gl = lane & (GS - 1), gbase = lane & ~(GS - 1);
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
+    const int ndet = min(__ldg(P.n_items), P.item_cap);
     const int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (P.nq - 1);
-    int *ctr = P.work + q * C_QSTRIDE;
-    int j = 0;
-    if (lane == 0) j = atom_inc(ctr);
-    for (;;) {
-        const int item = __shfl_sync(0xffffffffu, q + P.nq * j, 0);
-        if (item >= total) break;
-        if (lane == 0) j = atom_inc(ctr);   // next item of the queue: in flight while this one is processed
-        if (item < ndet) {
-            const int2 it = __ldg(P.items + item);
-            det_item(P, it.x, it.y, lane);
-        } else {
-            const int m = item - ndet;
+    {
+        int *ctr = P.work + q * C_QSTRIDE;
+        int j = 0;
+        if (gl == 0) j = atom_inc(ctr);
+        bool have = false, done = false;
+        DetWork w{};
+        int area = 0, inter = 0, uarea = 0, uinter = 0;   // uarea / uinter: pixels this detection ADDS to the image's union
+        for (;;) {
+            if (!have && !done) {
+                const int item = q + P.nq * __shfl_sync(gmask, j, gbase);
+                if (item < ndet) {
+                    if (gl == 0) j = atom_inc(ctr);   // next item of the queue: in flight while this one is processed
+                    const int2 it = __ldg(P.items + item);
+                    det_begin(P, it.x, it.y, w);
+                    have = true;
+                } else {
+                    done = true;
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (have) {
+                det_pass(P, w, gl, area, inter, uarea, uinter);
+                w.i += GS;
+                if (w.i >= w.i_end) {
+                    det_end(P, w, gmask, gl, area, inter, uarea, uinter);
+                    area = inter = uarea = uinter = 0;
+                    have = false;
+                }
+            }
+        }
+    }
+    {
+        const int total = P.B * P.m1_items;
+        int *ctr = P.work + q * C_QSTRIDE + 1;
+        int j = 0;
+        if (lane == 0) j = atom_inc(ctr);
+        for (;;) {
+            const int m = __shfl_sync(0xffffffffu, q + P.nq * j, 0);
+            if (m >= total) break;
+            if (lane == 0) j = atom_inc(ctr);
             int b = __float2int_rz(((float)m + 0.5f) * P.inv_m1);
             int c = m - b * P.m1_items;
             if (c < 0) { --b; c += P.m1_items; } else if (c >= P.m1_items) { ++b; c -= P.m1_items; }
@@ -970,6 +1044,8 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
     P.NBY = mask_blocks(p.proto_h); P.NBX = mask_blocks(p.proto_w);
     P.ntx = (p.proto_w + TA_W - 1) / TA_W; P.nty = (p.proto_h + TA_H - 1) / TA_H;
     P.m1_items = (P.NBY * P.NBX + 31) / 32;
+    P.interleave = dbg_env_int("BTPOST_A_ILV", 0);
+    P.pref = dbg_env_int("BTPOST_A_PREF", 0);   // measured: 0 / 1 / 2 / 4 tiles ahead = 99.6 / 101.5 / 102.6 / 106.6 us per pipelined step
     P.inv_K = 1.0f / (float)p.max_det; P.inv_m1 = 1.0f / (float)P.m1_items; P.inv_NBX = 1.0f / (float)P.NBX;
     {
         const int rows[3] = {0, P.NBY > 2 ? 1 : 0, P.NBY - 1}, cols[3] = {0, P.NBX > 2 ? 1 : 0, P.NBX - 1};
@@ -1020,7 +1096,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
         }
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);   // grid sizing only: the kernel reads the real count
-        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * dbg_env_int("BTPOST_C_CTAS", 7);
+        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * dbg_env_int("BTPOST_C_CTAS", 8);
         if (parts & BT_MASKS_CELLS) {
             const long long ctas = want < cap ? want : cap;
             P.nq = 1;   // queues: a power of two <= warps in the grid (every queue needs a home warp), at most C_NQ
@@ -1028,10 +1104,15 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             const size_t inst_words = (size_t)p.batch * p.max_det * p.img_h * (p.img_w / 32);
             if (io.inst_bits && cudaMemsetAsync(io.inst_bits, 0, inst_words * 4, s) != cudaSuccess) return BT_ERR_CUDA;
 #ifdef BT_DEBUG_HOOKS
-            if (dbg_env_int("BTPOST_C_MINB", 7) == 8) cells_kernel<8><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            const int gs = dbg_env_int("BTPOST_C_GS", 16), mb = dbg_env_int("BTPOST_C_MINB", 8);
+            if (gs == 32 && mb == 7) cells_kernel<7, 32><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            else if (gs == 32) cells_kernel<8, 32><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            else if (gs == 16 && mb == 7) cells_kernel<7, 16><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            else if (gs == 8 && mb == 7) cells_kernel<7, 8><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            else if (gs == 8) cells_kernel<8, 8><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
             else
 #endif
-            cells_kernel<7><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);
+            cells_kernel<8, 16><<<(unsigned)ctas, C_WARPS * 32, 0, s>>>(P);   // measured (pipelined step): groups of 32 / 16 / 8 / 4 lanes = 99.4 / 97.4 / 101.1 / 108.4 us
             if (io.inst_bits && io.inst_masks) {
                 const size_t want_d = (inst_words + C_THREADS - 1) / C_THREADS, cap_d = (size_t)sm_count * 16;
                 inst_dense_kernel<<<(unsigned)(want_d < cap_d ? want_d : cap_d), C_THREADS, 0, s>>>(P.inst_bits, io.inst_masks, inst_words);

@@ -236,6 +236,100 @@ __device__ __forceinline__ void sort_to_smem(const float *cscore, int M, int nth
     __syncthreads();
 }
 
+// Stable LSD radix sort (four passes of 8 bits) of the 32-bit descending score keys for lists of <= RADIX_MAX
+// candidates: stability gives "ties -> lower index" for free, so only 32-bit keys are compared, and a pass is two
+// walks of 32 candidates per warp step (match.any on the digit) plus one block scan -- a fifth of the instructions of
+// the 64-bit bitonic network and a third of its barriers.  Warp w owns a contiguous tile of the list; counters are
+// laid out digit-major ([256][warps]) so their exclusive scan is the stable order.  On return s_sidx[i] (i < M) =
+// index of the i-th candidate in NMS order.  Every thread of the block must call this.
+constexpr int RADIX_MAX = 2048;
+// lanes of the warp that hold the same digit: 8 independent ballots
+__device__ __forceinline__ unsigned digit_peers(int d, bool valid) {
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool one = (d >> bit) & 1;
+        const unsigned bm = __ballot_sync(0xffffffffu, one);
+        peers &= one ? bm : ~bm;
+    }
+    return peers;
+}
+template <int NT>
+__device__ __forceinline__ void radix_sort_to_smem(const float *cscore, int M, unsigned char *smem_raw, uint32_t *s_sidx) {
+    constexpr int NW = NT / 32;
+    __shared__ int s_wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Mp = (M + 31) & ~31;
+    unsigned long long *bufA = reinterpret_cast<unsigned long long *>(smem_raw), *bufB = bufA + Mp;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(bufB + Mp);   // [256 * NW]
+    const int nchunks = Mp >> 5, cpw = (nchunks + NW - 1) / NW;
+    const int c_lo = min(wid * cpw, nchunks), c_hi = min(c_lo + cpw, nchunks);
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = tid; i < M; i += NT) bufA[i] = ((unsigned long long)desc_key(__ldg(cscore + i)) << 32) | (unsigned)i;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const unsigned long long *src = (pass & 1) ? bufB : bufA;
+        unsigned long long *dst = (pass & 1) ? bufA : bufB;
+        const int shift = 32 + 8 * pass;
+        for (int i = tid; i < 256 * NW; i += NT) hist[i] = 0;
+        __syncthreads();
+        for (int c = c_lo; c < c_hi; ++c) {
+            const int i = c * 32 + lane;
+            const bool valid = i < M;
+            const int d = valid ? (int)((src[valid ? i : 0] >> shift) & 255ull) : 256;
+            const unsigned peers = digit_peers(d, valid);
+            if (valid && lane == __ffs(peers) - 1) hist[d * NW + wid] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan of the 256 * NW counters: 8 consecutive ones per thread
+            uint4 *h4 = reinterpret_cast<uint4 *>(hist) + 2 * tid;
+            uint4 a = h4[0], b = h4[1];
+            const unsigned v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            unsigned ex[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ex[j] = sum; sum += v[j]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, incl, dd);
+                if (lane >= dd) incl += u;
+            }
+            if (lane == 31) s_wsum[wid] = (int)incl;
+            __syncthreads();
+            const unsigned wv = lane < NW ? (unsigned)s_wsum[lane] : 0u;
+            unsigned winc = wv;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, winc, dd);
+                if (lane >= dd) winc += u;
+            }
+            const unsigned base = __shfl_sync(0xffffffffu, winc - wv, wid) + incl - sum;
+            a = make_uint4(ex[0] + base, ex[1] + base, ex[2] + base, ex[3] + base);
+            b = make_uint4(ex[4] + base, ex[5] + base, ex[6] + base, ex[7] + base);
+            h4[0] = a; h4[1] = b;
+        }
+        __syncthreads();
+        for (int c = c_lo; c < c_hi; ++c) {
+            const int i = c * 32 + lane;
+            const bool valid = i < M;
+            const unsigned long long e = src[valid ? i : 0];
+            const int d = valid ? (int)((e >> shift) & 255ull) : 256;
+            const unsigned peers = digit_peers(d, valid);
+            unsigned rank = 0;
+            if (valid) rank = hist[d * NW + wid] + __popc(peers & lt);
+            __syncwarp();
+            if (valid && lane == __ffs(peers) - 1) hist[d * NW + wid] += __popc(peers);
+            __syncwarp();
+            if (valid) {
+                if (pass < 3) dst[rank] = e;
+                else s_sidx[rank] = (uint32_t)e;   // the keys are not needed any more: the index list lands where bufA was
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // =================================================================================================
 // fused NMS kernel
 // =================================================================================================
@@ -250,20 +344,18 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     uint32_t *s_sidx = reinterpret_cast<uint32_t *>(smem_raw);
     float4 *s_sbox = reinterpret_cast<float4 *>(smem_raw + P.region0_bytes);                 // [WIN] window, NMS coordinates
     float4 *s_kbox = s_sbox + WIN;                                                           // [K] kept boxes
-    float2 *s_sctr = reinterpret_cast<float2 *>(s_kbox + K);                                 // [WIN] centres
-    float2 *s_kctr = s_sctr + WIN;                                                           // [K] kept centres
-    float *s_sarea = reinterpret_cast<float *>(s_kctr + K);                                  // [WIN]
+    // [K] (area bits, label, next kept box of the same cell, index into the filtered list): with the box, everything the
+    // walk over a cell's list needs arrives in ONE round trip to shared memory (two 16-byte loads issued together)
+    int4 *s_kmeta = reinterpret_cast<int4 *>(s_kbox + K);
+    float2 *s_sctr = reinterpret_cast<float2 *>(s_kmeta + K);                                // [WIN] centres
+    float *s_sarea = reinterpret_cast<float *>(s_sctr + WIN);                                // [WIN]
     float *s_sscore = s_sarea + WIN;                                                         // [WIN]
     int *s_slabel = reinterpret_cast<int *>(s_sscore + WIN);                                 // [WIN]
     int *s_sanchor = s_slabel + WIN;                                                         // [WIN]
     int *s_sorig = s_sanchor + WIN;                                                          // [WIN] index into the filtered list
-    float *s_karea = reinterpret_cast<float *>(s_sorig + WIN);                               // [K]
-    float *s_kscore = s_karea + K;                                                           // [K]
-    int *s_klabel = reinterpret_cast<int *>(s_kscore + K);                                   // [K]
-    int *s_kanchor = s_klabel + K;                                                           // [K]
-    int *s_korig = s_kanchor + K;                                                            // [K]
-    int *s_knext = s_korig + K;                                                              // [K] next kept box of the same cell
-    int *s_scell = s_knext + K;                                                              // [WIN] packed cell range under the box
+    float *s_kscore = reinterpret_cast<float *>(s_sorig + WIN);                              // [K]
+    int *s_kanchor = reinterpret_cast<int *>(s_kscore + K);                                  // [K]
+    int *s_scell = s_kanchor + K;                                                            // [WIN] packed cell range under the box
     __shared__ unsigned int s_row32[NMS_CHUNK * 2];
     __shared__ int s_cellhead[MAX_CELLS], s_celltail[MAX_CELLS];
     __shared__ unsigned int s_supA[2];
@@ -294,7 +386,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     const unsigned long long *gkeys = nullptr;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        if (K2_THREADS == 256 && M_all <= 256) sort_to_smem<1>(cscore, M_all, 256, s_x, s_sidx);
+        if (M_all <= RADIX_MAX) radix_sort_to_smem<K2_THREADS>(cscore, M_all, smem_raw, s_sidx);
+        else if (K2_THREADS == 256 && M_all <= 256) sort_to_smem<1>(cscore, M_all, 256, s_x, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 512) sort_to_smem<2>(cscore, M_all, 256, s_x, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 1024) sort_to_smem<4>(cscore, M_all, 256, s_x, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 2048) sort_to_smem<8>(cscore, M_all, 256, s_x, s_sidx);
@@ -393,11 +486,15 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                         while (qx >= ncx) { qx -= ncx; ++qy; }
                         while (qy < ncy && !f) {
                             // lists are in keep order: the strongest box of a cluster comes first and usually settles it
-                            for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0 && !f; k = s_knext[k]) {
-                                const float2 ck = s_kctr[k];
-                                if (!(ck.x >= bj.x && ck.x <= bj.z && ck.y >= bj.y && ck.y <= bj.w)) continue;
-                                f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
-                                               P.class_mode, 1, cj.x, cj.y, P.fast);
+                            for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0 && !f;) {
+                                const float4 kb = s_kbox[k];
+                                const int4 km = s_kmeta[k];
+                                k = km.z;
+                                // the kept box's centre, the expression its cell was chosen by
+                                const float ckx = __fmul_rn(__fadd_rn(kb.x, kb.z), 0.5f), cky = __fmul_rn(__fadd_rn(kb.y, kb.w), 0.5f);
+                                if (!(ckx >= bj.x && ckx <= bj.z && cky >= bj.y && cky <= bj.w)) continue;
+                                f = suppresses(kb, __int_as_float(km.x), km.y, bj, aj, lj, P.thr_up, P.early_out, P.class_mode, 1,
+                                               cj.x, cj.y, P.fast);
                             }
                             qx += 4;
                             while (qx >= ncx) { qx -= ncx; ++qy; }
@@ -414,9 +511,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                         const float4 bj = s_sbox[c0 + ci];
                         const float aj = s_sarea[c0 + ci];
                         const int lj = s_slabel[c0 + ci];
-                        for (int k = sub; k < nkept && !f; k += 16)
-                            f = suppresses(s_kbox[k], s_karea[k], s_klabel[k], bj, aj, lj, P.thr_up, P.early_out,
-                                           P.class_mode, 0, 0.0f, 0.0f, P.fast);
+                        for (int k = sub; k < nkept && !f; k += 16) {
+                            const int4 km = s_kmeta[k];
+                            f = suppresses(s_kbox[k], __int_as_float(km.x), km.y, bj, aj, lj, P.thr_up, P.early_out, P.class_mode, 0,
+                                           0.0f, 0.0f, P.fast);
+                        }
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, f);
                     if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
@@ -504,18 +603,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                 const int slot = nkept + __popcll(keepm & ((1ull << tid) - 1ull));
                 const float2 ctr = s_sctr[c0 + tid];
                 s_kbox[slot] = s_sbox[c0 + tid];
-                s_kctr[slot] = ctr;
-                s_karea[slot] = s_sarea[c0 + tid];
-                s_klabel[slot] = s_slabel[c0 + tid];
+                s_kmeta[slot] = make_int4(__float_as_int(s_sarea[c0 + tid]), s_slabel[c0 + tid], -1, s_sorig[c0 + tid]);
                 s_kscore[slot] = s_sscore[c0 + tid];
                 s_kanchor[slot] = s_sanchor[c0 + tid];
-                s_korig[slot] = s_sorig[c0 + tid];
                 if (P.centre_cull) {
                     // append to the cell's list (keep order: earlier, stronger boxes first)
                     const int cell = cell_y(ctr.y) * P.gx + cell_x(ctr.x);
-                    s_knext[slot] = -1;
                     const int prev = atomicExch(&s_celltail[cell], slot);
-                    if (prev < 0) s_cellhead[cell] = slot; else s_knext[prev] = slot;
+                    if (prev < 0) s_cellhead[cell] = slot; else s_kmeta[prev].z = slot;
                 }
             }
             nkept += __popcll(keepm);
@@ -530,12 +625,13 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     for (int k = tid; k < K; k += K2_THREADS) {
         float *o = P.dets + ((size_t)b * K + k) * 6;
         if (k < nkept) {
-            const int idx = s_korig[k];
+            const int4 km = s_kmeta[k];
+            const int idx = km.w;
             float4 bx = s_kbox[k];
             if (P.class_mode == BT_CLASS_OFFSET) bx = __ldg(cbox + idx);   // un-offset coordinates
             o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
             o[4] = s_kscore[k];
-            o[5] = (float)s_klabel[k];
+            o[5] = (float)km.y;
             P.det_keep[(size_t)b * K + k] = idx;
             P.det_anchor[(size_t)b * K + k] = s_kanchor[k];
             int r_lo, r_hi, c_lo, c_hi;
@@ -950,6 +1046,11 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     P.region0_bytes = (int)region0;
     size_t smem_a = region0 + (size_t)K2_TAIL_WIN * 48 + (size_t)p.max_det * 48 + 64;
     if (smem_a < (size_t)sort_slots * 8) smem_a = (size_t)sort_slots * 8;
+    {   // radix sort of short lists: two (key, index) buffers + [256][warps] counters
+        const size_t mp = (size_t)(P.cap < RADIX_MAX ? (P.cap + 31) / 32 * 32 : RADIX_MAX);
+        const size_t need = 16 * mp + 1024 * (size_t)(nt / 32);
+        if (smem_a < need) smem_a = need;
+    }
     if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
     // match_kernel: COCO tables
     const int coco_doubles = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;   // boxes + room for a [K x 4] IoU block

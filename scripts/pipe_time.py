@@ -15,6 +15,13 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 label = sys.argv[3] if len(sys.argv) > 3 else ""
 B, S = 64, 640
 dev = torch.device("cuda:0")
+torch.zeros(1, device=dev)
+if os.environ.get("L2G"):   # cudaLimitMaxL2FetchGranularity (0x05): DRAM -> L2 fetch size hint, default 64 bytes
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2G"])))
+    v = ctypes.c_size_t(0); rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
+    print("cudaLimitMaxL2FetchGranularity ->", rc, v.value, flush=True)
 first = synth.make_batch_device(synth.SynthConfig(batch=B, img_size=S, seed=20262), dev)
 cfg = PostConfig(batch=B, img_size=S, nms_threads=int(os.environ.get("NMS_NT", "0")))
 sweep = DeviceSweep(cfg.nc, map_iou_thresholds(), (1, 10, 100), capacity=1 << 23, max_det_per_image=300, device=dev) if os.environ.get("SWEEP") else None
@@ -39,6 +46,6 @@ run(4 * depth)
 t20 = min(run(20) for _ in range(5))
 tn = min(run(steps) for _ in range(3))
 o = pipe.procs[0].out
-sw = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if (k.startswith("BTPOST_") or k in ("NMS_NT", "SWEEP", "FILL")) and k != "BTPOST_LIB")
+sw = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if (k.startswith("BTPOST_") or k in ("NMS_NT", "SWEEP", "FILL", "L2G")) and k != "BTPOST_LIB")
 print(f"{label:24s} depth {depth}: {tn:7.2f} us/step over {steps} steps, {t20:7.2f} over 20 | dets {o['det_count'][:3].tolist()} "
       f"dice {o['seg_dice'][0].item():.6f} uni {o['uni_dice'][0].item():.6f} | {sw}", flush=True)
