@@ -54,29 +54,74 @@ def workload_name(args):
 
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock + throttle reasons during the timed region with the recipe's own
-    `nvidia-smi --query-gpu=... -lms` line, run as a SEPARATE process (NVML calls made from a thread
-    of this process serialise against CUDA launches and were measured to double the step time)."""
+    """SM clock + throttle reasons DURING the timed region.  NVML is read in-process from the launching thread, but only
+    after every step of the region has been enqueued and until the closing event completes: the GPU is still working
+    through the region while the host has nothing left to launch (NVML calls made from a second thread serialise against
+    CUDA launches and were measured to double the step time; a `nvidia-smi -lms` child process started next to the region
+    spends the region's 2 ms loading NVML and competes for the driver with the launches).  Falls back to the recipe's
+    `nvidia-smi --query-gpu=... -lms` line, started before the warm-up, when pynvml is missing."""
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index, period_ms=100):
+        self.nv = self.handle = self.proc = self.path = None
+        self.mhz, self.max_mhz, self.reasons, self.t0 = [], None, set(), None
+        if period_ms <= 0:
+            return
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            try:
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            return
+        except Exception:
+            self.nv = self.handle = None
         import shutil
         import subprocess
         import tempfile
-        self.proc, self.path = None, None
         exe = shutil.which("nvidia-smi")
-        if exe is None or period_ms <= 0:
+        if exe is None:
             return
         f = tempfile.NamedTemporaryFile(prefix="btpost_clocks_", suffix=".csv", delete=False)
         self.path = f.name
         self.proc = subprocess.Popen([exe, "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                       "-lms", str(period_ms)], stdout=f, stderr=subprocess.DEVNULL)
 
+    def mark_start(self):
+        """The timed region starts now (the nvidia-smi fallback keeps only the lines written from here on)."""
+        if self.path is not None:
+            self.t0 = os.path.getsize(self.path)
+
+    def poll_until(self, event):
+        """Called once the whole region is enqueued: sample until `event` (recorded at its end) has completed."""
+        if self.nv is None:
+            return
+        while True:
+            try:
+                self.mhz.append(int(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.reasons.update(n for n, bit in self.REASONS.items() if mask & bit)
+            except Exception:
+                break
+            if event.query():
+                break
+
     def stop(self):
+        if self.nv is not None:
+            mhz = sorted(self.mhz)
+            return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(mhz), "source": "nvml, polled by the launching thread between the last launch and the end of the region"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "nvidia-smi not found"}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "neither pynvml nor nvidia-smi found"}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -84,7 +129,8 @@ class ClockSampler:
             self.proc.kill()
         mhz, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in open(self.path).read().splitlines():
+        text = open(self.path).read()
+        for ln in text[self.t0 or 0:].splitlines() or text.splitlines()[-1:]:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6 or not parts[0].isdigit():
                 continue
@@ -99,7 +145,7 @@ class ClockSampler:
             pass
         mhz.sort()
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz)}
+                "samples": len(mhz), "source": "nvidia-smi -lms child process"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -205,7 +251,7 @@ def main():
         sweep = DeviceSweep(cfg.nc, map_iou_thresholds(), (1, 10, 100), capacity=cap, max_det_per_image=args.max_det, device=dev)
     first = synth.make_batch_device(synth.SynthConfig(batch=B, img_size=S, seed=SEED, image_offset=(rank * depth) * B), dev)
     bias = float(first["proj_bias"])
-    pipe = Pipeline(cfg, dev, depth=depth, proj_weight=first["proj_weight"], proj_bias=bias, sweep=sweep)
+    pipe = Pipeline(cfg, dev, depth=depth, proj_weight=first["proj_weight"], proj_bias=bias, sweep=sweep, auto_image_offset=True)
     # every slot gets its OWN, different batch (generated on the device, bit-identical to the numpy generator): a buffer
     # is read again only after the other depth-1 input sets (depth x 320 MB at 640^2) have streamed through
     gt_rows = []
@@ -229,31 +275,32 @@ def main():
         torch.cuda.synchronize()
 
     graph = pp.capture(i0["head"], i0["protos"], i0["det_boxes_gt"], i0["masks_gt"], pipe.proj_weight, bias)
-    img_base = 0
+    sampler = ClockSampler(local_rank, args.clock_period_ms)   # NVML is initialised here, outside the timed region
+    # the images are numbered on the device (every captured step bumps its slot's counter): no host work per step
+    pipe.set_image_base(rank * (args.steps + args.warmup) * B)
     pipe.fork()
     for _ in range(args.warmup):
-        pipe.replay(image_offset=img_base)
-        img_base += B
+        pipe.replay()
     pipe.join()
     hdr = sweep.hdr if sweep is not None else torch.zeros(8, dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(hdr.clone())    # connects the NCCL peers: communicator set-up is not part of the timed region
     barrier()
-    sampler = ClockSampler(local_rank, args.clock_period_ms)
 
     # ---------------- timed region: K steps over rotating input sets, inputs resident in HBM
     pipe.reset_metrics()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_start()
     ev0.record()
     pipe.fork()
     for _ in range(args.steps):
-        pipe.replay(image_offset=img_base)      # step i on slot i % depth: consecutive batches overlap, every step does all of its work
-        img_base += B
+        pipe.replay()      # step i on slot i % depth: consecutive batches overlap, every step does all of its work
     pipe.join()
     if world > 1:
         dist.all_reduce(hdr)  # the only collective: the sweep header = all metric counters (NCCL over NVLink)
     ev1.record()
+    sampler.poll_until(ev1)   # everything is enqueued: read the clocks while the GPU works through the region
     barrier()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -305,14 +305,18 @@ class PostProcessor:
         _lib.check(rc, f"btpost_{stage}")
         return self.out
 
-    def capture(self, head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias=0.0, **kw):
+    def capture(self, head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias=0.0, image_stride=0, **kw):
         """Capture one step on these (static) buffers into a CUDA graph; returns the graph, whose
         ``replay()`` re-runs the whole hot path with one host call (the library is capture-safe:
-        no allocation, no synchronisation, caller's stream only)."""
+        no allocation, no synchronisation, caller's stream only).  ``image_stride`` > 0: every replay first adds it to
+        the device-resident ``image_base`` (global index of the batch's first image in the sweep records), so a
+        round-robin of slots numbers its images without any host work per step."""
         self.run(head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias, **kw)   # warm-up: attributes, module load
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
+            if image_stride:
+                self.image_base.add_(int(image_stride))
             self.run(head, protos, det_boxes_gt, masks_gt, proj_weight, proj_bias, **kw)
         return g
 
@@ -357,7 +361,7 @@ class Pipeline:
     matches no image."""
 
     def __init__(self, cfg: PostConfig, device="cuda:0", depth: int = 2, gt_rows_cap: int | None = None,
-                 proj_weight=None, proj_bias: float = 0.0, sweep=None):
+                 proj_weight=None, proj_bias: float = 0.0, sweep=None, auto_image_offset: bool = False):
         conf = cfg.conf_thres if cfg.conf_thres is not None else CONF_TH
         if depth > 1 and cfg.nms_threads == 0 and conf >= 0.01:
             # small-footprint NMS kernel: its CTAs share SMs with the mask kernels of the other batches in flight
@@ -366,6 +370,7 @@ class Pipeline:
         if cfg.layout != _lib.LAYOUT_L2:
             raise ValueError("Pipeline takes the L2 head layout ([B, 4+nc+nm, N])")
         self.cfg, self.depth = cfg, depth
+        self.auto_image_offset = bool(auto_image_offset)   # images numbered on the device (see set_image_base)
         self.device = dev = torch.device(device)
         nc, B, S = cfg.nc, cfg.batch, cfg.img_size
         self.sweep = sweep
@@ -398,9 +403,36 @@ class Pipeline:
         self.graphs = []
         for p, inp in zip(self.procs, self.inputs):
             self.graphs.append(p.capture(inp["head"], inp["protos"], inp["det_boxes_gt"], inp["masks_gt"], self.proj_weight,
-                                         self.proj_bias))
+                                         self.proj_bias, image_stride=self.depth * self.cfg.batch if self.auto_image_offset else 0))
         self.reset_metrics()   # the warm-up / capture runs counted the zero inputs
+        if self.auto_image_offset:
+            self.set_image_base(0)
         torch.cuda.synchronize(self.device)
+        self._bind_graphs()
+
+    def _bind_graphs(self):
+        """Raw executable-graph handles: a replay is then ONE cudaGraphLaunch on the slot's stream (a few microseconds of
+        host time instead of a stream context manager around CUDAGraph.replay(); with five batches in flight the host has
+        to get five launches out before the GPU is full).  Falls back to CUDAGraph.replay() when this torch build does
+        not expose the handles."""
+        self._exec, self._cudart = None, None
+        try:
+            rt = C.CDLL("libcudart.so.12")
+            rt.cudaGraphLaunch.argtypes = [C.c_void_p, C.c_void_p]
+            rt.cudaGraphLaunch.restype = C.c_int
+            self._exec = [int(g.raw_cuda_graph_exec()) for g in self.graphs]
+            self._cudart = rt
+        except Exception:
+            self._exec, self._cudart = None, None
+
+    def set_image_base(self, first: int):
+        """auto_image_offset: the next replayed step holds the images first .. first + B - 1, the one after it the
+        next B, and so on (each slot's captured step adds depth * B to its own counter before it runs)."""
+        if not self.auto_image_offset:
+            raise ValueError("Pipeline was built without auto_image_offset")
+        B, d = self.cfg.batch, self.depth
+        for s, p in enumerate(self.procs):
+            p.image_base.fill_(int(first) + ((s - self._i) % d) * B - d * B)
 
     # -- feeding --------------------------------------------------------------------------------
     def load(self, slot, head, protos, det_boxes_gt, masks_gt, stream=None):
@@ -425,21 +457,31 @@ class Pipeline:
 
     def replay(self, slot=None, image_offset=None):
         """Run the captured step of `slot` (default: round robin) on its stream; returns the slot's PostProcessor.
-        `image_offset` = global index of the batch's first image (sweep records; one 4-byte fill on the slot's stream)."""
+        `image_offset` = global index of the batch's first image (sweep records; one 4-byte fill on the slot's stream);
+        a pipeline built with ``auto_image_offset`` numbers the images itself (round-robin replays only)."""
         i = self._i % self.depth if slot is None else slot
         self._i += 1
-        with torch.cuda.stream(self.streams[i]):
-            if image_offset is not None:
+        if self.auto_image_offset and (image_offset is not None or slot is not None):
+            raise ValueError("auto_image_offset: replay() takes neither a slot nor an image offset")
+        st = self.streams[i]
+        if image_offset is not None:
+            with torch.cuda.stream(st):
                 self.procs[i].image_base.fill_(int(image_offset))
-            self.graphs[i].replay()
-            self.events[i].record()
+        if self._exec is not None:
+            rc = self._cudart.cudaGraphLaunch(self._exec[i], st.cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"cudaGraphLaunch failed with CUDA error {rc}")
+        else:
+            with torch.cuda.stream(st):
+                self.graphs[i].replay()
+        self.events[i].record(st)
         return self.procs[i]
 
     def submit(self, head, protos, det_boxes_gt, masks_gt, image_offset=None):
         """Copy one batch into the next slot and run it; returns the slot index (pass it to `wait`)."""
         i = self._i % self.depth
         self.load(i, head, protos, det_boxes_gt, masks_gt)
-        self.replay(i, image_offset)
+        self.replay(None if self.auto_image_offset else i, image_offset)
         return i
 
     def wait(self, slot):

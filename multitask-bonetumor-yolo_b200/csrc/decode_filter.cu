@@ -64,13 +64,16 @@ __device__ __forceinline__ int block_excl_scan(int c, int &total, int *s_warp) {
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    int off = 0, tot = 0;
+    // second level: every warp scans the (<= 32) warp totals with shuffles
     const int nw = (blockDim.x + 31) >> 5;
-    for (int w = 0; w < nw; ++w) {
-        int v = s_warp[w];
-        if (w < wid) off += v;
-        tot += v;
+    const int wv = lane < nw ? s_warp[lane] : 0;
+    int winc = wv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += v;
     }
+    const int off = __shfl_sync(0xffffffffu, winc - wv, wid), tot = __shfl_sync(0xffffffffu, winc, 31);
     __syncthreads();
     total = tot;
     return off + incl - c;
@@ -240,7 +243,7 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
     __shared__ int s_warp[K1_MAX_WARPS];
     __shared__ int s_ex;                 // this CTA's survivor count, read by peers through DSMEM
     __shared__ float s_coord[K1_MAX_GT][4];
-    __shared__ float s_gtraw[K1_MAX_GT * 4];
+    __shared__ __align__(16) float s_gtraw[K1_MAX_GT * 4];
     __shared__ int s_gl[K1_MAX_GT];
     __shared__ int s_G;
     __shared__ int s_cm[BT_MAX_CLASSES * BT_MAX_CLASSES];
@@ -339,15 +342,17 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
                 // max / first-argmax over GT is evaluated exactly as the reference does.
                 bool any = P.cm_thr < 0.0f;
                 for (int q = 0; q < G && !any; ++q) {
-                    float iw = __fsub_rn(fminf(x2[i], s_gtraw[4 * q + 2]), fmaxf(x1[i], s_gtraw[4 * q]));
-                    float ih = __fsub_rn(fminf(y2[i], s_gtraw[4 * q + 3]), fmaxf(y1[i], s_gtraw[4 * q + 1]));
+                    const float4 gq = reinterpret_cast<const float4 *>(s_gtraw)[q];
+                    float iw = __fsub_rn(fminf(x2[i], gq.z), fmaxf(x1[i], gq.x));
+                    float ih = __fsub_rn(fminf(y2[i], gq.w), fmaxf(y1[i], gq.y));
                     any = (iw > 0.0f) && (ih > 0.0f);
                 }
                 if (!any) continue;
                 float a1 = __fmul_rn(__fsub_rn(x2[i], x1[i]), __fsub_rn(y2[i], y1[i]));
                 float bi = 0.0f; int bg = 0;
                 for (int q = 0; q < G; ++q) {
-                    float qx1 = s_gtraw[4 * q], qy1 = s_gtraw[4 * q + 1], qx2 = s_gtraw[4 * q + 2], qy2 = s_gtraw[4 * q + 3];
+                    const float4 gq = reinterpret_cast<const float4 *>(s_gtraw)[q];
+                    float qx1 = gq.x, qy1 = gq.y, qx2 = gq.z, qy2 = gq.w;
                     float ix1 = fmaxf(x1[i], qx1), iy1 = fmaxf(y1[i], qy1);
                     float ix2 = fminf(x2[i], qx2), iy2 = fminf(y2[i], qy2);
                     float iw = __fsub_rn(ix2, ix1); iw = iw < 0.0f ? 0.0f : iw;

@@ -106,6 +106,16 @@ __device__ __forceinline__ void tma_tile_prefetch_l2(const CUtensorMap *tm, int 
                  "r"(row), "r"(chan0)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -410,9 +420,11 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     constexpr int TILE_FLOATS = NM * TA_H * TA_W / (BF16 ? 2 : 1);                     // tile size in 4-byte words
     float *s_tiles = reinterpret_cast<float *>(smem);                                  // [NBUF][NM][TA_H][TA_W], 16-byte chunks XOR row
     __shared__ __align__(8) uint64_t s_bar[NBUF];
-    __shared__ __align__(16) float s_cf[A_LCAP][NM];
-    __shared__ short4 s_reg[A_LCAP];
-    __shared__ int s_off[A_LCAP];        // pool offset of the box origin minus (r_lo * bw + c_lo): + r * bw + c addresses a pixel
+    // per-tile tables of the listed detections (coefficients, crop regions, pool offsets of the box origins), two sets:
+    // the next tile's set is filled by cp.async while this tile is computed, so a tile costs ONE block barrier
+    __shared__ __align__(16) float s_cf2[2][A_LCAP][NM];
+    __shared__ __align__(8) short4 s_reg2[2][A_LCAP];
+    __shared__ int s_off2[2][A_LCAP];
     __shared__ __align__(16) float s_w[NM];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -474,9 +486,9 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
     const int soff = BF16 ? row * (TA_W / 2) + ((((colp >> 3) ^ (row >> 1)) & 3) << 2) + ((colp & 7) >> 1)
                           : row * TA_W + (((colp >> 2) ^ row) << 2) + (colp & 3);
 
-    // The tile's detections were binned by the plan (coeff_gather_kernel).  List length and the list entries this
-    // thread needs for the first round are fetched one tile ahead, so that a tile starts with ONE round of
-    // independent loads (coefficients, regions, pool offsets) that travel under the tile wait and the projection.
+    // The tile's detections were binned by the plan.  List length and the list entries this thread copies are fetched
+    // TWO tiles ahead; one tile ahead (right after the barrier that retires the previous tile's reads) every thread issues
+    // its cp.async copies of the coefficients / regions / pool offsets into the other table set.
     struct Meta { int nlist, kq0, kq1, k0; };
     auto fetch_meta = [&](int tile) {
         Meta m;
@@ -488,27 +500,32 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         m.k0 = (tid < nch0) ? __ldg(list + tid) : 0;
         return m;
     };
-    Meta cur = fetch_meta(t_begin);
+    auto stage_async = [&](const Meta &m, int b, int set) {   // round 0 of a tile's tables -> table set `set`
+        const int nch0 = min(A_LCAP, m.nlist);
+        if (tid < nch0 * (NM / 4))
+            cp_async16(&s_cf2[set][tid >> 3][(tid & 7) * 4], P.det_coeff + ((size_t)b * K + m.kq0) * NM + (tid & 7) * 4);
+        if (tid + A_THREADS < nch0 * (NM / 4))
+            cp_async16(&s_cf2[set][(tid + A_THREADS) >> 3][(tid & 7) * 4], P.det_coeff + ((size_t)b * K + m.kq1) * NM + (tid & 7) * 4);
+        if (tid < nch0) {
+            cp_async8(&s_reg2[set][tid], P.det_region + (size_t)b * K + m.k0);
+            cp_async4(&s_off2[set][tid], P.scr_off + (size_t)b * K + m.k0);
+        }
+    };
+    Meta cur = fetch_meta(t_begin), nxt = cur;
+    stage_async(cur, at.b, 0);
+    TileAt at_n = at;   // the tile after the current one
+    step(at_n);
+    if (t_begin + ts < t_end) nxt = fetch_meta(t_begin + ts);
 
-    for (int tile = t_begin, it = 0; tile < t_end; tile += ts, ++it, step(at)) {
+    for (int tile = t_begin, it = 0; tile < t_end; tile += ts, ++it, step(at), step(at_n)) {
         const int b = at.b;
         const int R0 = at.ty * TA_H, C0 = at.tx * TA_W;
         const int r = R0 + row, c = C0 + colp;
-
-        const int nlist = cur.nlist;
+        const int nlist = cur.nlist, set = it & 1;
         const unsigned short *list = P.tile_list + (size_t)tile * K;
-        const int nch0 = min(A_LCAP, nlist);
-        float4 cfr[2];
-        if (tid < nch0 * (NM / 4)) cfr[0] = __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + cur.kq0) * NM) + (tid & 7));
-        if (tid + A_THREADS < nch0 * (NM / 4))
-            cfr[1] = __ldg(reinterpret_cast<const float4 *>(P.det_coeff + ((size_t)b * K + cur.kq1) * NM) + (tid & 7));
-        short4 rg0 = make_short4(1, 0, 1, 0);
-        int off0 = 0;
-        if (tid < nch0) {
-            rg0 = __ldg(P.det_region + (size_t)b * K + cur.k0);
-            off0 = __ldg(P.scr_off + (size_t)b * K + cur.k0);
-        }
-        if (tile + ts < t_end) cur = fetch_meta(tile + ts);
+        float (*s_cf)[NM] = s_cf2[set];
+        short4 *s_reg = s_reg2[set];
+        int *s_off = s_off2[set];
 
         // ---- the tile: shared memory -> registers, then the buffer is free for the next tile
         const int buf = it % NBUF;
@@ -527,10 +544,16 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                 for (int k = 0; k < NM; ++k) p[k] = *reinterpret_cast<const u64 *>(src + k * (TA_H * TA_W));
             }
         }
-        __syncthreads();
+        cp_async_wait_all();   // this thread's copies into the tile's table set (issued a tile ago)
+        __syncthreads();       // the tile buffer is free, the table set is complete, the other set is no longer read
         if (tid == 0 && tile + NBUF * ts < t_end) {
             issue(at_issue, buf); step(at_issue);
             if (pref > 0 && tile + (NBUF + pref) * ts < t_end) { tma_tile_prefetch_l2(&tmap, at_pref.tx * TA_W, at_pref.ty * TA_H, at_pref.b * NM); step(at_pref); }
+        }
+        if (tile + ts < t_end) {
+            cur = nxt;
+            stage_async(cur, at_n.b, set ^ 1);
+            if (tile + 2 * ts < t_end) nxt = fetch_meta(tile + 2 * ts);
         }
 
         // ---- M1 projection: bias + sum_k w_k p_k, sequential fma (== torch conv2d, pinned)
@@ -552,14 +575,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
         const int wc0 = C0 + (wid << 3);   // the warp's 8 x 8 block: rows R0 .. R0+7, columns wc0 .. wc0+7
         for (int r0 = 0; r0 < nlist; r0 += A_LCAP) {
             const int nch = min(A_LCAP, nlist - r0);
-            if (r0 == 0) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int q = tid + j * A_THREADS;
-                    if (q < nch * (NM / 4)) reinterpret_cast<float4 *>(&s_cf[q >> 3][0])[q & 7] = cfr[j];
-                }
-                if (tid < nch) { s_reg[tid] = rg0; s_off[tid] = off0 - (rg0.x * (rg0.w - rg0.z + 1) + rg0.z); }
-            } else {
+            if (r0 > 0) {
                 __syncthreads();   // the previous round's tables are still being read
                 for (int q = tid; q < nch * (NM / 4); q += A_THREADS)
                     reinterpret_cast<float4 *>(&s_cf[q >> 3][0])[q & 7] =
@@ -568,10 +584,10 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                     const int k = __ldg(list + r0 + tid);
                     const short4 rg = __ldg(P.det_region + (size_t)b * K + k);
                     s_reg[tid] = rg;
-                    s_off[tid] = __ldg(P.scr_off + (size_t)b * K + k) - (rg.x * (rg.w - rg.z + 1) + rg.z);
+                    s_off[tid] = __ldg(P.scr_off + (size_t)b * K + k);
                 }
+                __syncthreads();
             }
-            __syncthreads();
             // the round's detections that touch this warp's block: one lane tests one detection
             short4 mine = make_short4(1, 0, 1, 0);
             if (lane < nch) mine = s_reg[lane];
@@ -582,7 +598,7 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                 if (r >= rg.x && r <= rg.y) {
                     float a0, a1;
                     unpack2(acc, a0, a1);
-                    float *dst = P.pool + (s_off[e] + r * (rg.w - rg.z + 1) + c);
+                    float *dst = P.pool + (s_off[e] + (r - rg.x) * (rg.w - rg.z + 1) + (c - rg.z));
                     if (c >= rg.z && c <= rg.w) dst[0] = a0;
                     if (c + 1 >= rg.z && c + 1 <= rg.w) dst[1] = a1;
                 }
@@ -620,7 +636,6 @@ contract_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUte
                 store(e, acc);
             }
         }
-        if (nlist) __syncthreads();   // the round tables are rewritten for the next tile
     }
 }
 
@@ -745,7 +760,7 @@ __device__ __forceinline__ void det_begin(const K3Params &P, int bk, int chunk, 
     w.i = chunk * C_CHUNK;
     w.i_end = min(nbx * nby, (chunk + 1) * C_CHUNK);
     w.off = __ldg(P.scr_off + bk);
-    w.inv = 1.0f / (float)nbx;
+    w.inv = __fdividef(1.0f, (float)nbx);   // approximate is enough: det_pass repairs a quotient that is off by one
 }
 // one pass: block w.i + gl of the item (gl = lane within the group)
 __device__ __forceinline__ void det_pass(const K3Params &P, const DetWork &w, int gl, int &area, int &inter, int &uarea, int &uinter) {

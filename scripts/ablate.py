@@ -33,6 +33,7 @@ for mask, name in names.items():
         with torch.cuda.graph(g):
             p.run(inp["head"], inp["protos"], inp["det_boxes_gt"], inp["masks_gt"], pipe.proj_weight, pipe.proj_bias)
         pipe.graphs.append(g)
+    pipe._bind_graphs()
     L.btpost_debug_skip(0)
     n = 300
     pipe.fork()

@@ -115,17 +115,17 @@ def test_device_sweep_through_pipeline_drop_flag_and_overflow():
     """Sweep records from captured steps replayed with several batches in flight (image index through the device-side
     `image_base`), the v2 `drop_gt_no_cand` rule in the GT counts, and the ring-overflow report."""
     B, S, depth = 4, 160, 3
-    for drop in (False, True):
+    for drop, auto in ((False, False), (True, False), (False, True)):   # auto: the images are numbered on the device
         sweep = DeviceSweep(3, oracle.iou_thresholds(), (1, 10, 100), capacity=8192, max_det_per_image=100, device="cuda:0")
         cfg = PostConfig(batch=B, img_size=S, max_det=100, gt_mode=1, with_coco=True, drop_gt_no_cand=drop)
         batches = [helpers.make(batch=B, img_size=S, seed=91, image_offset=B * i) for i in range(6)]
         batches[2]["head"][1, 4:7] = 0.0
         w, bias = helpers.to_dev(batches[0], "cuda:0")["proj_weight"], float(batches[0]["proj_bias"])
-        pipe = Pipeline(cfg, "cuda:0", depth=depth, proj_weight=w, proj_bias=bias, sweep=sweep)
+        pipe = Pipeline(cfg, "cuda:0", depth=depth, proj_weight=w, proj_bias=bias, sweep=sweep, auto_image_offset=auto)
         outs, offs = [], []
         for i, bt in enumerate(batches):
             d = helpers.to_dev(bt, "cuda:0")
-            pipe.submit(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], image_offset=B * i)
+            pipe.submit(d["head"], d["protos"], d["det_boxes_gt"], d["masks_gt"], image_offset=None if auto else B * i)
             outs.append(oracle.run_pipeline(bt, img_size=S, max_det=100, gt_mode=1)); offs.append(B * i)
         pipe.join()
         torch.cuda.synchronize()
