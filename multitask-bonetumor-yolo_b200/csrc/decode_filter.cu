@@ -53,7 +53,10 @@ struct K1Params {
     int32_t *cm_pos;
 };
 
-// Exclusive prefix of `c` over the block in thread order; `total` = block sum.
+// Exclusive prefix of `c` over the block in thread order; `total` = block sum.  SHFL: the second level (<= 32 warp totals)
+// is a shuffle scan done by every warp (L2 decoder); otherwise every thread walks the totals in shared memory (the L1
+// decoder is short of registers: the shuffle version spilled more and cost 30 us on the 64 x 640^2 batch).
+template <bool SHFL>
 __device__ __forceinline__ int block_excl_scan(int c, int &total, int *s_warp) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int incl = c;
@@ -64,16 +67,25 @@ __device__ __forceinline__ int block_excl_scan(int c, int &total, int *s_warp) {
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    // second level: every warp scans the (<= 32) warp totals with shuffles
     const int nw = (blockDim.x + 31) >> 5;
-    const int wv = lane < nw ? s_warp[lane] : 0;
-    int winc = wv;
+    int off = 0, tot = 0;
+    if (SHFL) {
+        const int wv = lane < nw ? s_warp[lane] : 0;
+        int winc = wv;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, winc, d);
-        if (lane >= d) winc += v;
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += v;
+        }
+        off = __shfl_sync(0xffffffffu, winc - wv, wid);
+        tot = __shfl_sync(0xffffffffu, winc, 31);
+    } else {
+        for (int w = 0; w < nw; ++w) {
+            int v = s_warp[w];
+            if (w < wid) off += v;
+            tot += v;
+        }
     }
-    const int off = __shfl_sync(0xffffffffu, winc - wv, wid), tot = __shfl_sync(0xffffffffu, winc, 31);
     __syncthreads();
     total = tot;
     return off + incl - c;
@@ -287,7 +299,7 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
                 hit = (row[0] == (float)b);
             }
             int tot;
-            int pos = base + block_excl_scan(hit ? 1 : 0, tot, s_warp);
+            int pos = base + block_excl_scan<!INTERLEAVED>(hit ? 1 : 0, tot, s_warp);
             if (hit && pos < P.max_gt) {
                 float cx = row[2], cy = row[3], w = row[4], h = row[5];
                 float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
@@ -381,12 +393,12 @@ __device__ __forceinline__ void k1_body(const K1Params &P, Dec &dec, int b) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {   // anchor order = pass-major
             int tot;
-            exclv[i] = run + block_excl_scan((flags >> i) & 1u, tot, s_warp);
+            exclv[i] = run + block_excl_scan<false>((flags >> i) & 1u, tot, s_warp);
             run += tot;
         }
         my_total = run;
     } else {
-        excl = block_excl_scan(c, my_total, s_warp);
+        excl = block_excl_scan<true>(c, my_total, s_warp);
     }
     if (tid == 0) s_ex = my_total;
     cluster.sync();
@@ -507,7 +519,8 @@ int launch_decode_filter(const BtParams &p, const BtIO &io, const Workspace &w, 
             else if (vec) decode_filter_l2_kernel<4, 1024, true><<<grid, block, 0, s>>>(P);
             else if (small) decode_filter_l2_kernel<1, 320, true><<<grid, block, 0, s>>>(P);
             else decode_filter_l2_kernel<1, 1024, true><<<grid, block, 0, s>>>(P);
-        } else if (vec && small) decode_filter_l2_kernel<4, 320><<<grid, block, 0, s>>>(P);
+        } else if (vec && block.x <= 288) decode_filter_l2_kernel<4, 288><<<grid, block, 0, s>>>(P);   // 8400 anchors: 56 registers, no second wave
+        else if (vec && small) decode_filter_l2_kernel<4, 320><<<grid, block, 0, s>>>(P);
         else if (vec) decode_filter_l2_kernel<4, 1024><<<grid, block, 0, s>>>(P);
         else if (small) decode_filter_l2_kernel<1, 320><<<grid, block, 0, s>>>(P);
         else decode_filter_l2_kernel<1, 1024><<<grid, block, 0, s>>>(P);

@@ -763,7 +763,9 @@ __device__ __forceinline__ void det_begin(const K3Params &P, int bk, int chunk, 
     w.inv = __fdividef(1.0f, (float)nbx);   // approximate is enough: det_pass repairs a quotient that is off by one
 }
 // one pass: block w.i + gl of the item (gl = lane within the group)
-__device__ __forceinline__ void det_pass(const K3Params &P, const DetWork &w, int gl, int &area, int &inter, int &uarea, int &uinter) {
+template <int GS>
+__device__ __forceinline__ void det_pass(const K3Params &P, const DetWork &w, int gl, unsigned gmask, int gbase, int &area, int &inter,
+                                         int &uarea, int &uinter) {
     const int PH = P.PH, PW = P.PW, NBX = P.NBX, NBY = P.NBY;
     const int r_lo = w.rg.x, r_hi = w.rg.y, c_lo = w.rg.z, c_hi = w.rg.w, bw = c_hi - c_lo + 1;
     const int by0 = r_lo >> 1, bx0 = c_lo >> 1, nbx = w.nbx, b = w.b;
@@ -800,8 +802,12 @@ __device__ __forceinline__ void det_pass(const K3Params &P, const DetWork &w, in
             }
     } else {
         // no room in the logit pool (huge crop boxes / crop off): contract the 9 corners here, same sequential order;
-        // the coefficients are broadcast loads (the lanes of a group read the same address)
+        // the group's lanes hold the 32 coefficients between them and broadcast one per channel with a shuffle
+        constexpr int NPL = NM / GS;
         const float *cf = P.det_coeff + (size_t)w.bk * NM;
+        float mycf[NPL];
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) mycf[q] = __ldg(cf + q * GS + gl);
         const size_t pr0 = (size_t)b * NM * PH * PW;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
@@ -809,27 +815,31 @@ __device__ __forceinline__ void det_pass(const K3Params &P, const DetWork &w, in
             for (int c = 0; c < 3; ++c) v[a][c] = 0.0f;
         if (!P.proto_bf16) {
             const float *pr = static_cast<const float *>(P.protos) + pr0;
-            for (int ch = 0; ch < NM; ++ch) {
-                const float wt = __ldg(cf + ch);
-                const float *pc = pr + (size_t)ch * PH * PW;
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
+            for (int q = 0; q < NPL; ++q)
+                for (int cl = 0; cl < GS; ++cl) {
+                    const float wt = __shfl_sync(gmask, mycf[q], gbase + cl);
+                    const float *pc = pr + (size_t)(q * GS + cl) * PH * PW;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(wt, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
-            }
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (rin[a] && cin[c]) v[a][c] = __fmaf_rn(wt, __ldg(pc + rr[a] * PW + cc[c]), v[a][c]);
+                }
         } else {
             const unsigned short *pr = static_cast<const unsigned short *>(P.protos) + pr0;
-            for (int ch = 0; ch < NM; ++ch) {
-                const float wt = __ldg(cf + ch);
-                const unsigned short *pc = pr + (size_t)ch * PH * PW;
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
+            for (int q = 0; q < NPL; ++q)
+                for (int cl = 0; cl < GS; ++cl) {
+                    const float wt = __shfl_sync(gmask, mycf[q], gbase + cl);
+                    const unsigned short *pc = pr + (size_t)(q * GS + cl) * PH * PW;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (rin[a] && cin[c])
-                            v[a][c] = __fmaf_rn(wt, __uint_as_float((uint32_t)__ldg(pc + rr[a] * PW + cc[c]) << 16), v[a][c]);
-            }
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (rin[a] && cin[c])
+                                v[a][c] = __fmaf_rn(wt, __uint_as_float((uint32_t)__ldg(pc + rr[a] * PW + cc[c]) << 16), v[a][c]);
+                }
         }
     }
     const size_t o = ((size_t)b * NBY + by) * NBX + bx;
@@ -907,43 +917,52 @@ __device__ __forceinline__ int atom_inc(int *p) {
 // holds the same mix of items and has the same number of warps, so they drain together (stealing from the other queues
 // cost a scan of 31 counters per warp at the end).  Detection items are taken by lane GROUPS (see DetWork), the projector
 // mask's runs of 32 blocks by whole warps once the queue's detections are out.
-template <int MINB, int GS>
-__global__ void __launch_bounds__(C_WARPS * 32, MINB) cells_kernel(const __grid_constant__ K3Params P) {
-    const int lane = threadIdx.x & 31, gl = lane & (GS - 1), gbase = lane & ~(GS - 1);
+// The detection items of queue q, taken by groups of GS lanes.
+template <int GS>
+__device__ __forceinline__ void det_phase(const K3Params &P, int q, int ndet, int lane) {
+    const int gl = lane & (GS - 1), gbase = lane & ~(GS - 1);
     const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
-    const int ndet = min(__ldg(P.n_items), P.item_cap);
-    const int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (P.nq - 1);
-    {
-        int *ctr = P.work + q * C_QSTRIDE;
-        int j = 0;
-        if (gl == 0) j = atom_inc(ctr);
-        bool have = false, done = false;
-        DetWork w{};
-        int area = 0, inter = 0, uarea = 0, uinter = 0;   // uarea / uinter: pixels this detection ADDS to the image's union
-        for (;;) {
-            if (!have && !done) {
-                const int item = q + P.nq * __shfl_sync(gmask, j, gbase);
-                if (item < ndet) {
-                    if (gl == 0) j = atom_inc(ctr);   // next item of the queue: in flight while this one is processed
-                    const int2 it = __ldg(P.items + item);
-                    det_begin(P, it.x, it.y, w);
-                    have = true;
-                } else {
-                    done = true;
-                }
+    int *ctr = P.work + q * C_QSTRIDE;
+    int j = 0;
+    if (gl == 0) j = atom_inc(ctr);
+    bool have = false, done = false;
+    DetWork w{};
+    int area = 0, inter = 0, uarea = 0, uinter = 0;   // uarea / uinter: pixels this detection ADDS to the image's union
+    for (;;) {
+        if (!have && !done) {
+            const int item = q + P.nq * __shfl_sync(gmask, j, gbase);
+            if (item < ndet) {
+                if (gl == 0) j = atom_inc(ctr);   // next item of the queue: in flight while this one is processed
+                const int2 it = __ldg(P.items + item);
+                det_begin(P, it.x, it.y, w);
+                have = true;
+            } else {
+                done = true;
             }
-            if (__all_sync(0xffffffffu, done)) break;
-            if (have) {
-                det_pass(P, w, gl, area, inter, uarea, uinter);
-                w.i += GS;
-                if (w.i >= w.i_end) {
-                    det_end(P, w, gmask, gl, area, inter, uarea, uinter);
-                    area = inter = uarea = uinter = 0;
-                    have = false;
-                }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (have) {
+            det_pass<GS>(P, w, gl, gmask, gbase, area, inter, uarea, uinter);
+            w.i += GS;
+            if (w.i >= w.i_end) {
+                det_end(P, w, gmask, gl, area, inter, uarea, uinter);
+                area = inter = uarea = uinter = 0;
+                have = false;
             }
         }
     }
+}
+
+template <int MINB, int GS>
+__global__ void __launch_bounds__(C_WARPS * 32, MINB) cells_kernel(const __grid_constant__ K3Params P) {
+    const int lane = threadIdx.x & 31;
+    const int ndet = min(__ldg(P.n_items), P.item_cap);
+    const int q = (blockIdx.x * C_WARPS + (threadIdx.x >> 5)) & (P.nq - 1);
+    // Some detection found no room in the logit pool (huge crop boxes / crop off): its items contract their corners from
+    // the prototypes, 32 channels x 9 loads per block; that path runs best with whole-warp items (measured: L1 layout with
+    // random DFL boxes, mask stage 519 us with whole warps, 685 us with groups of 16).
+    if (GS != 32 && __ldg(P.n_items + 1) != 0) det_phase<32>(P, q, ndet, lane);
+    else det_phase<GS>(P, q, ndet, lane);
     {
         const int total = P.B * P.m1_items;
         int *ctr = P.work + q * C_QSTRIDE + 1;

@@ -66,11 +66,15 @@ ev1.record()
 res = sweep.finish(num_images_bound=nbatches * B)
 ev2.record()
 torch.cuda.synchronize()
+tms = torch.tensor([ev0.elapsed_time(ev1), ev1.elapsed_time(ev2), ev0.elapsed_time(ev2)], dtype=torch.float64, device=dev)
+if world > 1:
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)   # device times are the maximum over the ranks
+tms = tms.tolist()
 if rank == 0:
     keys = ("n_images", "n_records", "map", "map_50", "map_75", "mar_100", "seg_f1", "seg_dice", "seg_iou", "uni_dice", "uni_iou")
     line = {k: res[k] for k in keys}
-    line.update(world=world, images=nbatches * B, batches_in_flight=args.depth, device_ms_batches_incl_generation=ev0.elapsed_time(ev1),
-                device_ms_reduce_gather_accumulate=ev1.elapsed_time(ev2), host_s=time.perf_counter() - t_host)
+    line.update(world=world, images=nbatches * B, batches_in_flight=args.depth, device_ms_batches_incl_generation=tms[0],
+                device_ms_reduce_gather_accumulate=tms[1], device_ms_total=tms[2], host_s=time.perf_counter() - t_host)
     print(json.dumps(line))
 if world > 1:
     dist.destroy_process_group()
