@@ -290,7 +290,14 @@ def merge_shards(hdr: torch.Tensor, records: torch.Tensor, group=None):
         send[:n_local] = records[:n_local]
     allrec = torch.empty(W * cap, REC_BYTES, dtype=torch.uint8, device=records.device)
     dist.all_gather_into_tensor(allrec, send.contiguous(), group=group)
-    merged = torch.cat([allrec[r * cap: r * cap + ns[r]] for r in range(W)]) if sum(ns) else allrec[:0]
+    if all(n == cap for n in ns):
+        return ns, allrec                      # equal shards: the gathered buffer is the merged list
+    # ragged shards: contiguous 8-byte copies (torch.cat on [n, 32] uint8 rows copies byte by byte: 13 ms for 52 MB on a B200)
+    merged = torch.empty(sum(ns), REC_BYTES, dtype=torch.uint8, device=records.device)
+    m64, a64, o = merged.view(torch.int64), allrec.view(torch.int64), 0
+    for r in range(W):
+        m64[o: o + ns[r]].copy_(a64[r * cap: r * cap + ns[r]])
+        o += ns[r]
     return ns, merged
 
 
@@ -348,14 +355,27 @@ class DeviceSweep:
                        "btpost_sweep_reset")
 
     @torch.no_grad()
-    def finish(self, group=None, num_images_bound: int | None = None) -> dict:
+    def finish(self, group=None, num_images_bound: int | None = None, timings: dict | None = None) -> dict:
         """End of the sweep: merge the shards (header all-reduce + record all-gather), run COCOeval.accumulate on the
-        device and summarize.  Every rank returns the same result."""
+        device and summarize.  Every rank returns the same result.  `timings` (developer aid): filled with the host time
+        of each stage in ms, with a device synchronisation after each."""
+        import time as _time
+        _t = [_time.perf_counter()]
+
+        def _mark(name):
+            if timings is not None:
+                torch.cuda.synchronize(self.device)
+                now = _time.perf_counter()
+                timings[name] = (now - _t[0]) * 1e3
+                _t[0] = now
+
         n_here = int(self.hdr[_lib.SWEEP_N_RECORDS])
+        _mark("read_count")
         if n_here > self.capacity:
             raise RuntimeError(f"DeviceSweep ring too small: {n_here} records offered, capacity {self.capacity}")
         hdr = self.hdr.clone()
         ns, rec = merge_shards(hdr, self.records, group)
+        _mark("merge_shards")
         n = int(sum(ns))
         if n and rec.data_ptr() == self.records.data_ptr():
             rec = rec.clone()                              # the sort reorders in place: keep the ring as it was
@@ -377,9 +397,11 @@ class DeviceSweep:
                 C.c_void_p(precision.data_ptr()), C.c_void_p(recall.data_ptr()), C.c_void_p(scratch.data_ptr()), C.c_size_t(sb.value),
                 C.c_void_p(st.cuda_stream))
         _lib.check(rc, "btpost_sweep_accumulate")
+        _mark("accumulate")
         pr, rcl = precision.cpu().numpy(), recall.cpu().numpy()
         h = hdr.cpu().numpy()
         res = summarize(pr, rcl, self.iou_thrs, self.max_dets)
+        _mark("summarize")
         ni = max(n_images, 1)
         u = _lib.SWEEP_USER
         tp, fp, fn, tn = [int(v) for v in h[u + 256: u + 260]]

@@ -46,6 +46,9 @@ del probe
 # host part of the generator for all of this rank's batches, done before the clock starts
 preps = [synth.prepare_batch_device(synth.SynthConfig(batch=B, img_size=args.img, seed=args.seed, image_offset=i * B), dev) for i in mine]
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()              # the ranks start the sweep together: a rank that began early would wait in the collectives
+    torch.cuda.synchronize()
 ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 t_host = time.perf_counter()
 ev0.record()
@@ -63,7 +66,8 @@ for n, (i, prep) in enumerate(zip(mine, preps)):
     pipe.replay(slot, image_offset=i * B)
 pipe.join()
 ev1.record()
-res = sweep.finish(num_images_bound=nbatches * B)
+tim = {} if os.environ.get("SWEEP_TIMINGS") else None
+res = sweep.finish(num_images_bound=nbatches * B, timings=tim)
 ev2.record()
 torch.cuda.synchronize()
 tms = torch.tensor([ev0.elapsed_time(ev1), ev1.elapsed_time(ev2), ev0.elapsed_time(ev2)], dtype=torch.float64, device=dev)
@@ -75,6 +79,8 @@ if rank == 0:
     line = {k: res[k] for k in keys}
     line.update(world=world, images=nbatches * B, batches_in_flight=args.depth, device_ms_batches_incl_generation=tms[0],
                 device_ms_reduce_gather_accumulate=tms[1], device_ms_total=tms[2], host_s=time.perf_counter() - t_host)
+    if tim is not None:
+        line["finish_stage_ms_rank0"] = tim
     print(json.dumps(line))
 if world > 1:
     dist.destroy_process_group()
