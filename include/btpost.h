@@ -83,7 +83,7 @@ typedef struct BtParams {
     double iou_thrs[BT_MAX_IOU_THRS]; /* float64(fp32 linspace(0.5,0.95,10))                  */
     int32_t image_offset;     /* global index of image 0 of this batch: written into the sweep records (BtIO.sweep)
                                  so that the AP order does not depend on the sharding                         */
-    int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = default (1024), 512 (small footprint: several batches in flight), 1024 */
+    int32_t nms_threads;      /* threads per image of the NMS kernel: 0 = default (1024), 512 (small footprint: several batches in flight), 256, 1024 */
     int32_t proto_dtype;      /* BT_PROTO_F32 (default) or BT_PROTO_BF16: dtype of `protos`; bf16 values are widened exactly, so the
                                  results equal those of the reference on `protos.float()` (it validates under bf16-mixed) */
     int32_t head_dtype;       /* BT_HEAD_F32 (default) or BT_HEAD_BF16: dtype of the L2 `head` / the L1 raw maps + coeffs (same exact widening) */
