@@ -192,9 +192,10 @@ enum { BT_MASKS_PACK = 1, BT_MASKS_CONTRACT = 2, BT_MASKS_CELLS = 4 };
 BTPOST_API int btpost_masks_parts(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream, int parts);
 
 /* Whole hot path for one batch: the three stages above, ordered on `stream`.  The GT-bit packing and the COCO
- * matching run on a helper stream of the library (one per device) that is forked from and joined back into `stream`
- * with events, so the call is still a unit of work on `stream` and capturable into a CUDA graph; concurrent
- * btpost_run calls on the same device from several host threads are not supported. */
+ * matching run on a helper stream of the library that is forked from and joined back into `stream` with events, so
+ * the call is still a unit of work on `stream` and capturable into a CUDA graph.  Every call borrows its (helper stream,
+ * events) set from a mutex-guarded per-device pool: concurrent calls from several host threads are safe as long as
+ * they use different workspaces / output buffers (two calls that share a workspace must be ordered by the caller). */
 BTPOST_API int btpost_run(const BtParams *p, const BtIO *io, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
