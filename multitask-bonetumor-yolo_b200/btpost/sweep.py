@@ -343,6 +343,20 @@ class DeviceSweep:
         self._md = (C.c_int32 * len(self.max_dets))(*self.max_dets)
         self.reset()
 
+    def reserve(self, total_records: int, world: int = 1):
+        """Optional: warm torch's caching allocator for `finish()` on a sweep of `total_records` records over `world`
+        ranks (the gathered record buffer, the merged copy and the accumulate scratch), so that the end of the sweep does
+        not pay cudaMalloc calls while the GPU waits."""
+        sb = C.c_size_t()
+        _lib.check(self.lib.btpost_sweep_accumulate_bytes(C.c_int64(int(total_records)), C.byref(sb)), "btpost_sweep_accumulate_bytes")
+        per = -(-int(total_records) // max(world, 1))
+        keep = [torch.empty(sb.value, dtype=torch.uint8, device=self.device),
+                torch.empty(max(world * per, 1), REC_BYTES, dtype=torch.uint8, device=self.device),
+                torch.empty(max(int(total_records), 1), REC_BYTES, dtype=torch.uint8, device=self.device),
+                torch.empty(self.T, 101, self.nc, 4, len(self.max_dets), dtype=torch.float64, device=self.device),
+                torch.empty(self.T, self.nc, 4, len(self.max_dets), dtype=torch.float64, device=self.device)]
+        del keep   # back to the allocator's cache
+
     def counters(self):
         """cm / seg_cnt4 / uni_cnt4 views INSIDE the header: hand them to PostProcessor / Pipeline as accumulators and
         they are merged by the same all-reduce."""

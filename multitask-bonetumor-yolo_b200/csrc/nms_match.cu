@@ -55,6 +55,9 @@ extern "C" __attribute__((visibility("default"))) int btpost_debug_phase_cycles(
 namespace bt {
 
 constexpr int NMS_CHUNK = 64;
+#ifndef A_SUBS_WIDE
+#define A_SUBS_WIDE 8
+#endif
 constexpr int SORT_REG_MAX = 16384;  // keys sorted in registers (16 per thread) up to this many
 constexpr int SORT_SMALL_MAX = 4096; // same for the 512-thread variant (8 per thread): its shared memory stays below 80 KB
 constexpr int GM_THREADS = 256;      // match_kernel block
@@ -339,6 +342,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = P.max_det;
     constexpr int WIN = K2_TAIL_WIN;
+    // phase A: threads per candidate that share the walk over the cells under its box (the walks are chains of dependent
+    // shared-memory loads: more, shorter chains as long as the CTA has the threads)
+    constexpr int A_SUBS = K2_THREADS >= 512 ? A_SUBS_WIDE : 4;
 
     // ---- shared-memory carve-up (the sort's exchange buffer / sorted-index list overlays it)
     uint32_t *s_sidx = reinterpret_cast<uint32_t *>(smem_raw);
@@ -472,8 +478,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
             const long long _a0 = clock64();
 #endif
             if (P.centre_cull) {
-                if (tid < 4 * NMS_CHUNK) {
-                    const int ci = tid >> 2, sub = tid & 3;
+                if (tid < A_SUBS * NMS_CHUNK) {
+                    const int ci = tid / A_SUBS, sub = tid % A_SUBS;
                     bool f = false;
                     if (ci < n_in) {
                         const float4 bj = s_sbox[c0 + ci];
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                         const int lj = s_slabel[c0 + ci];
                         const int pc = s_scell[c0 + ci];
                         const int gx0 = pc & 15, gy0 = (pc >> 4) & 15, ncx = (pc >> 8) & 31, ncy = (pc >> 13) & 31;
-                        int qx = sub, qy = 0;   // cells sub, sub + 4, ... in row-major order (ncx >= 1)
+                        int qx = sub, qy = 0;   // cells sub, sub + A_SUBS, ... in row-major order (ncx >= 1)
                         while (qx >= ncx) { qx -= ncx; ++qy; }
                         while (qy < ncy && !f) {
                             // lists are in keep order: the strongest box of a cluster comes first and usually settles it
@@ -496,12 +502,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                                 f = suppresses(kb, __int_as_float(km.x), km.y, bj, aj, lj, P.thr_up, P.early_out, P.class_mode, 1,
                                                cj.x, cj.y, P.fast);
                             }
-                            qx += 4;
+                            qx += A_SUBS;
                             while (qx >= ncx) { qx -= ncx; ++qy; }
                         }
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, f);
-                    if ((lane & 3) == 0 && ((m >> lane) & 0xfu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
+                    if ((lane & (A_SUBS - 1)) == 0 && ((m >> lane) & ((1u << A_SUBS) - 1u))) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
                 }
             } else {
                 for (int ci = tid >> 4; ci < NMS_CHUNK; ci += K2_THREADS >> 4) {   // warp-uniform trip count

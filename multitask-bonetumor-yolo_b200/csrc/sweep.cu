@@ -64,19 +64,21 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint4 *__r
     }
 }
 
-// exclusive scan of `len` counters, one block; 4 counters per thread and step (len is a multiple of 4: 256 digits)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned *__restrict__ h, long long len) {
+// Scan of the [256][nw] counters in two levels: block d turns the nw counters of digit d into exclusive prefixes inside
+// the digit and leaves the digit's total in dtot[d]; the scatter kernel adds the digit bases (a 256-element scan every
+// block does for itself).  (One block scanning all 256 * nw counters took 0.2-0.3 ms per pass at 1.6 M records: most of
+// the accumulate.)
+__global__ void __launch_bounds__(1024) radix_scan_digit_kernel(unsigned *__restrict__ h, int nw, unsigned *__restrict__ dtot) {
     __shared__ unsigned s_w[32];
     __shared__ unsigned s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned *row = h + (size_t)blockIdx.x * nw;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (long long base = 0; base < len; base += 4096) {
-        const long long i = base + 4 * tid;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (i < len) v = *reinterpret_cast<uint4 *>(h + i);
-        const unsigned s1 = v.x, s2 = s1 + v.y, s3 = s2 + v.z, tot = s3 + v.w;
-        unsigned incl = tot;
+    for (int base = 0; base < nw; base += 1024) {
+        const int i = base + tid;
+        const unsigned v = i < nw ? row[i] : 0u;
+        unsigned incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned u = __shfl_up_sync(0xffffffffu, incl, d);
@@ -95,21 +97,38 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned *__restrict__
         }
         __syncthreads();
         const unsigned carry = s_carry;
-        const unsigned excl = carry + s_w[wid] + incl - tot;
-        if (i < len) *reinterpret_cast<uint4 *>(h + i) = make_uint4(excl, excl + s1, excl + s2, excl + s3);
+        if (i < nw) row[i] = carry + s_w[wid] + incl - v;
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_w[31] + incl;
         __syncthreads();
     }
+    if (tid == 0) dtot[blockIdx.x] = s_carry;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint4 *__restrict__ rec, uint4 *__restrict__ out, long long n,
-                                                                   int field, int nw, const unsigned *__restrict__ ghist) {
+                                                                   int field, int nw, const unsigned *__restrict__ ghist,
+                                                                   const unsigned *__restrict__ dtot) {
     __shared__ unsigned s_off[RS_WARPS][256];
+    __shared__ unsigned s_base[256], s_wt[RS_WARPS];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int w = blockIdx.x * RS_WARPS + wl;
+    {   // digit bases: exclusive scan of the 256 digit totals (RS_THREADS == 256: one digit per thread)
+        const unsigned v = dtot[threadIdx.x];
+        unsigned incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) s_wt[wl] = incl;
+        __syncthreads();
+        unsigned before = 0;
+        for (int q = 0; q < wl; ++q) before += s_wt[q];
+        s_base[threadIdx.x] = before + incl - v;
+        __syncthreads();
+    }
     if (w >= nw) return;
-    for (int i = lane; i < 256; i += 32) s_off[wl][i] = ghist[(size_t)i * nw + w];
+    for (int i = lane; i < 256; i += 32) s_off[wl][i] = ghist[(size_t)i * nw + w] + s_base[i];
     __syncwarp();
     const long long base = (long long)w * RS_WTILE;
     const unsigned lt = (1u << lane) - 1u;
@@ -284,6 +303,7 @@ __global__ void __launch_bounds__(ACC_THREADS) acc_final_kernel(const AccParams 
 struct AccScratch {
     uint4 *tmp;           // second record buffer of the radix sort
     unsigned *ghist;      // [256][warps]
+    unsigned *dtot;       // [256] records per digit
     long long *cls_start;
     uint2 *sums, *totals;
     u64 *table;
@@ -302,6 +322,7 @@ static AccScratch acc_carve(long long n, void *base) {
     const long long chunks = (n + ACC_CHUNK - 1) / ACC_CHUNK + BT_MAX_CLASSES;
     s.tmp = reinterpret_cast<uint4 *>(take((size_t)(n > 0 ? n : 1) * sizeof(BtSweepRecord)));
     s.ghist = reinterpret_cast<unsigned *>(take((size_t)256 * (nw > 0 ? nw : 1) * sizeof(unsigned)));
+    s.dtot = reinterpret_cast<unsigned *>(take(256 * sizeof(unsigned)));
     s.cls_start = reinterpret_cast<long long *>(take((BT_MAX_CLASSES + 1) * sizeof(long long)));
     s.sums = reinterpret_cast<uint2 *>(take((size_t)chunks * ACC_MAX_COMBOS * sizeof(uint2)));
     s.totals = reinterpret_cast<uint2 *>(take((size_t)BT_MAX_CLASSES * ACC_MAX_COMBOS * sizeof(uint2)));
@@ -364,8 +385,8 @@ int btpost_sweep_accumulate(void *records, int64_t n_records, const int64_t *npi
         for (int f = 0; f < 11; ++f) {
             if (!need[f]) continue;
             radix_hist_kernel<<<blocks, RS_THREADS, 0, s>>>(bufs[cur], n, f, nw, sc.ghist);
-            radix_scan_kernel<<<1, 1024, 0, s>>>(sc.ghist, 256ll * nw);
-            radix_scatter_kernel<<<blocks, RS_THREADS, 0, s>>>(bufs[cur], bufs[cur ^ 1], n, f, nw, sc.ghist);
+            radix_scan_digit_kernel<<<256, 1024, 0, s>>>(sc.ghist, nw, sc.dtot);
+            radix_scatter_kernel<<<blocks, RS_THREADS, 0, s>>>(bufs[cur], bufs[cur ^ 1], n, f, nw, sc.ghist, sc.dtot);
             cur ^= 1;
         }
         if (cur == 1 && cudaMemcpyAsync(records, sc.tmp, (size_t)n * sizeof(BtSweepRecord), cudaMemcpyDeviceToDevice, s) != cudaSuccess)

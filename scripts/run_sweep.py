@@ -43,6 +43,7 @@ sweep = DeviceSweep(cfg.nc, map_iou_thresholds(), (1, 10, 100), capacity=max(len
 probe = synth.make_batch_device(synth.SynthConfig(batch=B, img_size=args.img, seed=args.seed), dev)
 pipe = Pipeline(cfg, dev, depth=args.depth, proj_weight=probe["proj_weight"], proj_bias=probe["proj_bias"], sweep=sweep)
 del probe
+sweep.reserve(nbatches * B * K, world)   # the end-of-sweep buffers come out of the allocator's cache
 # host part of the generator for all of this rank's batches, done before the clock starts
 preps = [synth.prepare_batch_device(synth.SynthConfig(batch=B, img_size=args.img, seed=args.seed, image_offset=i * B), dev) for i in mine]
 torch.cuda.synchronize()
