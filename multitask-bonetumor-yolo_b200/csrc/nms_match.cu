@@ -147,6 +147,7 @@ struct K2Params {
     int32_t *acc, *inst_area, *inst_inter;
     double *seg_prob_sum;
     int region0_bytes;    // shared region 0: list of candidate indices in NMS order
+    int bucket_max;       // longest list the bucket rank sort takes (shared memory behind region 0 holds its pairs)
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
     int32_t *scr_off; unsigned long long *pool_used; long long pool_cap;   // logit-pool plan of the mask stage
     int2 *items; int32_t *n_items; int item_cap;                            // work items of cells_kernel
@@ -333,6 +334,94 @@ __device__ __forceinline__ void radix_sort_to_smem(const float *cscore, int M, u
     }
 }
 
+// Bucket rank sort (lists of <= P.bucket_max candidates; the default path).  The four radix passes above cost 31 k cycles
+// per image at ~930 candidates (r02c phase counters: a third of the kernel) in barriers and dependent shuffle chains;
+// this is one pass: (1) min / max of the 32-bit descending keys, (2) a MONOTONE map key -> one of BUCKETS buckets
+// (float scale of key - min: conversion, product and truncation are all non-decreasing, equal keys share a bucket),
+// histogram with shared-memory atomics, (3) exclusive scan of the counters, (4) scatter of the 64-bit (key, index)
+// pairs into their bucket's range in any order, (5) every element counts the pairs of its own bucket that compare
+// below it: bucket start + that count is its exact rank in the (key, index) order, i.e. the stable order
+// ("ties -> lower index").  The result does not depend on the bucket map or on the order of the atomics.  A list
+// with a bucket of more than BUCKET_OCC_MAX entries (hundreds of equal scores) returns false without having written
+// s_sidx and the caller takes the radix / bitonic path.  Every thread of the block must call this.
+// Shared memory: s_sidx = [0, 4 M) of region 0; pairs and counters overlay the window area behind region 0.
+constexpr int BUCKETS = 2048;
+constexpr int BUCKET_OCC_MAX = 256;
+template <int NT>
+__device__ __forceinline__ bool bucket_sort_to_smem(const float *cscore, int M, unsigned char *smem_raw, int region0_bytes,
+                                                    uint32_t *s_sidx) {
+    constexpr int NW = NT / 32, PER = BUCKETS / NT;
+    __shared__ unsigned s_kmin, s_kmax, s_occ;
+    __shared__ int s_bsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Mp = (M + 31) & ~31;
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw + region0_bytes);   // [Mp]
+    int *start = reinterpret_cast<int *>(buf + Mp);                                                 // [BUCKETS]
+    int *cur = start + BUCKETS;                                                                     // [BUCKETS]
+    if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_occ = 0u; }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) start[tid * PER + j] = 0;
+    __syncthreads();
+    {
+        unsigned lo = 0xffffffffu, hi = 0u;
+        for (int i = tid; i < M; i += NT) {
+            const unsigned k = desc_key(__ldg(cscore + i));
+            lo = min(lo, k); hi = max(hi, k);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { atomicMin(&s_kmin, lo); atomicMax(&s_kmax, hi); }
+    }
+    __syncthreads();
+    const unsigned kmin = s_kmin;
+    const float scale = __fdiv_rn((float)BUCKETS, __fadd_rn(__uint2float_rn(s_kmax - kmin), 1.0f));
+    auto bucket_of = [&](unsigned k) { return min(__float2int_rz(__fmul_rn(__uint2float_rn(k - kmin), scale)), BUCKETS - 1); };
+    for (int i = tid; i < M; i += NT) atomicAdd(&start[bucket_of(desc_key(__ldg(cscore + i)))], 1);
+    __syncthreads();
+    {   // exclusive scan of the counters, PER consecutive ones per thread
+        int v[PER], sum = 0, occ = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { v[j] = start[tid * PER + j]; occ = max(occ, v[j]); sum += v[j]; }
+        int incl = sum;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lane >= dd) incl += u;
+        }
+        occ = __reduce_max_sync(0xffffffffu, occ);
+        if (lane == 31) s_bsum[wid] = incl;
+        if (lane == 0 && occ > BUCKET_OCC_MAX) atomicMax(&s_occ, (unsigned)occ);
+        __syncthreads();
+        const int wv = lane < NW ? s_bsum[lane] : 0;
+        int winc = wv;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, winc, dd);
+            if (lane >= dd) winc += u;
+        }
+        int run = __shfl_sync(0xffffffffu, winc - wv, wid) + incl - sum;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { start[tid * PER + j] = run; cur[tid * PER + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+    if (s_occ) return false;   // block-uniform
+    for (int i = tid; i < M; i += NT) {
+        const unsigned k = desc_key(__ldg(cscore + i));
+        buf[atomicAdd(&cur[bucket_of(k)], 1)] = ((unsigned long long)k << 32) | (unsigned)i;
+    }
+    __syncthreads();
+    for (int p = tid; p < M; p += NT) {
+        const unsigned long long e = buf[p];
+        const int bk = bucket_of((unsigned)(e >> 32));
+        const int s0 = start[bk], s1 = cur[bk];   // cur has advanced to the end of the bucket
+        int rank = s0;
+        for (int q = s0; q < s1; ++q) rank += buf[q] < e;
+        s_sidx[rank] = (uint32_t)e;
+    }
+    __syncthreads();
+    return true;
+}
+
 // =================================================================================================
 // fused NMS kernel
 // =================================================================================================
@@ -392,7 +481,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     const unsigned long long *gkeys = nullptr;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        if (M_all <= RADIX_MAX) radix_sort_to_smem<K2_THREADS>(cscore, M_all, smem_raw, s_sidx);
+        if (M_all <= P.bucket_max && bucket_sort_to_smem<K2_THREADS>(cscore, M_all, smem_raw, P.region0_bytes, s_sidx)) {
+        } else if (M_all <= RADIX_MAX) radix_sort_to_smem<K2_THREADS>(cscore, M_all, smem_raw, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 256) sort_to_smem<1>(cscore, M_all, 256, s_x, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 512) sort_to_smem<2>(cscore, M_all, 256, s_x, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 1024) sort_to_smem<4>(cscore, M_all, 256, s_x, s_sidx);
@@ -1056,6 +1146,19 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
         const size_t mp = (size_t)(P.cap < RADIX_MAX ? (P.cap + 31) / 32 * 32 : RADIX_MAX);
         const size_t need = 16 * mp + 1024 * (size_t)(nt / 32);
         if (smem_a < need) smem_a = need;
+    }
+    {   // bucket rank sort: (key, index) pairs + two counter arrays behind region 0.  The 1024-thread variant owns its SM
+        // anyway and grows its shared memory to take whole lists up to the register-sort limit; the smaller variants keep
+        // their footprint (two images per SM) and take what fits.
+        const size_t cap32 = (size_t)(P.cap + 31) / 32 * 32, fixed = region0 + 8 * (size_t)BUCKETS + 64;
+        size_t want = cap32 < (size_t)sort_slots ? cap32 : (size_t)sort_slots;
+        if (nt == 1024) {
+            while (want > 0 && fixed + 8 * want > 200 * 1024) want -= 32;
+            if (smem_a < fixed + 8 * want) smem_a = fixed + 8 * want;
+        } else {
+            while (want > 0 && fixed + 8 * want > smem_a) want -= 32;
+        }
+        P.bucket_max = dbg_env_int("BTPOST_NMS_BUCKET", 1) ? (int)want : 0;
     }
     if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
     // match_kernel: COCO tables

@@ -53,13 +53,13 @@ def decoded(head_img, conf, S):
 _PP = {}
 
 
-def run_det(heads, conf=0.05, iou=0.6, max_det=300, S=64, class_mode=0, max_cand=0):
+def run_det(heads, conf=0.05, iou=0.6, max_det=300, S=64, class_mode=0, max_cand=0, nms_threads=0):
     heads = np.ascontiguousarray(heads, np.float32)
     B, _, N = heads.shape
-    key = (B, N, conf, iou, max_det, S, class_mode, max_cand)
+    key = (B, N, conf, iou, max_det, S, class_mode, max_cand, nms_threads)
     if key not in _PP:
         cfg = PostConfig(batch=B, img_size=S, num_anchors=N, conf_thres=conf, iou_thres=iou, max_det=max_det, class_mode=class_mode,
-                         max_cand=max_cand, with_coco=False)
+                         max_cand=max_cand, with_coco=False, nms_threads=nms_threads)
         pp = PostProcessor(cfg, DEV)
         pp._dummy = (torch.zeros(B, NM, S // 4, S // 4, device=DEV), torch.zeros(B, 1, S, S, dtype=torch.uint8, device=DEV),
                      torch.zeros(NM, device=DEV))
@@ -80,8 +80,8 @@ def tv_keep(head_img, conf, iou, max_det, S):
     return torchvision.ops.nms(torch.from_numpy(b), torch.from_numpy(s), iou)[:max_det].numpy()
 
 
-def check_vs_torchvision(heads, conf, iou, max_det, S):
-    got = run_det(heads, conf, iou, max_det, S)
+def check_vs_torchvision(heads, conf, iou, max_det, S, nms_threads=0):
+    got = run_det(heads, conf, iou, max_det, S, nms_threads=nms_threads)
     for b in range(heads.shape[0]):
         want = tv_keep(heads[b], conf, iou, max_det, S)
         k = int(got["det_count"][b])
@@ -239,3 +239,40 @@ def test_max_cand_is_top_k_by_score_like_ultralytics(max_cand):
         want = top[keep].numpy()                              # indices into the filtered (anchor-ordered) list
         k = int(got["det_count"][b])
         np.testing.assert_array_equal(got["det_keep"][b, :k], want)
+
+
+@pytest.mark.parametrize("nms_threads", [0, 512, 256])
+@pytest.mark.parametrize("n", [700, 1024, 3000, 4096, 6000, 8400])
+def test_sort_paths_against_torchvision(n, nms_threads):
+    """The order the sweep consumes the candidates in, on every sort path of the kernel (bucket rank sort; radix /
+    register / global bitonic fallbacks) and in each thread variant.  Image 0: every score equal (one bucket holds the whole
+    list: the bucket sort hands over to the fallback, ties -> lower index decides everything); image 1: two score values;
+    image 2: continuous scores in a narrow band (the bucket map stretches min..max); image 3: quantised clusters (buckets
+    of dozens of ties); image 4: continuous scores with a block of 300 duplicates."""
+    S = 640
+    rng = np.random.default_rng(77 + n)
+    heads = []
+    for kind in range(5):
+        h = fuzz_heads(5000 + n + kind, n, S)
+        sc = h[4:4 + NC]
+        live = sc.max(0) > 0.05
+        lab = sc.argmax(0)
+        if kind == 0:
+            new = np.full(n, 0.5, np.float32)
+        elif kind == 1:
+            new = np.where(rng.uniform(size=n) < 0.5, np.float32(0.25), np.float32(0.75)).astype(np.float32)
+        elif kind == 2:
+            new = (0.3 + 1e-4 * rng.uniform(size=n)).astype(np.float32)
+        elif kind == 3:
+            new = sc.max(0)
+        else:
+            new = rng.uniform(0.06, 1.0, n).astype(np.float32)
+            d = rng.integers(0, n, 300)
+            new[d] = new[d[0]]
+        if kind != 3:
+            sc[:] = -1.0
+            sc[lab, np.arange(n)] = new
+            if kind in (0, 1):
+                sc[:, ~live] = -1.0          # keep some anchors below the threshold so list positions != anchor indices
+        heads.append(h)
+    check_vs_torchvision(np.stack(heads), 0.05, 0.6, 300, S, nms_threads=nms_threads)
