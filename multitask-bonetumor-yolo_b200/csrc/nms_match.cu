@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
     __shared__ unsigned int s_row32[NMS_CHUNK * 2];
     __shared__ int s_cellhead[MAX_CELLS], s_celltail[MAX_CELLS];
     __shared__ unsigned int s_supA[2];
+    __shared__ unsigned char s_und[NMS_CHUNK];
     __shared__ int s_anyrow;
     __shared__ unsigned short s_pair[NMS_CHUNK * (NMS_CHUNK - 1) / 2];   // (i << 8) | j for every pair i < j of a chunk
     __shared__ unsigned long long s_keepm;
@@ -564,9 +565,6 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
             // (A) chunk vs kept boxes.  Centre-cull mode: only kept boxes whose centre lies in a cell under
             // the candidate's box can suppress it; 4 threads per candidate walk those cells (8 warps: the
             // phase is issue-bound, r01k).  Otherwise 16 threads per candidate stride over all kept boxes.
-#ifdef BT_PHASE_TIMING
-            const long long _a0 = clock64();
-#endif
             if (P.centre_cull) {
                 if (tid < A_SUBS * NMS_CHUNK) {
                     const int ci = tid / A_SUBS, sub = tid % A_SUBS;
@@ -617,14 +615,6 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                     if ((lane & 15) == 0 && ((m >> lane) & 0xffffu)) atomicOr(&s_supA[ci >> 5], 1u << (ci & 31));
                 }
             }
-#ifdef BT_PHASE_TIMING
-            {
-                const unsigned dt = (unsigned)(clock64() - _a0);
-                const unsigned mx = __reduce_max_sync(0xffffffffu, dt);
-                if (lane == 0 && wid < 8) { atomicAdd(&g_phase_cycles[1][12], (unsigned long long)mx); atomicAdd(&g_phase_cycles[1][13], 1ull); }
-                if (lane == 0 && wid >= 8) { atomicAdd(&g_phase_cycles[1][14], (unsigned long long)mx); }
-            }
-#endif
             __syncthreads();
             BT_PHASE_MARK(1, 8);   // chunk: A
             // (B) "who suppresses me" rows of the candidates A left undecided, against the undecided
@@ -633,9 +623,18 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
             // table of the 2016 pairs; the exact IoU runs only for pairs that pass the cheap necessary test.
             const unsigned long long valid = (n_in == 64) ? ~0ull : ((1ull << n_in) - 1ull);
             const unsigned long long und0 = valid & ~(((unsigned long long)s_supA[1] << 32) | s_supA[0]);
-            for (int pq = tid; pq < NMS_CHUNK * (NMS_CHUNK - 1) / 2; pq += K2_THREADS) {
-                const int pr = s_pair[pq], io = pr >> 8, jo = pr & 255;
-                if (!((und0 >> io) & (und0 >> jo) & 1ull)) continue;
+            // Only the pairs of UNDECIDED candidates are enumerated: every warp compacts the undecided set into the same
+            // 64-byte table (identical values from every warp: no block barrier), pair number pq of the triangular table
+            // then names two table positions.  Usually one trip per thread instead of 2016 / threads.
+            const int n_und = __popcll(und0);
+            {
+                const unsigned ulo = (unsigned)und0, uhi = (unsigned)(und0 >> 32), ltm = (1u << lane) - 1u;
+                if ((ulo >> lane) & 1u) s_und[__popc(ulo & ltm)] = (unsigned char)lane;
+                if ((uhi >> lane) & 1u) s_und[__popc(ulo) + __popc(uhi & ltm)] = (unsigned char)(lane + 32);
+                __syncwarp();
+            }
+            for (int pq = tid; pq < n_und * (n_und - 1) / 2; pq += K2_THREADS) {
+                const int pr = s_pair[pq], io = s_und[pr >> 8], jo = s_und[pr & 255];
                 const int i = c0 + io, j = c0 + jo;
                 const float4 bi = s_sbox[i], bj = s_sbox[j];
                 const float2 cj = s_sctr[j];

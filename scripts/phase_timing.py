@@ -2,7 +2,7 @@
 import ctypes as C, os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
-os.environ["BTPOST_LIB"] = str(ROOT / "multitask-bonetumor-yolo_b200" / "btpost" / "libbtpost_dbg.so")
+os.environ.setdefault("BTPOST_LIB", str(ROOT / "multitask-bonetumor-yolo_b200" / "btpost" / "libbtpost_dbg.so"))
 sys.path[:0] = [str(ROOT), str(ROOT / "multitask-bonetumor-yolo_b200")]
 import numpy as np, torch
 from btpost import PostConfig, PostProcessor, synth, _lib
@@ -21,7 +21,7 @@ torch.cuda.synchronize(); L.btpost_debug_phase_cycles(buf, 1)
 n = 10
 for _ in range(n): pp.run(*args)
 torch.cuda.synchronize(); L.btpost_debug_phase_cycles(buf, 1)
-names = {1: {0: "sort", 1: "stage window", 3: "chunks (tail mark)", 8: "chunk A", 12: "A: sum of per-warp max (warps 0-7)", 13: "A: warp-chunks counted", 14: "A: sum per-warp max (idle warps)", 11: "chunk B", 9: "chunk C", 10: "chunk insert", 6: "package", 7: "COCO match (other kernel)"}}
+names = {1: {0: "sort", 1: "stage window", 3: "chunks (tail mark)", 8: "chunk A", 11: "chunk B", 9: "chunk C", 10: "chunk insert", 6: "package", 7: "COCO match (other kernel)"}}
 for k, nb in ((1, B),):   # the mask stage is four plain kernels now: time them with bench.py / ncu
     tot = sum(buf[k * 16 + i] for i in range(16))
     print(f"kernel {k}: total cycles/launch {tot / n:.0f}  ({tot / n / nb:.0f} per image, thread 0 of every CTA)")

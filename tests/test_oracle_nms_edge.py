@@ -13,7 +13,7 @@ from test_gpu_nms_edge import (test_fuzz_against_torchvision, test_fuzz_class_aw
                                test_k5_k6_empty_input_and_output_format, test_max_cand_is_top_k_by_score_like_ultralytics)
 
 
-def oracle_run_det(heads, conf=0.05, iou=0.6, max_det=300, S=64, class_mode=0, max_cand=0):
+def oracle_run_det(heads, conf=0.05, iou=0.6, max_det=300, S=64, class_mode=0, max_cand=0, nms_threads=0):
     heads = np.ascontiguousarray(heads, np.float32)
     B, _, N = heads.shape
     out = dict(det_count=np.zeros(B, np.int32), det_keep=np.full((B, max_det), -1, np.int64), dets=np.zeros((B, max_det, 6), np.float32),
