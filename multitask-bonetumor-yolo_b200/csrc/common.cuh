@@ -63,7 +63,7 @@ struct Workspace {
     float *cand_score;    // [B, cap]
     int32_t *cand_label;  // [B, cap]
     int32_t *cand_anchor; // [B, cap]
-    unsigned long long *sort_keys;  // [B, cap_pow2] (only used when the list exceeds the register sort)
+    unsigned long long *sort_keys;  // [B, sort_stride_u64(cap)] (lists that do not fit the shared-memory sorts)
     int32_t *acc;         // [B, 8] per-image int counters: seg inter,P,G ; uni inter,P,G
     short4 *det_region;   // [B, K] crop region of each kept detection at prototype resolution (r_lo, r_hi, c_lo, c_hi)
     int32_t *scr_off;     // [B, K] offset (floats) of the detection's crop-box logits in `pool`; -1: none (invalid / pool full)
@@ -123,6 +123,14 @@ static inline int next_pow2(int v) {
     return r;
 }
 
+// Per-image slice of Workspace.sort_keys in 8-byte words: the bitonic network's padded key array, or the bucket sort's
+// (key, index) pairs + 32-bit index list of a long candidate list (12 bytes per candidate, rounded up to 32 candidates).
+static inline size_t sort_stride_u64(size_t cap) {
+    const size_t pow2 = (size_t)next_pow2((int)cap), pairs = (cap + 31) / 32 * 32;
+    const size_t bucket = pairs + (pairs + 1) / 2;
+    return pow2 > bucket ? pow2 : bucket;
+}
+
 // Sorted candidates are consumed by the NMS kernel in shared-memory windows of this many.
 constexpr int K2_TAIL_WIN = 1024;
 
@@ -140,7 +148,7 @@ static inline Workspace carve(const BtParams *p, void *base) {
     w.cand_score = reinterpret_cast<float *>(take(B * cap * sizeof(float)));
     w.cand_label = reinterpret_cast<int32_t *>(take(B * cap * sizeof(int32_t)));
     w.cand_anchor = reinterpret_cast<int32_t *>(take(B * cap * sizeof(int32_t)));
-    w.sort_keys = reinterpret_cast<unsigned long long *>(take(B * (size_t)next_pow2((int)cap) * 8));
+    w.sort_keys = reinterpret_cast<unsigned long long *>(take(B * sort_stride_u64(cap) * 8));
     w.acc = reinterpret_cast<int32_t *>(take(B * 8 * sizeof(int32_t)));
     w.det_region = reinterpret_cast<short4 *>(take(B * (size_t)p->max_det * sizeof(short4)));
     const size_t nby = (size_t)mask_blocks(p->proto_h), nbx = (size_t)mask_blocks(p->proto_w);

@@ -147,6 +147,8 @@ struct K2Params {
     int32_t *acc, *inst_area, *inst_inter;
     double *seg_prob_sum;
     int region0_bytes;    // shared region 0: list of candidate indices in NMS order
+    int bucket_global;    // longer lists: bucket rank sort with its pairs in the workspace (developer switch, default on)
+    size_t sort_stride;   // u64 words per image of sort_keys
     int bucket_max;       // longest list the bucket rank sort takes (shared memory behind region 0 holds its pairs)
     int crop, PW, PH; float rx, ry; short4 *det_region;   // crop regions for the mask kernel
     int32_t *scr_off; unsigned long long *pool_used; long long pool_cap;   // logit-pool plan of the mask stage
@@ -344,19 +346,18 @@ __device__ __forceinline__ void radix_sort_to_smem(const float *cscore, int M, u
 // ("ties -> lower index").  The result does not depend on the bucket map or on the order of the atomics.  A list
 // with a bucket of more than BUCKET_OCC_MAX entries (hundreds of equal scores) returns false without having written
 // s_sidx and the caller takes the radix / bitonic path.  Every thread of the block must call this.
-// Shared memory: s_sidx = [0, 4 M) of region 0; pairs and counters overlay the window area behind region 0.
+// Lists that fit (<= P.bucket_max): the index list is [0, 4 M) of shared region 0, pairs and counters overlay the window
+// area behind it.  Longer lists (GLOBAL): pairs and the index list live in the image's slice of the workspace sort
+// buffer, only the counters are in shared memory -- one pass over the L2 instead of the ~100 barrier-separated stages
+// of a bitonic network in global memory.
 constexpr int BUCKETS = 2048;
 constexpr int BUCKET_OCC_MAX = 256;
-template <int NT>
-__device__ __forceinline__ bool bucket_sort_to_smem(const float *cscore, int M, unsigned char *smem_raw, int region0_bytes,
-                                                    uint32_t *s_sidx) {
+template <int NT, bool GLOBAL>
+__device__ __forceinline__ bool bucket_sort(const float *cscore, int M, unsigned long long *buf, int *start, uint32_t *out) {
     constexpr int NW = NT / 32, PER = BUCKETS / NT;
     __shared__ unsigned s_kmin, s_kmax, s_occ;
     __shared__ int s_bsum[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int Mp = (M + 31) & ~31;
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw + region0_bytes);   // [Mp]
-    int *start = reinterpret_cast<int *>(buf + Mp);                                                 // [BUCKETS]
     int *cur = start + BUCKETS;                                                                     // [BUCKETS]
     if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_occ = 0u; }
 #pragma unroll
@@ -411,12 +412,13 @@ __device__ __forceinline__ bool bucket_sort_to_smem(const float *cscore, int M, 
     }
     __syncthreads();
     for (int p = tid; p < M; p += NT) {
-        const unsigned long long e = buf[p];
+        // GLOBAL: the pairs were written by other threads of this CTA before the barrier; read them from the L2
+        const unsigned long long e = GLOBAL ? __ldcg(buf + p) : buf[p];
         const int bk = bucket_of((unsigned)(e >> 32));
         const int s0 = start[bk], s1 = cur[bk];   // cur has advanced to the end of the bucket
         int rank = s0;
-        for (int q = s0; q < s1; ++q) rank += buf[q] < e;
-        s_sidx[rank] = (uint32_t)e;
+        for (int q = s0; q < s1; ++q) rank += (GLOBAL ? __ldcg(buf + q) : buf[q]) < e;
+        out[rank] = (uint32_t)e;
     }
     __syncthreads();
     return true;
@@ -480,9 +482,19 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
 
     // ---- 1. stable descending sort: key = (descending score key << 32) | candidate index
     const unsigned long long *gkeys = nullptr;
+    const uint32_t *gidx = nullptr;   // long lists sorted by the bucket sort: index list in the workspace
+    bool sorted = false;
     {
         unsigned long long *s_x = reinterpret_cast<unsigned long long *>(smem_raw);
-        if (M_all <= P.bucket_max && bucket_sort_to_smem<K2_THREADS>(cscore, M_all, smem_raw, P.region0_bytes, s_sidx)) {
+        const int Mp_all = (M_all + 31) & ~31;
+        unsigned long long *gslice = P.sort_keys + (size_t)b * P.sort_stride;
+        unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(smem_raw + P.region0_bytes);
+        if (M_all <= P.bucket_max) sorted = bucket_sort<K2_THREADS, false>(cscore, M_all, sbuf, reinterpret_cast<int *>(sbuf + Mp_all), s_sidx);
+        else if (P.bucket_global) {
+            sorted = bucket_sort<K2_THREADS, true>(cscore, M_all, gslice, reinterpret_cast<int *>(sbuf), reinterpret_cast<uint32_t *>(gslice + Mp_all));
+            if (sorted) gidx = reinterpret_cast<const uint32_t *>(gslice + Mp_all);
+        }
+        if (sorted) {
         } else if (M_all <= RADIX_MAX) radix_sort_to_smem<K2_THREADS>(cscore, M_all, smem_raw, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 256) sort_to_smem<1>(cscore, M_all, 256, s_x, s_sidx);
         else if (K2_THREADS == 256 && M_all <= 512) sort_to_smem<2>(cscore, M_all, 256, s_x, s_sidx);
@@ -502,7 +514,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
             // very long lists (30k-candidate stress case): bitonic network in global memory
             int P2 = 1;
             while (P2 < M_all) P2 <<= 1;
-            unsigned long long *keys = P.sort_keys + (size_t)b * P.cap_pow2;
+            unsigned long long *keys = gslice;
             for (int i = tid; i < P2; i += K2_THREADS)
                 keys[i] = (i < M_all) ? (((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)i) : ~0ull;
             __syncthreads();
@@ -532,7 +544,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
         const int wn = min(WIN, M - w0);
         // (a) stage the window in NMS order; bucket its candidates by the cell of their centre
         for (int t = tid; t < wn; t += K2_THREADS) {
-            const int idx = gkeys ? (int)(unsigned)gkeys[w0 + t] : (int)s_sidx[w0 + t];
+            const int idx = gidx ? (int)__ldcg(gidx + w0 + t) : gkeys ? (int)(unsigned)gkeys[w0 + t] : (int)s_sidx[w0 + t];
             float4 bx = __ldg(cbox + idx);
             const int lb = __ldg(clabel + idx);
             s_sscore[t] = __ldg(cscore + idx);
@@ -576,8 +588,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                         const int lj = s_slabel[c0 + ci];
                         const int pc = s_scell[c0 + ci];
                         const int gx0 = pc & 15, gy0 = (pc >> 4) & 15, ncx = (pc >> 8) & 31, ncy = (pc >> 13) & 31;
-                        int qx = sub, qy = 0;   // cells sub, sub + A_SUBS, ... in row-major order (ncx >= 1)
-                        while (qx >= ncx) { qx -= ncx; ++qy; }
+                        // cells sub, sub + A_SUBS, ... in row-major order (1 <= ncx <= 16): row = floor(cell / ncx) from a float
+                        // product ((cell + 0.5) / ncx is at least 1/32 away from an integer; stepping qx down by ncx cost 11 %
+                        // of the kernel's instructions, r02c)
+                        const float inv_ncx = __frcp_rn((float)ncx);
+                        int cell = sub;
+                        int qy = __float2int_rz(__fmul_rn((float)cell + 0.5f, inv_ncx)), qx = cell - qy * ncx;
                         while (qy < ncy && !f) {
                             // lists are in keep order: the strongest box of a cluster comes first and usually settles it
                             for (int k = s_cellhead[(gy0 + qy) * P.gx + gx0 + qx]; k >= 0 && !f;) {
@@ -590,8 +606,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(cons
                                 f = suppresses(kb, __int_as_float(km.x), km.y, bj, aj, lj, P.thr_up, P.early_out, P.class_mode, 1,
                                                cj.x, cj.y, P.fast);
                             }
-                            qx += A_SUBS;
-                            while (qx >= ncx) { qx -= ncx; ++qy; }
+                            cell += A_SUBS;
+                            qy = __float2int_rz(__fmul_rn((float)cell + 0.5f, inv_ncx));
+                            qx = cell - qy * ncx;
                         }
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, f);
@@ -1158,6 +1175,8 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
             while (want > 0 && fixed + 8 * want > smem_a) want -= 32;
         }
         P.bucket_max = dbg_env_int("BTPOST_NMS_BUCKET", 1) ? (int)want : 0;
+        P.bucket_global = dbg_env_int("BTPOST_NMS_BUCKET_G", 1);
+        P.sort_stride = sort_stride_u64((size_t)P.cap);
     }
     if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
     // match_kernel: COCO tables

@@ -1,5 +1,5 @@
 """Developer tool: step time of the BASELINE configs that are not the bench headline (graph replays, CUDA events).
-usage: python scripts/config_timing.py dense|hires|l1|bf16"""
+usage: python scripts/config_timing.py dense|dense1024|hires|l1|bf16 [pipe]   (BTPOST_LIB picks the library build)"""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -11,6 +11,8 @@ which = sys.argv[1] if len(sys.argv) > 1 else "dense"
 dev = torch.device("cuda:0")
 if which == "dense":      # config 4: conf 0.001, every anchor a candidate, max_det 300, batch 128
     B, S, kw, l1 = 128, 640, dict(conf_thres=0.001), False
+elif which == "dense1024":  # config 4 at its stated size: 21 504 candidates / image at 1024^2, batch 128
+    B, S, kw, l1 = 128, 1024, dict(conf_thres=0.001), False
 elif which == "hires":    # config 3: 1024^2, 21504 anchors, 256^2 protos
     B, S, kw, l1 = 64, 1024, dict(), False
 elif which == "bf16":     # headline shapes with bfloat16 prototypes (what the reference's bf16-mixed forward produces)
