@@ -55,6 +55,12 @@ extern "C" __attribute__((visibility("default"))) int btpost_debug_phase_cycles(
 namespace bt {
 
 constexpr int NMS_CHUNK = 64;
+#ifndef NMS_MINB_512
+#define NMS_MINB_512 3   // CTAs per SM the 512-thread variant is compiled for (3: 40 registers, measured in profiles/r02c_summary.md)
+#endif
+#ifndef NMS_WIN_512
+#define NMS_WIN_512 1024  // sorted candidates staged per window by the 512-thread variant
+#endif
 #ifndef A_SUBS_WIDE
 #define A_SUBS_WIDE 8
 #endif
@@ -428,11 +434,11 @@ __device__ __forceinline__ bool bucket_sort(const float *cscore, int M, unsigned
 // fused NMS kernel
 // =================================================================================================
 template <int K2_THREADS>
-__global__ void __launch_bounds__(K2_THREADS, 1024 / K2_THREADS) nms_kernel(const __grid_constant__ K2Params P) {
+__global__ void __launch_bounds__(K2_THREADS, K2_THREADS == 512 ? NMS_MINB_512 : 1024 / K2_THREADS) nms_kernel(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = P.max_det;
-    constexpr int WIN = K2_TAIL_WIN;
+    constexpr int WIN = K2_THREADS == 512 ? NMS_WIN_512 : K2_TAIL_WIN;
     // phase A: threads per candidate that share the walk over the cells under its box (the walks are chains of dependent
     // shared-memory loads: more, shorter chains as long as the CTA has the threads)
     constexpr int A_SUBS = K2_THREADS >= 512 ? A_SUBS_WIDE : 4;
@@ -1156,7 +1162,7 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     const int sort_slots = P.cap_pow2 < 1024 ? 1024 : (P.cap_pow2 > sort_max ? sort_max : P.cap_pow2);
     const size_t region0 = align_up((size_t)sort_slots * 4, 16);
     P.region0_bytes = (int)region0;
-    size_t smem_a = region0 + (size_t)K2_TAIL_WIN * 48 + (size_t)p.max_det * 48 + 64;
+    size_t smem_a = region0 + (size_t)(nt == 512 ? NMS_WIN_512 : K2_TAIL_WIN) * 48 + (size_t)p.max_det * 48 + 64;
     if (smem_a < (size_t)sort_slots * 8) smem_a = (size_t)sort_slots * 8;
     {   // radix sort of short lists: two (key, index) buffers + [256][warps] counters
         const size_t mp = (size_t)(P.cap < RADIX_MAX ? (P.cap + 31) / 32 * 32 : RADIX_MAX);
