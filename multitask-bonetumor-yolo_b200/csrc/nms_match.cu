@@ -1184,7 +1184,10 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
         P.bucket_global = dbg_env_int("BTPOST_NMS_BUCKET_G", 1);
         P.sort_stride = sort_stride_u64((size_t)P.cap);
     }
-    if (smem_a > 220 * 1024) return BT_ERR_UNSUPPORTED;
+    // dynamic + static (~7 KB) shared memory of nms_kernel must stay below the 227 KB an SM offers one CTA: with 220 KB
+    // the attribute call below was within 80 bytes of failing
+    constexpr size_t NMS_SMEM_MAX = 212 * 1024;
+    if (smem_a > NMS_SMEM_MAX) return BT_ERR_UNSUPPORTED;
     // match_kernel: COCO tables
     const int coco_doubles = p.max_det * 4 + p.max_gt * 4 + p.max_det * 4;   // boxes + room for a [K x 4] IoU block
     P.coco_smem_doubles = coco_doubles;
@@ -1195,9 +1198,9 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
     int attr_dev = 0;
     if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev >= 64) return BT_ERR_CUDA;
     if (!attr_done[attr_dev]) {
-        if (cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(nms_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(nms_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+        if (cudaFuncSetAttribute(nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM_MAX) != cudaSuccess ||
+            cudaFuncSetAttribute(nms_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM_MAX) != cudaSuccess ||
+            cudaFuncSetAttribute(nms_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_SMEM_MAX) != cudaSuccess ||
             cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return BT_ERR_CUDA;
         attr_done[attr_dev] = true;
