@@ -207,7 +207,8 @@ def main():
     ap.add_argument("--conf", type=float, default=0.05)
     ap.add_argument("--iou", type=float, default=0.6)
     ap.add_argument("--max-det", dest="max_det", type=int, default=300)
-    ap.add_argument("--cpu-sample", type=int, default=4, help="images the cpu_baseline leg times (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=64,
+                    help="images the cpu_baseline leg times (0 = skip); default: one full batch, ~10-25 s of CPU work with warm-up")
     ap.add_argument("--pipeline", type=int, default=0,
                     help="batches in flight = slots with their own input set (0 = auto: 6, 5 or 4, whichever divides --steps; 2 for c2; 1 = strictly serial steps)")
     ap.add_argument("--no-e2e", action="store_true")
