@@ -11,10 +11,15 @@
 //   matching  torchmetrics MeanAveragePrecision.update -> pycocotools COCOeval.evaluateImg
 //             (configured at running_main_v2.py:228-251, evaluate_model.py:81-94)
 //
-// B200 mapping.  nms_kernel, one 1024-thread CTA per image:
-//   1. sort    64-bit (score key, index) bitonic network with the keys in REGISTERS: strides
-//              inside a thread are plain compare-exchanges, strides inside a warp are shuffles,
-//              only the widest strides go through shared memory.
+// B200 mapping.  nms_kernel, one CTA of 1024 / 512 / 256 threads per image:
+//   1. sort    bucket rank sort (bucket_sort below): one pass -- min / max of the 32-bit descending
+//              score keys, monotone map to 2048 buckets, histogram, scan, scatter of the 64-bit
+//              (key, index) pairs, exact rank inside the bucket -- in shared memory, or in the
+//              workspace for lists that do not fit.  Fallbacks for buckets of hundreds of equal
+//              scores: stable LSD radix sort, 64-bit bitonic network with the keys in REGISTERS
+//              (strides inside a thread are plain compare-exchanges, strides inside a warp are
+//              shuffles, only the widest strides go through shared memory), the same network in
+//              global memory.
 //   2. sweep   the sorted list is staged in windows of 1024 and consumed 64 at a time:
 //              (A) chunk vs KEPT boxes -- kept boxes are binned by the cell of their centre, and
 //              for IoU thresholds >= 0.55 a suppressing pair has each centre inside the other
