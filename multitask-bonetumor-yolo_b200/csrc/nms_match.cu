@@ -1157,10 +1157,10 @@ int launch_nms_match(const BtParams &p, const BtIO &io, const Workspace &w, cuda
 
     // shared memory of nms_kernel: [sorted-index list | window (48 B/candidate) + kept arrays (48 B/slot)];
     // the sort's exchange buffer overlays everything.
-    // BtParams.nms_threads = 512: 32 k registers and < 80 KB of shared memory per image leave room on the SM for CTAs of
-    // the mask kernels of other batches in flight, or for a second image (btpost.Pipeline asks for it: +8 % images/s
-    // with six batches in flight, but a single step is 11 us slower).  The 1024-thread variant (default) also sorts
-    // long candidate lists in registers; the small one falls back to the global-memory network above 4096 candidates.
+    // BtParams.nms_threads = 512: 20 k registers (40 per thread) and 80 KB of shared memory per image leave room on the
+    // SM for a second image and for CTAs of the other batches' kernels (btpost.Pipeline asks for it: 93.8 vs 98.7 us per
+    // pipelined step, profiles/r02c_nms_threads.txt).  The 1024-thread variant (default) sorts lists of up to 16 384
+    // candidates in shared memory; the small ones keep the pairs of lists above 4096 in the workspace.
     const int nt_req = p.nms_threads ? p.nms_threads : dbg_env_int("BTPOST_NMS_NT", 1024);
     const int nt = nt_req == 512 ? 512 : (nt_req == 256 ? 256 : 1024);
     const int sort_max = nt <= 512 ? SORT_SMALL_MAX : SORT_REG_MAX;
