@@ -90,7 +90,11 @@ typedef struct BtParams {
     int32_t drop_gt_no_cand;  /* 1 = v2 behaviour (running_main_v2.py:797-814): an image in which no anchor passes
                                  CONF_TH gets an EMPTY target, i.e. its GT boxes leave the mAP denominator;
                                  0 = v3 behaviour (running_main_v3.py:541-571): the target is kept             */
-    int32_t reserved[3];
+    int32_t in_flight;        /* batches the caller keeps in flight on this device (btpost.Pipeline: its depth).  0 / 1: the
+                                 persistent kernels of the mask stage size their grids for a GPU of their own (4 / 8 CTAs per
+                                 SM); >= 2: for a shared one (3 / 6: other batches' CTAs find room beside them, measured
+                                 -1.5 % per pipelined step).  Results do not depend on it.                              */
+    int32_t reserved[2];
 } BtParams;
 
 /* Device buffers.  Inputs are read-only.  Any OUTPUT pointer may be NULL to skip that output

@@ -34,7 +34,7 @@ class BtParams(C.Structure):
         ("proj_bias", C.c_float), ("num_iou_thrs", C.c_int32),
         ("iou_thrs", C.c_double * BT_MAX_IOU_THRS),
         ("image_offset", C.c_int32), ("nms_threads", C.c_int32), ("proto_dtype", C.c_int32), ("head_dtype", C.c_int32),
-        ("drop_gt_no_cand", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("drop_gt_no_cand", C.c_int32), ("in_flight", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

@@ -132,6 +132,7 @@ class PostConfig:
     with_seg_map: bool = False           # v3 segmentation-mAP prep (score numerator per image)
     num_anchors: int | None = None
     nms_threads: int = 0                 # 0 = auto; 512 / 1024 force a variant of the NMS kernel
+    in_flight: int = 0                   # batches kept in flight on the device (Pipeline sets its depth): grid sizes of the mask stage
     proto_bf16: bool = False             # prototypes arrive as torch.bfloat16 (widened exactly in the kernel)
     head_bf16: bool = False              # same for the L2 head tensor / the L1 raw maps
 
@@ -163,6 +164,7 @@ class PostProcessor:
         p.iou_match_thresh, p.crop, p.gt_mask_dtype = cfg.iou_match_thresh, int(cfg.crop), cfg.gt_mask_dtype
         p.num_iou_thrs = len(cfg.iou_thrs)
         p.nms_threads = cfg.nms_threads
+        p.in_flight = cfg.in_flight
         p.proto_dtype = _lib.PROTO_BF16 if cfg.proto_bf16 else _lib.PROTO_F32
         p.head_dtype = _lib.HEAD_BF16 if cfg.head_bf16 else _lib.HEAD_F32
         p.drop_gt_no_cand = int(cfg.drop_gt_no_cand)
@@ -367,6 +369,8 @@ class Pipeline:
             # small-footprint NMS kernel: its CTAs share SMs with the mask kernels of the other batches in flight
             # (dense candidate lists keep the 1024-thread variant, which sorts them in registers)
             cfg = dataclasses.replace(cfg, nms_threads=512)
+        if depth > 1 and cfg.in_flight == 0:
+            cfg = dataclasses.replace(cfg, in_flight=depth)   # the mask stage's persistent kernels leave room for the other batches
         if cfg.layout != _lib.LAYOUT_L2:
             raise ValueError("Pipeline takes the L2 head layout ([B, 4+nc+nm, N])")
         self.cfg, self.depth = cfg, depth

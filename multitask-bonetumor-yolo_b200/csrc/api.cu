@@ -23,6 +23,7 @@ int check_params(const BtParams *p, const BtIO *io) {
     if (p->num_gt_rows < 0) return BT_ERR_BAD_ARG;
     if (!(p->iou_thres == p->iou_thres)) return BT_ERR_BAD_ARG;
     if (p->nms_threads != 0 && p->nms_threads != 256 && p->nms_threads != 512 && p->nms_threads != 1024) return BT_ERR_BAD_ARG;
+    if (p->in_flight < 0) return BT_ERR_BAD_ARG;
     if (p->proto_dtype != BT_PROTO_F32 && p->proto_dtype != BT_PROTO_BF16) return BT_ERR_BAD_ARG;
     if (p->head_dtype != BT_HEAD_F32 && p->head_dtype != BT_HEAD_BF16) return BT_ERR_BAD_ARG;
     if (p->layout == BT_LAYOUT_L1) {

@@ -1118,7 +1118,11 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
              sm_count_dev[attr_dev] <= 0))
             return BT_ERR_CUDA;
         const int sm_count = sm_count_dev[attr_dev];
-        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * dbg_env_int("BTPOST_A_CTAS", nbuf == 1 ? 4 : nbuf == 2 ? 3 : 2);
+        // BtParams.in_flight >= 2: several batches share the GPU.  Smaller grids of the two persistent kernels (3 / 6 CTAs per
+        // SM instead of 4 / 8, which fill the register file) let the other batches' CTAs become resident beside them:
+        // 93.1 -> 91.7 us per pipelined step (profiles/r02c_ctas.txt); alone, the kernels are fastest with the full grids.
+        const bool shared_gpu = p.in_flight >= 2;
+        const int ntiles = p.batch * P.ntx * P.nty, cta_a = sm_count * dbg_env_int("BTPOST_A_CTAS", nbuf == 1 ? (shared_gpu ? 3 : 4) : nbuf == 2 ? 3 : 2);
         const int grid_a = ntiles < cta_a ? ntiles : cta_a;
         if (parts & BT_MASKS_CONTRACT) {
             if (P.proto_bf16) contract_kernel<1, 4, true><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
@@ -1130,7 +1134,7 @@ int launch_masks(const BtParams &p, const BtIO &io, const Workspace &w, cudaStre
             else contract_kernel<1, 4><<<grid_a, A_THREADS, smem_a, s>>>(P, tm);
         }
         const long long items = (long long)p.batch * (p.max_det + P.m1_items);   // grid sizing only: the kernel reads the real count
-        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * dbg_env_int("BTPOST_C_CTAS", 8);
+        const long long want = (items + C_WARPS - 1) / C_WARPS, cap = (long long)sm_count * dbg_env_int("BTPOST_C_CTAS", shared_gpu ? 6 : 8);
         if (parts & BT_MASKS_CELLS) {
             const long long ctas = want < cap ? want : cap;
             P.nq = 1;   // queues: a power of two <= warps in the grid (every queue needs a home warp), at most C_NQ

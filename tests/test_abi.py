@@ -32,15 +32,15 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "btpost.h"\nint main(){'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(BtParams), offsetof(BtParams, iou_thres),'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(BtParams), offsetof(BtParams, iou_thres),'
                    'offsetof(BtParams, iou_thrs), offsetof(BtParams, image_offset), sizeof(BtIO), offsetof(BtIO, dt_match),'
-                   'offsetof(BtParams, drop_gt_no_cand), offsetof(BtIO, inst_bits), offsetof(BtIO, sweep));return 0;}')
+                   'offsetof(BtParams, drop_gt_no_cand), offsetof(BtParams, in_flight), offsetof(BtIO, inst_bits), offsetof(BtIO, sweep));return 0;}')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(_lib.BtParams), _lib.BtParams.iou_thres.offset, _lib.BtParams.iou_thrs.offset,
             _lib.BtParams.image_offset.offset, C.sizeof(_lib.BtIO), _lib.BtIO.dt_match.offset,
-            _lib.BtParams.drop_gt_no_cand.offset, _lib.BtIO.inst_bits.offset, _lib.BtIO.sweep.offset]
+            _lib.BtParams.drop_gt_no_cand.offset, _lib.BtParams.in_flight.offset, _lib.BtIO.inst_bits.offset, _lib.BtIO.sweep.offset]
     assert got == want
 
 
