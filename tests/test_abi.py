@@ -55,6 +55,12 @@ def test_argument_validation_without_gpu():
     p.img_h = p.img_w = 640
     p.proto_h = p.proto_w = 160
     assert L.btpost_workspace_bytes(C.byref(p), C.byref(n)) == 0 and n.value > 2 * 8400 * 28
+    # the sort buffer holds the bitonic network's padded keys or the bucket sort's pairs + index list (12 B / candidate)
+    q, m = _lib.BtParams(), C.c_size_t()
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(p))
+    q.num_anchors = 16384                                                  # a power of two: pairs + indices need 1.5 x the keys
+    assert L.btpost_workspace_bytes(C.byref(q), C.byref(m)) == 0
+    assert m.value - n.value >= 2 * ((16384 - 8400) * 28 + (16384 * 12 - 16384 * 8)) - 4096   # 256-byte rounding of each buffer
     assert L.btpost_run(C.byref(p), C.byref(io), None, 0, None) == -1      # null workspace
     p.nm = 16
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -2   # unsupported nm
@@ -64,7 +70,7 @@ def test_argument_validation_without_gpu():
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(260), n.value, None) == -4   # misaligned workspace
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), 16, None) == -3        # workspace too small
     assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1   # null head
-    for field, bad in (("nms_threads", 384), ("proto_dtype", 2), ("head_dtype", 7)):          # scheduling / dtype knobs
+    for field, bad in (("nms_threads", 384), ("proto_dtype", 2), ("head_dtype", 7), ("in_flight", -1)):   # scheduling / dtype knobs
         setattr(p, field, bad)
         assert L.btpost_run(C.byref(p), C.byref(io), C.c_void_p(256), n.value, None) == -1, field
         setattr(p, field, 0)
